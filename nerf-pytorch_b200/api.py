@@ -1,0 +1,657 @@
+"""Host-side mirror of the reference's renderer interface (run_nerf.py / run_nerf_helpers.py).
+
+Same names, argument meaning and return structure as yenchenlin/nerf-pytorch, so that these
+functions can be rebound onto the reference's `run_nerf` module (see dropin.py) and `train()`
+runs unchanged -- but every tensor-op chain of the hot path is one call into the hand-written
+sm_100a library behind include/nerf_b200.h.  PyTorch is used for memory, streams and autograd
+plumbing only.  There is no CPU fallback: tensors must live on a CUDA device.
+
+Reference sites: render run_nerf.py:69-134, batchify_rays :54-66, render_rays :308-418,
+run_network :37-51, batchify :27-34, raw2outputs :262-305, create_nerf :178-259;
+Embedder/get_embedder run_nerf_helpers.py:15-63, NeRF :67-119, get_rays :153-162,
+ndc_rays :175-192, sample_pdf :196-239.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import NerfNetGrads, NerfNetParams, NerfPassOut, NerfRenderCfg, PREC_FP32, PREC_TC_FP16, check
+
+__all__ = ["NeRF", "Embedder", "get_embedder", "sample_pdf", "raw2outputs", "run_network", "batchify",
+           "batchify_rays", "render_rays", "render", "create_nerf", "get_rays", "get_rays_np", "ndc_rays",
+           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "launch_count", "DEBUG"]
+
+DEBUG = False
+_PRECISION = {"mode": PREC_TC_FP16}
+
+img2mse = lambda x, y: torch.mean((x - y) ** 2)                                    # run_nerf_helpers.py:9
+mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))   # :10
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)                          # :11
+
+
+def set_precision(mode: str):
+    """'tc_fp16' (tcgen05 fp16 operands / fp32 accumulate, default) or 'fp32' (CUDA-core exact mode)."""
+    _PRECISION["mode"] = {"tc_fp16": PREC_TC_FP16, "fp32": PREC_FP32}[mode]
+
+
+def get_precision() -> str:
+    return "tc_fp16" if _PRECISION["mode"] == PREC_TC_FP16 else "fp32"
+
+
+def launch_count() -> int:
+    return _lib.launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# small helpers
+# ------------------------------------------------------------------------------------------------
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"nerf_b200: {what} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Embedder  (run_nerf_helpers.py:15-63)
+# ------------------------------------------------------------------------------------------------
+
+class Embedder:
+    """Positional encoding [x, sin(2^k x), cos(2^k x)]_{k<L}; same kwargs as the reference's
+    Embedder, restricted to what get_embedder ever passes (include_input, log_sampling, sin/cos)."""
+
+    def __init__(self, **kwargs):
+        self.kwargs = kwargs
+        if not (kwargs.get("include_input", True) and kwargs.get("log_sampling", True) and kwargs.get("input_dims", 3) == 3):
+            raise NotImplementedError("nerf_b200 Embedder supports include_input=True, log_sampling=True, input_dims=3")
+        self.num_freqs = int(kwargs["num_freqs"])
+        if int(kwargs.get("max_freq_log2", self.num_freqs - 1)) != self.num_freqs - 1:
+            raise NotImplementedError("nerf_b200 Embedder needs max_freq_log2 == num_freqs - 1 (powers of two)")
+        self.out_dim = 3 + 6 * self.num_freqs
+
+    def embed(self, inputs: torch.Tensor) -> torch.Tensor:
+        x = _f32c(inputs, "embed input")
+        flat = x.reshape(-1, 3)
+        out = torch.empty((flat.shape[0], self.out_dim), device=x.device, dtype=torch.float32)
+        check(_lib.load().nerf_b200_embed(_ptr(flat), flat.shape[0], self.num_freqs, _ptr(out), _stream(x)), "embed")
+        return out.reshape(*x.shape[:-1], self.out_dim)
+
+
+def get_embedder(multires, i=0):
+    """run_nerf_helpers.py:48-63."""
+    if i == -1:
+        return nn.Identity(), 3
+    eo = Embedder(include_input=True, input_dims=3, max_freq_log2=multires - 1, num_freqs=multires,
+                  log_sampling=True, periodic_fns=[torch.sin, torch.cos])
+    embed = lambda x, eo=eo: eo.embed(x)
+    embed.num_freqs = multires          # lets run_network recover L without re-deriving it
+    return embed, eo.out_dim
+
+
+# ------------------------------------------------------------------------------------------------
+# NeRF module  (run_nerf_helpers.py:67-119): parameter container with the reference's state_dict keys
+# ------------------------------------------------------------------------------------------------
+
+class NeRF(nn.Module):
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False):
+        super().__init__()
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_views = input_ch, input_ch_views
+        self.skips, self.use_viewdirs, self.output_ch = skips, use_viewdirs, output_ch
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] + [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + input_ch, W)
+                                        for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        if use_viewdirs:
+            self.feature_linear = nn.Linear(W, W)
+            self.alpha_linear = nn.Linear(W, 1)
+            self.rgb_linear = nn.Linear(W // 2, 3)
+        else:
+            self.output_linear = nn.Linear(W, output_ch)
+        self._pack = None           # (key, packed fp16 weight stream) for the tensor-core path
+
+    def forward(self, x):
+        """Evaluate on ALREADY-EMBEDDED rows [M, input_ch + input_ch_views] (run_nerf_helpers.py:96-119).
+
+        Interface parity only: the renderer never calls this (the fused kernel encodes and evaluates
+        the MLP itself from ray / sample coordinates); it exists so user code that calls
+        `network_fn(embedded)` keeps working, and uses plain torch ops."""
+        input_pts, input_views = torch.split(x, [self.input_ch, self.input_ch_views], dim=-1)
+        h = input_pts
+        for i, l in enumerate(self.pts_linears):
+            h = F.relu(l(h))
+            if i in self.skips:
+                h = torch.cat([input_pts, h], -1)
+        if self.use_viewdirs:
+            alpha = self.alpha_linear(h)
+            feature = self.feature_linear(h)
+            h = torch.cat([feature, input_views], -1)
+            for l in self.views_linears:
+                h = F.relu(l(h))
+            return torch.cat([self.rgb_linear(h), alpha], -1)
+        return self.output_linear(h)
+
+    # ---- C-ABI views of the live parameter storages ------------------------------------------
+    def _check_device(self):
+        p = self.pts_linears[0].weight
+        if not p.is_cuda:
+            raise RuntimeError("nerf_b200: NeRF parameters must be on a CUDA device (no CPU fallback exists)")
+        return p.device
+
+    def net_params(self) -> NerfNetParams:
+        self._check_device()
+        if len(self.skips) > 1:
+            raise NotImplementedError("nerf_b200 supports at most one skip connection")
+        n = NerfNetParams()
+        n.D, n.W, n.input_ch = self.D, self.W, self.input_ch
+        n.input_ch_views = self.input_ch_views if self.use_viewdirs else 0
+        n.skip = self.skips[0] if len(self.skips) == 1 else -1
+        n.use_viewdirs, n.output_ch = int(self.use_viewdirs), self.output_ch
+        for i, l in enumerate(self.pts_linears):
+            if not (l.weight.is_contiguous() and l.weight.dtype == torch.float32):
+                raise RuntimeError("nerf_b200: parameters must be contiguous fp32")
+            n.pts_w[i], n.pts_b[i] = l.weight.data_ptr(), l.bias.data_ptr()
+        if self.use_viewdirs:
+            n.feature_w, n.feature_b = self.feature_linear.weight.data_ptr(), self.feature_linear.bias.data_ptr()
+            n.alpha_w, n.alpha_b = self.alpha_linear.weight.data_ptr(), self.alpha_linear.bias.data_ptr()
+            n.views_w, n.views_b = self.views_linears[0].weight.data_ptr(), self.views_linears[0].bias.data_ptr()
+            n.rgb_w, n.rgb_b = self.rgb_linear.weight.data_ptr(), self.rgb_linear.bias.data_ptr()
+        else:
+            n.output_w, n.output_b = self.output_linear.weight.data_ptr(), self.output_linear.bias.data_ptr()
+        return n
+
+    def grad_struct(self, grads: dict) -> NerfNetGrads:
+        """grads: name -> fp32 CUDA tensor shaped like the parameter (see named_parameters())."""
+        g = NerfNetGrads()
+        for i in range(self.D):
+            g.pts_w[i], g.pts_b[i] = grads[f"pts_linears.{i}.weight"].data_ptr(), grads[f"pts_linears.{i}.bias"].data_ptr()
+        if self.use_viewdirs:
+            for nm in ("feature", "alpha", "rgb"):
+                setattr(g, nm + "_w", grads[f"{nm}_linear.weight"].data_ptr())
+                setattr(g, nm + "_b", grads[f"{nm}_linear.bias"].data_ptr())
+            g.views_w, g.views_b = grads["views_linears.0.weight"].data_ptr(), grads["views_linears.0.bias"].data_ptr()
+        else:
+            g.output_w, g.output_b = grads["output_linear.weight"].data_ptr(), grads["output_linear.bias"].data_ptr()
+        return g
+
+    def packed(self):
+        """fp16 UMMA-swizzled weight stream, re-packed whenever a parameter changed in place
+        (optimizer.step bumps Parameter._version; load_state_dict / .to() change data_ptr)."""
+        dev = self._check_device()
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._pack is not None and self._pack[0] == key:
+            return self._pack[1]
+        lib = _lib.load()
+        n = self.net_params()
+        nbytes = lib.nerf_b200_packed_bytes(C.byref(n))
+        if nbytes == 0:
+            raise RuntimeError("nerf_b200: " + lib.nerf_b200_last_error().decode())
+        buf = self._pack[1] if (self._pack is not None and self._pack[1].numel() == nbytes and self._pack[1].device == dev) \
+            else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.nerf_b200_pack_weights(C.byref(n), _ptr(buf), nbytes, _stream(buf)), "pack_weights")
+        self._pack = (key, buf)
+        return buf
+
+    def load_weights_from_keras(self, weights):
+        """run_nerf_helpers.py:121-148 (import of the original TF/Keras weight list)."""
+        assert self.use_viewdirs, "Not implemented if use_viewdirs=False"
+        dev = self.pts_linears[0].weight.device
+        t = lambda a: torch.from_numpy(np.transpose(a)).to(dev)
+        for i in range(self.D):
+            self.pts_linears[i].weight.data, self.pts_linears[i].bias.data = t(weights[2 * i]), t(weights[2 * i + 1])
+        j = 2 * self.D
+        self.feature_linear.weight.data, self.feature_linear.bias.data = t(weights[j]), t(weights[j + 1])
+        self.views_linears[0].weight.data, self.views_linears[0].bias.data = t(weights[j + 2]), t(weights[j + 3])
+        self.rgb_linear.weight.data, self.rgb_linear.bias.data = t(weights[j + 4]), t(weights[j + 5])
+        self.alpha_linear.weight.data, self.alpha_linear.bias.data = t(weights[j + 6]), t(weights[j + 7])
+
+
+# ------------------------------------------------------------------------------------------------
+# ray helpers (run_nerf_helpers.py:153-192) -- per-image glue, plain torch
+# ------------------------------------------------------------------------------------------------
+
+def get_rays(H, W, K, c2w):
+    c2w = torch.as_tensor(c2w, dtype=torch.float32)
+    dev = c2w.device
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev), indexing="ij")
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
+def get_rays_np(H, W, K, c2w):
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing="xy")
+    dirs = np.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -np.ones_like(i)], -1)
+    rays_d = np.sum(dirs[..., np.newaxis, :] * c2w[:3, :3], -1)
+    rays_o = np.broadcast_to(c2w[:3, -1], np.shape(rays_d))
+    return rays_o, rays_d
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    rays_o = rays_o + t[..., None] * rays_d
+    o0 = -1. / (W / (2. * focal)) * rays_o[..., 0] / rays_o[..., 2]
+    o1 = -1. / (H / (2. * focal)) * rays_o[..., 1] / rays_o[..., 2]
+    o2 = 1. + 2. * near / rays_o[..., 2]
+    d0 = -1. / (W / (2. * focal)) * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
+    d1 = -1. / (H / (2. * focal)) * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
+    d2 = -2. * near / rays_o[..., 2]
+    return torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
+
+
+# ------------------------------------------------------------------------------------------------
+# sample_pdf  (run_nerf_helpers.py:196-239)
+# ------------------------------------------------------------------------------------------------
+
+def _draw_u(shape, det, pytest, device):
+    """The `u` of sample_pdf (run_nerf_helpers.py:204-219) -> (tensor, row_stride)."""
+    n_rows, n = shape
+    if pytest:
+        np.random.seed(0)
+        if det:
+            return torch.tensor(np.linspace(0., 1., n), dtype=torch.float32, device=device), 0
+        return torch.tensor(np.random.rand(n_rows, n), dtype=torch.float32, device=device), n
+    if det:
+        return torch.linspace(0., 1., steps=n, device=device), 0
+    return torch.rand(n_rows, n, device=device), n
+
+
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    bins, weights = _f32c(bins, "bins"), _f32c(weights, "weights")
+    lead = bins.shape[:-1]
+    B = bins.shape[-1]
+    b2, w2 = bins.reshape(-1, B), weights.reshape(-1, B - 1)
+    u, stride = _draw_u((b2.shape[0], N_samples), det, pytest, bins.device)
+    out = torch.empty((b2.shape[0], N_samples), device=bins.device, dtype=torch.float32)
+    check(_lib.load().nerf_b200_sample_pdf(_ptr(b2), _ptr(w2), _ptr(u), stride, b2.shape[0], B, N_samples,
+                                           _ptr(out), _stream(bins)), "sample_pdf")
+    return out.reshape(*lead, N_samples)
+
+
+# ------------------------------------------------------------------------------------------------
+# raw2outputs  (run_nerf.py:262-305), differentiable w.r.t. raw through rgb_map
+# ------------------------------------------------------------------------------------------------
+
+def _draw_noise(shape, std, pytest, device):
+    """sigma noise of raw2outputs (run_nerf.py:283-291); note the pytest path is uniform, the live path normal."""
+    if std > 0.:
+        if pytest:
+            np.random.seed(0)
+            return torch.tensor(np.random.rand(*shape) * std, dtype=torch.float32, device=device)
+        return torch.randn(shape, device=device) * std
+    return None
+
+
+class _Raw2Outputs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd):
+        N, S = z_vals.shape
+        dev = raw.device
+        rgb = torch.empty((N, 3), device=dev); disp = torch.empty(N, device=dev); acc = torch.empty(N, device=dev)
+        depth = torch.empty(N, device=dev); weights = torch.empty((N, S), device=dev)
+        out = NerfPassOut(_ptr(rgb), _ptr(disp), _ptr(acc), _ptr(depth), _ptr(weights), C.c_void_p(0))
+        check(_lib.load().nerf_b200_raw2outputs(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S,
+                                                int(white_bkgd), C.byref(out), _stream(raw)), "raw2outputs")
+        ctx.save_for_backward(raw, z_vals, rays_d, noise if noise is not None else torch.empty(0, device=dev))
+        ctx.white_bkgd = bool(white_bkgd)
+        ctx.mark_non_differentiable(disp, acc, weights, depth)
+        return rgb, disp, acc, weights, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, *_):
+        raw, z_vals, rays_d, noise = ctx.saved_tensors
+        noise = noise if noise.numel() else None
+        N, S = z_vals.shape
+        d_raw = torch.empty_like(raw)
+        check(_lib.load().nerf_b200_raw2outputs_bwd(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S,
+                                                    int(ctx.white_bkgd), _ptr(g_rgb.contiguous().float()), _ptr(d_raw),
+                                                    _stream(raw)), "raw2outputs_bwd")
+        return d_raw, None, None, None, None
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+    """-> rgb_map, disp_map, acc_map, weights, depth_map.  Gradient flows to `raw` through rgb_map
+    (the only output the reference's loss reads, run_nerf.py:765-772); the other outputs are
+    returned non-differentiable."""
+    raw, z_vals, rays_d = _f32c(raw, "raw"), _f32c(z_vals, "z_vals"), _f32c(rays_d, "rays_d")
+    if raw.shape[-1] != 4:
+        raw = raw[..., :4].contiguous()
+    noise = _draw_noise(tuple(z_vals.shape), float(raw_noise_std), pytest, raw.device)
+    return _Raw2Outputs.apply(raw, z_vals, rays_d, noise, white_bkgd)
+
+
+# ------------------------------------------------------------------------------------------------
+# run_network / batchify  (run_nerf.py:27-51)
+# ------------------------------------------------------------------------------------------------
+
+def batchify(fn, chunk):
+    """run_nerf.py:27-34 (kept for interface parity; the fused path needs no chunking)."""
+    if chunk is None:
+        return fn
+    def ret(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+    return ret
+
+
+def _freqs_of(embed_fn, out_dim_hint=None):
+    if embed_fn is None:
+        return 0
+    if isinstance(embed_fn, nn.Identity):
+        return 0
+    L = getattr(embed_fn, "num_freqs", None)
+    if L is None:
+        raise RuntimeError("nerf_b200.run_network needs embedders created by nerf_b200.get_embedder")
+    return int(L)
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """inputs [N,S,3] (+ viewdirs [N,3]) -> raw [N,S,4] in ONE fused kernel: encode + MLP.
+    `netchunk` is accepted and ignored ("does not affect final results", run_nerf.py:78-79)."""
+    if not isinstance(fn, NeRF):
+        raise RuntimeError("nerf_b200.run_network: network must be a nerf_b200.NeRF")
+    inputs = _f32c(inputs, "inputs")
+    N, S = int(np.prod(inputs.shape[:-2])) if inputs.dim() > 2 else 1, inputs.shape[-2]
+    pts = inputs.reshape(-1, 3)
+    vd = _f32c(viewdirs, "viewdirs").reshape(-1, 3) if viewdirs is not None else None
+    lib = _lib.load()
+    n = fn.net_params()
+    prec = _PRECISION["mode"]
+    packed = fn.packed() if prec == PREC_TC_FP16 else None
+    raw = torch.empty((N * S, 4), device=inputs.device, dtype=torch.float32)
+    ws_bytes = lib.nerf_b200_march_workspace_bytes(N, S)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=inputs.device)
+    check(lib.nerf_b200_run_network(_ptr(pts), _ptr(vd), N, S, C.byref(n), _ptr(packed), _freqs_of(embed_fn),
+                                    _freqs_of(embeddirs_fn), prec, _ptr(raw), _ptr(ws), ws_bytes, _stream(inputs)),
+          "run_network")
+    return raw.reshape(*inputs.shape[:-1], 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# render_rays  (run_nerf.py:308-418)
+# ------------------------------------------------------------------------------------------------
+
+class _QueryFn:
+    """The `network_query_fn` closure of create_nerf (run_nerf.py:201-204) as an object, so that
+    render_rays can read the encoder settings instead of calling back into Python per chunk."""
+
+    def __init__(self, embed_fn, embeddirs_fn, netchunk, multires, multires_views, i_embed):
+        self.embed_fn, self.embeddirs_fn, self.netchunk = embed_fn, embeddirs_fn, netchunk
+        self.multires = 0 if i_embed == -1 else multires
+        self.multires_views = 0 if i_embed == -1 else multires_views
+
+    def __call__(self, inputs, viewdirs, network_fn):
+        return run_network(inputs, viewdirs, network_fn, self.embed_fn, self.embeddirs_fn, self.netchunk)
+
+
+def _grad_buffers(net: NeRF):
+    return {k: torch.zeros_like(p, dtype=torch.float32) for k, p in net.named_parameters()}
+
+
+class _RenderRays(torch.autograd.Function):
+    """Forward: nerf_b200_render_rays_fwd (coarse z -> fused pass -> resample -> fused pass).
+    Backward: nerf_b200_march_bwd per pass (recompute), gradients w.r.t. rgb_map and rgb0 only --
+    exactly the terms of the reference's loss (run_nerf.py:765-772); z_samples is detached in the
+    reference (:394) so nothing flows through the resampling."""
+
+    @staticmethod
+    def forward(ctx, ray_batch, cfgd, net_c, net_f, t_rand, u_rand, noise0, noise1, *params):
+        lib = _lib.load()
+        dev = ray_batch.device
+        N = ray_batch.shape[0]
+        Sc, Ni = cfgd["N_samples"], cfgd["N_importance"]
+        Sf = Sc + Ni
+        cfg = NerfRenderCfg()
+        cfg.N_samples, cfg.N_importance = Sc, Ni
+        cfg.multires, cfg.multires_views = cfgd["multires"], cfgd["multires_views"]
+        cfg.lindisp, cfg.perturb, cfg.white_bkgd = int(cfgd["lindisp"]), int(cfgd["perturb"] > 0.), int(cfgd["white_bkgd"])
+        cfg.ray_stride, cfg.precision = ray_batch.shape[1], _PRECISION["mode"]
+        tc = cfg.precision == PREC_TC_FP16
+        pc, pf = net_c.net_params(), (net_f.net_params() if net_f is not None else None)
+        pk_c = net_c.packed() if tc else None
+        pk_f = net_f.packed() if (tc and net_f is not None) else None
+        f32 = dict(device=dev, dtype=torch.float32)
+        t_vals = torch.linspace(0., 1., steps=Sc, device=dev)                     # run_nerf.py:357
+        u_det = torch.linspace(0., 1., steps=Ni, device=dev) if Ni > 0 else None  # run_nerf_helpers.py:205
+        z_c = torch.empty((N, Sc), **f32)
+        o = {k: torch.empty(s, **f32) for k, s in (("rgb0", (N, 3)), ("disp0", (N,)), ("acc0", (N,)), ("w0", (N, Sc)))}
+        retraw, fine = cfgd["retraw"], Ni > 0
+        raw_c = torch.empty((N, Sc, 4), **f32) if ((retraw and not fine) or not tc) else None
+        out_c = NerfPassOut(_ptr(o["rgb0"]), _ptr(o["disp0"]), _ptr(o["acc0"]), C.c_void_p(0), _ptr(o["w0"]), _ptr(raw_c))
+        z_f = z_std = raw_f = None
+        out_f = None
+        if fine:
+            z_f, z_std = torch.empty((N, Sf), **f32), torch.empty((N,), **f32)
+            o.update(rgb=torch.empty((N, 3), **f32), disp=torch.empty((N,), **f32), acc=torch.empty((N,), **f32))
+            raw_f = torch.empty((N, Sf, 4), **f32) if (retraw or not tc) else None
+            out_f = NerfPassOut(_ptr(o["rgb"]), _ptr(o["disp"]), _ptr(o["acc"]), C.c_void_p(0), C.c_void_p(0), _ptr(raw_f))
+        ws_bytes = lib.nerf_b200_march_workspace_bytes(N, Sf)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.nerf_b200_render_rays_fwd(
+            _ptr(ray_batch), N, C.byref(cfg), C.byref(pc), _ptr(pk_c), C.byref(pf) if pf is not None else None, _ptr(pk_f),
+            _ptr(t_vals), _ptr(u_det), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1),
+            _ptr(z_c), C.byref(out_c), _ptr(z_f), _ptr(z_std), C.byref(out_f) if out_f is not None else None,
+            _ptr(ws), ws_bytes, _stream(ray_batch)), "render_rays_fwd")
+        ctx.cfgd, ctx.nets = cfgd, (net_c, net_f)
+        ctx.save_for_backward(ray_batch, z_c, z_f if fine else torch.empty(0, device=dev),
+                              noise0 if noise0 is not None else torch.empty(0, device=dev),
+                              noise1 if noise1 is not None else torch.empty(0, device=dev))
+        ctx.n_params_c = len(list(net_c.parameters()))
+        if fine:
+            rets = (o["rgb"], o["disp"], o["acc"], o["rgb0"], o["disp0"], o["acc0"], z_std,
+                    raw_f if retraw else torch.empty(0, device=dev))
+            ctx.mark_non_differentiable(o["disp"], o["acc"], o["disp0"], o["acc0"], z_std, rets[7])
+        else:
+            rets = (o["rgb0"], o["disp0"], o["acc0"], raw_c if retraw else torch.empty(0, device=dev))
+            ctx.mark_non_differentiable(o["disp0"], o["acc0"], rets[3])
+        return rets
+
+    @staticmethod
+    def backward(ctx, *g):
+        lib = _lib.load()
+        ray_batch, z_c, z_f, noise0, noise1 = ctx.saved_tensors
+        cfgd = ctx.cfgd
+        net_c, net_f = ctx.nets
+        fine = cfgd["N_importance"] > 0
+        N = ray_batch.shape[0]
+        cfg = NerfRenderCfg()
+        cfg.N_samples, cfg.N_importance = cfgd["N_samples"], cfgd["N_importance"]
+        cfg.multires, cfg.multires_views = cfgd["multires"], cfgd["multires_views"]
+        cfg.lindisp, cfg.perturb, cfg.white_bkgd = int(cfgd["lindisp"]), int(cfgd["perturb"] > 0.), int(cfgd["white_bkgd"])
+        cfg.ray_stride, cfg.precision = ray_batch.shape[1], _PRECISION["mode"]
+        g_fine, g_coarse = (g[0], g[3]) if fine else (None, g[0])
+        grads_c = _grad_buffers(net_c)
+        same_net = fine and (net_f is None)
+        grads_f = grads_c if same_net else (_grad_buffers(net_f) if fine else None)
+        passes = [(g_coarse, z_c, noise0, net_c, grads_c)]
+        if fine:
+            passes.append((g_fine, z_f, noise1, net_c if same_net else net_f, grads_f))
+        for g_rgb, z, noise, net, gbuf in passes:
+            if g_rgb is None:
+                continue
+            S = z.shape[1]
+            n = net.net_params()
+            gs = net.grad_struct(gbuf)
+            ws_bytes = lib.nerf_b200_march_bwd_workspace_bytes(N, S)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=z.device)
+            check(lib.nerf_b200_march_bwd(_ptr(ray_batch), _ptr(z), _ptr(noise if noise.numel() else None), N, S,
+                                          C.byref(n), _ptr(net.packed()), C.byref(cfg), _ptr(g_rgb.contiguous().float()),
+                                          C.byref(gs), _ptr(ws), ws_bytes, _stream(z)), "march_bwd")
+        out = [None] * 8
+        out += [grads_c[k] for k, _ in net_c.named_parameters()]
+        if net_f is not None:
+            out += [grads_f[k] for k, _ in net_f.named_parameters()]
+        return tuple(out)
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False):
+    """Volumetric rendering of one ray chunk; same contract as run_nerf.py:308-418.
+
+    Returns rgb_map, disp_map, acc_map, [raw], and with N_importance > 0 rgb0, disp0, acc0, z_std.
+    The reference's NaN/Inf scan (:414-416, 16 host syncs per call) is only run when DEBUG is set."""
+    ray_batch = _f32c(ray_batch, "ray_batch")
+    if not isinstance(network_fn, NeRF) or (network_fine is not None and not isinstance(network_fine, NeRF)):
+        raise RuntimeError("nerf_b200.render_rays: networks must be nerf_b200.NeRF modules")
+    N = ray_batch.shape[0]
+    dev = ray_batch.device
+    use_viewdirs = ray_batch.shape[-1] > 8
+    if use_viewdirs != bool(network_fn.use_viewdirs):
+        raise RuntimeError("ray batch / network disagree on use_viewdirs")
+    mr = getattr(network_query_fn, "multires", None)
+    if mr is None:
+        # a foreign closure: recover L from the module's input widths
+        mr, mrv = (network_fn.input_ch - 3) // 6, (network_fn.input_ch_views - 3) // 6 if use_viewdirs else 0
+    else:
+        mrv = network_query_fn.multires_views
+    if N == 0:
+        e = lambda *s: torch.empty(s, device=dev)
+        ret = {"rgb_map": e(0, 3), "disp_map": e(0), "acc_map": e(0)}
+        if retraw:
+            ret["raw"] = e(0, N_samples + N_importance, 4)
+        if N_importance > 0:
+            ret.update(rgb0=e(0, 3), disp0=e(0), acc0=e(0), z_std=e(0))
+        return ret
+    t_rand = u_rand = None
+    if perturb > 0.:                                                              # run_nerf.py:365-377
+        if pytest:
+            np.random.seed(0)
+            t_rand = torch.tensor(np.random.rand(N, N_samples), dtype=torch.float32, device=dev)
+        else:
+            t_rand = torch.rand(N, N_samples, device=dev)
+        if N_importance > 0:
+            u_rand, _ = _draw_u((N, N_importance), False, pytest, dev)           # det = (perturb == 0), :393
+    noise0 = _draw_noise((N, N_samples), float(raw_noise_std), pytest, dev)
+    noise1 = _draw_noise((N, N_samples + N_importance), float(raw_noise_std), pytest, dev) if N_importance > 0 else None
+    cfgd = dict(N_samples=int(N_samples), N_importance=int(N_importance), multires=int(mr), multires_views=int(mrv),
+                lindisp=bool(lindisp), perturb=float(perturb), white_bkgd=bool(white_bkgd), retraw=bool(retraw))
+    params = list(network_fn.parameters()) + (list(network_fine.parameters()) if network_fine is not None else [])
+    outs = _RenderRays.apply(ray_batch, cfgd, network_fn, network_fine if N_importance > 0 else None,
+                             t_rand, u_rand, noise0, noise1, *params)
+    if N_importance > 0:
+        rgb, disp, acc, rgb0, disp0, acc0, z_std, raw = outs
+        ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}
+        if retraw:
+            ret["raw"] = raw
+        ret.update(rgb0=rgb0, disp0=disp0, acc0=acc0, z_std=z_std)
+    else:
+        rgb, disp, acc, raw = outs
+        ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}
+        if retraw:
+            ret["raw"] = raw
+    if DEBUG:
+        for k in ret:
+            if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
+                print(f"! [Numerical Error] {k} contains nan or inf.")
+    return ret
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """run_nerf.py:54-66."""
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: (torch.cat(v, 0) if len(v) > 1 else v[0]) for k, v in all_ret.items()}
+
+
+def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, **kwargs):
+    """run_nerf.py:69-134: build the [N, 8|11] ray batch, render in `chunk`-ray slices, reshape."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w)
+    else:
+        rays_o, rays_d = rays
+    if use_viewdirs:
+        viewdirs = rays_d
+        if c2w_staticcam is not None:
+            rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
+        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    sh = rays_d.shape
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    rays = torch.cat([rays_o, rays_d, near, far], -1)
+    if use_viewdirs:
+        rays = torch.cat([rays, viewdirs], -1)
+    all_ret = batchify_rays(rays, chunk, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ["rgb_map", "disp_map", "acc_map"]
+    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+# ------------------------------------------------------------------------------------------------
+# create_nerf  (run_nerf.py:178-259)
+# ------------------------------------------------------------------------------------------------
+
+def create_nerf(args, device=None):
+    """Instantiate NeRF's MLP models, optimizer and render kwargs; same 5-tuple as the reference."""
+    device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+    embed_fn, input_ch = get_embedder(args.multires, args.i_embed)
+    input_ch_views, embeddirs_fn = 0, None
+    if args.use_viewdirs:
+        embeddirs_fn, input_ch_views = get_embedder(args.multires_views, args.i_embed)
+    output_ch = 5 if args.N_importance > 0 else 4
+    skips = [4]
+    model = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, output_ch=output_ch, skips=skips,
+                 input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
+    grad_vars = list(model.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, input_ch=input_ch, output_ch=output_ch,
+                          skips=skips, input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
+        grad_vars += list(model_fine.parameters())
+    network_query_fn = _QueryFn(embed_fn, embeddirs_fn, args.netchunk, args.multires, args.multires_views, args.i_embed)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    start = 0
+    basedir, expname = args.basedir, args.expname
+    if args.ft_path is not None and args.ft_path != 'None':
+        ckpts = [args.ft_path]
+    else:
+        ckpts = [os.path.join(basedir, expname, f) for f in sorted(os.listdir(os.path.join(basedir, expname))) if 'tar' in f]
+    print('Found ckpts', ckpts)
+    if len(ckpts) > 0 and not args.no_reload:
+        ckpt_path = ckpts[-1]
+        print('Reloading from', ckpt_path)
+        ckpt = torch.load(ckpt_path, map_location=device)
+        start = ckpt['global_step']
+        optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        model.load_state_dict(ckpt['network_fn_state_dict'])
+        if model_fine is not None:
+            model_fine.load_state_dict(ckpt['network_fine_state_dict'])
+    render_kwargs_train = {
+        'network_query_fn': network_query_fn, 'perturb': args.perturb, 'N_importance': args.N_importance,
+        'network_fine': model_fine, 'N_samples': args.N_samples, 'network_fn': model,
+        'use_viewdirs': args.use_viewdirs, 'white_bkgd': args.white_bkgd, 'raw_noise_std': args.raw_noise_std,
+    }
+    if args.dataset_type != 'llff' or args.no_ndc:
+        print('Not ndc!')
+        render_kwargs_train['ndc'] = False
+        render_kwargs_train['lindisp'] = args.lindisp
+    render_kwargs_test = {k: render_kwargs_train[k] for k in render_kwargs_train}
+    render_kwargs_test['perturb'] = False
+    render_kwargs_test['raw_noise_std'] = 0.
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer

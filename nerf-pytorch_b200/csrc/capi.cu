@@ -1,0 +1,318 @@
+// capi.cu -- extern "C" entry points of libnerf_b200.so (see include/nerf_b200.h).
+#include <stdarg.h>
+#include "common.cuh"
+#include "small_kernels.cuh"
+#include "mlp_simt.cuh"
+#include "fused_tc.cuh"
+
+namespace nb {
+thread_local char g_err[512] = {0};
+long long g_launches = 0;
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_tc_net(const NerfNetParams* net) {
+  NB_CHECK_ARG(net != nullptr, "net is NULL");
+  NB_CHECK_ARG(net->W == TC_W, "tensor-core path supports netwidth == 256 (got %d); use precision=FP32", net->W);
+  NB_CHECK_ARG(net->D >= 2 && net->D <= TC_MAXD, "tensor-core path supports 2 <= netdepth <= %d (got %d)", TC_MAXD, net->D);
+  NB_CHECK_ARG(net->input_ch >= 3 && net->input_ch <= 63, "input_ch must be in [3,63] (got %d)", net->input_ch);
+  NB_CHECK_ARG(net->skip < net->D - 1, "skip layer must be < D-1");
+  if (net->use_viewdirs) NB_CHECK_ARG(net->input_ch_views >= 3 && net->input_ch_views <= 63, "input_ch_views must be in [3,63]");
+  return 0;
+}
+
+static int smem_optin(const void* fn, size_t bytes) {
+  NB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+// shared launcher of the fused tcgen05 pass
+static int launch_march(const float* rays, int ray_stride, const float* z_vals, const float* pts,
+                        const float* dirs, int dir_stride, const float* noise, long long N, int S,
+                        const NerfNetParams* net, const void* packed, int L, int Lv, int white_bkgd, int do_composite,
+                        const NerfPassOut* out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (int rc = check_tc_net(net)) return rc;
+  NB_CHECK_ARG(packed != nullptr, "packed weights are NULL (call nerf_b200_pack_weights)");
+  NB_CHECK_ARG(N > 0 && S > 0, "empty ray batch must be handled by the caller (N=%lld S=%d)", N, S);
+  NB_CHECK_ARG((long long)N * S < (1ll << 40), "batch too large");
+  NB_CHECK_ARG(3 + 6 * L == net->input_ch || (L == 0 && net->input_ch == 3), "multires %d does not match input_ch %d", L, net->input_ch);
+  const PackLayout PL = make_pack_layout(*net);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  MarchParams p;
+  memset(&p, 0, sizeof(p));
+  p.rays = rays; p.ray_stride = ray_stride; p.z_vals = z_vals; p.pts = pts; p.noise = noise;
+  p.N = N; p.S = S;
+  p.chunks = pk + PL.off_chunks; p.bias = reinterpret_cast<const float*>(pk + PL.off_bias);
+  p.heads = reinterpret_cast<const float*>(pk + PL.off_heads);
+  p.D = net->D; p.skip = net->skip; p.use_viewdirs = net->use_viewdirs; p.L = L; p.IC = net->input_ch;
+  p.white_bkgd = white_bkgd; p.do_composite = do_composite;
+  if (out) p.out = *out;
+  if (net->use_viewdirs) {
+    NB_CHECK_ARG(dirs != nullptr, "viewdirs required by a use_viewdirs network");
+    NB_CHECK_ARG(workspace != nullptr && workspace_bytes >= (size_t)N * 128 * 4, "workspace too small: need %zu bytes", (size_t)N * 128 * 4);
+    NB_CHECK_ARG(3 + 6 * Lv == net->input_ch_views || (Lv == 0 && net->input_ch_views == 3), "multires_views mismatch");
+    float* vb = static_cast<float*>(workspace);
+    view_bias_kernel<<<(unsigned)N, 128, 0, st>>>(dirs, dir_stride, N, Lv, net->input_ch_views,
+                                                  reinterpret_cast<const float*>(pk + PL.off_vdir), vb);
+    NB_LAUNCH_OK("view_bias_kernel");
+    p.vb = vb;
+  }
+  // persistent grid: whole rays per CTA, balanced over the SMs
+  const int sms = num_sms();
+  long long rows = N * (long long)S;
+  long long want = (rows + TC_ST - 1) / TC_ST;
+  int grid = (int)(want < sms ? want : sms);
+  if (grid > N) grid = (int)N;
+  if (grid < 1) grid = 1;
+  p.rays_per_cta = (int)((N + grid - 1) / grid);
+  grid = (int)((N + p.rays_per_cta - 1) / p.rays_per_cta);
+  NB_CHECK_ARG((long long)p.rays_per_cta * S < (1ll << 30), "rays_per_cta * S overflows");
+  static bool optin = false;
+  if (!optin) { if (int rc = smem_optin((const void*)march_tc_kernel, SM_ALLOC)) return rc; optin = true; }
+  march_tc_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
+  NB_LAUNCH_OK("march_tc_kernel");
+  return 0;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+int nerf_b200_abi_version(void) { return NERF_B200_ABI_VERSION; }
+const char* nerf_b200_last_error(void) { return g_err; }
+int64_t nerf_b200_launch_count(void) { return g_launches; }
+
+int nerf_b200_embed(const float* x, int64_t M, int L, float* out, void* stream) {
+  NB_CHECK_ARG(x && out, "NULL pointer");
+  NB_CHECK_ARG(L >= 0 && L <= 16, "num_freqs out of range");
+  if (M == 0) return 0;
+  long long total = M * (3 + 6 * L);
+  embed_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, M, L, out);
+  NB_LAUNCH_OK("embed_kernel");
+  return 0;
+}
+
+size_t nerf_b200_packed_bytes(const NerfNetParams* net) {
+  if (!net || check_tc_net(net)) return 0;
+  return make_pack_layout(*net).total;
+}
+
+int nerf_b200_pack_weights(const NerfNetParams* net, void* packed, size_t packed_bytes, void* stream) {
+  if (int rc = check_tc_net(net)) return rc;
+  const PackLayout PL = make_pack_layout(*net);
+  NB_CHECK_ARG(packed && packed_bytes >= PL.total, "packed buffer too small (%zu < %zu)", packed_bytes, PL.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  PackJob job;
+  job.n = 0;
+  unsigned off = (unsigned)PL.off_chunks;
+  const int IC = net->input_ch, W = net->W;
+  auto add = [&](const float* src, int ld, int k0, int kvalid, int nrows) {
+    PackChunk& c = job.c[job.n++];
+    c.src = src; c.ld = ld; c.k0 = k0; c.kvalid = kvalid < 0 ? 0 : (kvalid > 32 ? 32 : kvalid); c.nrows = nrows; c.dst_off = off;
+    off += (unsigned)nrows * 64;
+  };
+  for (int l = 0; l < PL.NL; ++l) {
+    if (l == 0) { add(net->pts_w[0], IC, 0, IC, 256); add(net->pts_w[0], IC, 32, IC - 32, 256); }
+    else if (l < net->D) {
+      const bool sk = (net->skip >= 0 && l == net->skip + 1);
+      const int ld = sk ? W + IC : W, base = sk ? IC : 0;
+      if (sk) { add(net->pts_w[l], ld, 0, IC, 256); add(net->pts_w[l], ld, 32, IC - 32, 256); }    // cat([input_pts, h])
+      for (int c = 0; c < 8; ++c) add(net->pts_w[l], ld, base + 32 * c, 32, 256);
+    } else if (l == net->D) { for (int c = 0; c < 8; ++c) add(net->feature_w, W, 32 * c, 32, 256); }
+    else { for (int c = 0; c < 8; ++c) add(net->views_w, W + net->input_ch_views, 32 * c, 32, 128); }
+  }
+  NB_CHECK_ARG(job.n == PL.n_chunks && off == PL.off_chunks + PL.chunk_bytes, "internal: chunk table mismatch");
+  dim3 grid(4, job.n);
+  pack_chunks_kernel<<<grid, 256, 0, st>>>(job, static_cast<uint8_t*>(packed));
+  NB_LAUNCH_OK("pack_chunks_kernel");
+  PackTables t;
+  t.net = *net; t.off_bias = PL.off_bias; t.off_heads = PL.off_heads; t.off_vdir = PL.off_vdir;
+  pack_tables_kernel<<<8, 256, 0, st>>>(t, static_cast<uint8_t*>(packed));
+  NB_LAUNCH_OK("pack_tables_kernel");
+  return 0;
+}
+
+int nerf_b200_run_network(const float* pts, const float* viewdirs, int64_t N, int S, const NerfNetParams* net,
+                          const void* packed, int multires, int multires_views, int precision, float* raw,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  NB_CHECK_ARG(pts && raw && net, "NULL pointer");
+  if (N == 0 || S == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == NERF_B200_PREC_FP32) {
+    NB_CHECK_ARG(net->W <= SIMT_THREADS && net->W % 4 == 0, "exact path supports netwidth <= 256");
+    NB_CHECK_ARG(!net->use_viewdirs || viewdirs, "viewdirs required");
+    const long long M = N * (long long)S;
+    const size_t sm = simt_smem_bytes(*net);
+    if (int rc = smem_optin((const void*)mlp_simt_kernel, sm)) return rc;
+    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, viewdirs, 3, M, S, *net, multires, multires_views, raw);
+    NB_LAUNCH_OK("mlp_simt_kernel");
+    return 0;
+  }
+  NB_CHECK_ARG(precision == NERF_B200_PREC_TC_FP16, "unknown precision %d", precision);
+  NerfPassOut out;
+  memset(&out, 0, sizeof(out));
+  out.raw = raw;
+  return launch_march(nullptr, 0, nullptr, pts, viewdirs, 3, nullptr, N, S, net, packed, multires, multires_views, 0, 0,
+                      &out, workspace, workspace_bytes, st);
+}
+
+int nerf_b200_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int d_stride, const float* noise,
+                          int64_t N, int S, int white_bkgd, const NerfPassOut* out, void* stream) {
+  NB_CHECK_ARG(raw && z_vals && rays_d && out, "NULL pointer");
+  NB_CHECK_ARG(S >= 1, "S must be >= 1");
+  if (N == 0) return 0;
+  raw2outputs_kernel<<<cdiv(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(raw, z_vals, rays_d, d_stride, noise, N, S, white_bkgd, *out);
+  NB_LAUNCH_OK("raw2outputs_kernel");
+  return 0;
+}
+
+int nerf_b200_raw2outputs_bwd(const float* raw, const float* z_vals, const float* rays_d, int d_stride, const float* noise,
+                              int64_t N, int S, int white_bkgd, const float* g_rgb, float* d_raw, void* stream) {
+  NB_CHECK_ARG(raw && z_vals && rays_d && g_rgb && d_raw, "NULL pointer");
+  NB_CHECK_ARG(S >= 1 && S <= 1024, "S must be in [1,1024]");
+  if (N == 0) return 0;
+  const int wpb = 4;
+  const size_t sm = (size_t)wpb * 4 * S * sizeof(float);
+  if (int rc = smem_optin((const void*)raw2outputs_bwd_kernel, sm)) return rc;
+  raw2outputs_bwd_kernel<<<cdiv(N, wpb), wpb * 32, sm, (cudaStream_t)stream>>>(raw, z_vals, rays_d, d_stride, noise, N, S, white_bkgd, g_rgb, d_raw);
+  NB_LAUNCH_OK("raw2outputs_bwd_kernel");
+  return 0;
+}
+
+int nerf_b200_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_row_stride, int64_t N, int B,
+                         int n_samples, float* samples, void* stream) {
+  NB_CHECK_ARG(bins && weights && u && samples, "NULL pointer");
+  NB_CHECK_ARG(B >= 2 && B <= 2048 && n_samples >= 1, "bad B / n_samples");
+  if (N == 0) return 0;
+  const int wpb = 4;
+  const size_t sm = (size_t)wpb * 3 * B * sizeof(float);
+  if (int rc = smem_optin((const void*)sample_pdf_kernel, sm)) return rc;
+  sample_pdf_kernel<<<cdiv(N, wpb), wpb * 32, sm, (cudaStream_t)stream>>>(bins, weights, u, u_row_stride, N, B, n_samples, samples);
+  NB_LAUNCH_OK("sample_pdf_kernel");
+  return 0;
+}
+
+int nerf_b200_coarse_z(const float* rays, int ray_stride, const float* t_vals, const float* t_rand, int64_t N, int S,
+                       int lindisp, float* z_vals, void* stream) {
+  NB_CHECK_ARG(rays && t_vals && z_vals, "NULL pointer");
+  NB_CHECK_ARG(ray_stride >= 8, "ray_stride must be >= 8");
+  if (N == 0) return 0;
+  coarse_z_kernel<<<cdiv(N * S, 256), 256, 0, (cudaStream_t)stream>>>(rays, ray_stride, t_vals, t_rand, N, S, lindisp, z_vals);
+  NB_LAUNCH_OK("coarse_z_kernel");
+  return 0;
+}
+
+int nerf_b200_fine_z(const float* z_vals, const float* weights, const float* u, int64_t u_row_stride, int64_t N, int S,
+                     int n_imp, float* z_fine, float* z_samples, float* z_std, void* stream) {
+  NB_CHECK_ARG(z_vals && weights && u && z_fine, "NULL pointer");
+  NB_CHECK_ARG(S >= 3 && n_imp >= 1 && S + n_imp <= 4096, "bad S / n_imp");
+  if (N == 0) return 0;
+  int P = 1;
+  while (P < S + n_imp) P <<= 1;
+  const int wpb = 4;
+  const size_t sm = (size_t)wpb * (3 * S + P) * sizeof(float);
+  if (int rc = smem_optin((const void*)fine_z_kernel, sm)) return rc;
+  fine_z_kernel<<<cdiv(N, wpb), wpb * 32, sm, (cudaStream_t)stream>>>(z_vals, weights, u, u_row_stride, N, S, n_imp, P, z_fine, z_samples, z_std);
+  NB_LAUNCH_OK("fine_z_kernel");
+  return 0;
+}
+
+size_t nerf_b200_march_workspace_bytes(int64_t N, int S) {
+  size_t tc = (size_t)N * 128 * 4, exact = (size_t)N * S * 28;   // view-bias table | pts + raw scratch
+  return (tc > exact ? tc : exact) + 256;
+}
+
+int nerf_b200_march(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
+                    const void* packed, const NerfRenderCfg* cfg, const NerfPassOut* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  NB_CHECK_ARG(rays && z_vals && net && cfg && out, "NULL pointer");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  NB_CHECK_ARG(cfg->ray_stride >= (net->use_viewdirs ? 11 : 8), "ray_stride %d too small", cfg->ray_stride);
+  if (cfg->precision == NERF_B200_PREC_FP32) {
+    // exact mode (validation path): materialise pts -> fp32 CUDA-core MLP -> raw2outputs kernel
+    const long long M = N * (long long)S;
+    const size_t need = (size_t)M * 12 + (out->raw ? 0 : (size_t)M * 16);
+    NB_CHECK_ARG(workspace && workspace_bytes >= need, "exact-mode workspace too small: need %zu bytes", need);
+    NB_CHECK_ARG(net->W <= SIMT_THREADS && net->W % 4 == 0, "exact path supports netwidth <= 256");
+    float* pts = static_cast<float*>(workspace);
+    float* raw = out->raw ? out->raw : pts + (size_t)M * 3;
+    pts_kernel<<<cdiv(M, 256), 256, 0, st>>>(rays, cfg->ray_stride, z_vals, M, S, pts);
+    NB_LAUNCH_OK("pts_kernel");
+    const size_t sm = simt_smem_bytes(*net);
+    if (int rc = smem_optin((const void*)mlp_simt_kernel, sm)) return rc;
+    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, rays + 8, cfg->ray_stride, M, S, *net, cfg->multires, cfg->multires_views, raw);
+    NB_LAUNCH_OK("mlp_simt_kernel");
+    raw2outputs_kernel<<<cdiv(N * 32, 256), 256, 0, st>>>(raw, z_vals, rays + 3, cfg->ray_stride, noise, N, S, cfg->white_bkgd, *out);
+    NB_LAUNCH_OK("raw2outputs_kernel");
+    return 0;
+  }
+  return launch_march(rays, cfg->ray_stride, z_vals, nullptr, rays + 8, cfg->ray_stride, noise, N, S, net, packed,
+                      cfg->multires, cfg->multires_views, cfg->white_bkgd, 1, out, workspace, workspace_bytes, st);
+}
+
+int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfNetParams* net_coarse,
+                              const void* packed_coarse, const NerfNetParams* net_fine, const void* packed_fine,
+                              const float* t_vals, const float* u_det, const float* t_rand, const float* u_rand,
+                              const float* noise0, const float* noise1, float* z_coarse, const NerfPassOut* coarse,
+                              float* z_fine, float* z_std, const NerfPassOut* fine, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  NB_CHECK_ARG(rays && cfg && net_coarse && t_vals && z_coarse && coarse, "NULL pointer");
+  if (N == 0) return 0;
+  const int Sc = cfg->N_samples, Ni = cfg->N_importance;
+  NB_CHECK_ARG(Sc >= 1 && Ni >= 0, "bad sample counts");
+  NB_CHECK_ARG(!cfg->perturb || t_rand, "perturb > 0 needs t_rand");
+  // z sampling (run_nerf.py:357-379)
+  if (int rc = nerf_b200_coarse_z(rays, cfg->ray_stride, t_vals, cfg->perturb ? t_rand : nullptr, N, Sc, cfg->lindisp, z_coarse, stream)) return rc;
+  // coarse pass (:381-386)
+  if (int rc = nerf_b200_march(rays, z_coarse, noise0, N, Sc, net_coarse, packed_coarse, cfg, coarse, workspace, workspace_bytes, stream)) return rc;
+  if (Ni == 0) return 0;
+  NB_CHECK_ARG(coarse->weights && z_fine && fine, "N_importance > 0 needs coarse->weights, z_fine and fine outputs");
+  // hierarchical sampling (:392-396, :412); det <=> perturb == 0 (:393)
+  const float* u = cfg->perturb ? u_rand : u_det;
+  NB_CHECK_ARG(u != nullptr, "missing u (u_det for perturb==0, u_rand otherwise)");
+  if (int rc = nerf_b200_fine_z(z_coarse, coarse->weights, u, cfg->perturb ? Ni : 0, N, Sc, Ni, z_fine, nullptr, z_std, stream)) return rc;
+  // fine pass on all S_c + N_importance samples (:397-403); network_fine None -> coarse net (:399)
+  const NerfNetParams* nf = net_fine ? net_fine : net_coarse;
+  const void* pf = net_fine ? packed_fine : packed_coarse;
+  return nerf_b200_march(rays, z_fine, noise1, N, Sc + Ni, nf, pf, cfg, fine, workspace, workspace_bytes, stream);
+}
+
+size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S) { (void)N; (void)S; return 0; }
+int nerf_b200_march_bwd(const float*, const float*, const float*, int64_t, int, const NerfNetParams*, const void*,
+                        const NerfRenderCfg*, const float*, const NerfNetGrads*, void*, size_t, void*) {
+  return nb::set_error(-6, "nerf_b200_march_bwd: not built yet");
+}
+
+int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  NB_CHECK_ARG(A && W && out && scratch, "NULL pointer");
+  NB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 256 && (N == 128 || N == 256), "bad K/N");
+  NB_CHECK_ARG(scratch_bytes >= (size_t)N * K * 2, "scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  PackJob job;
+  job.n = 0;
+  for (int c = 0; c < K / 32; ++c) { PackChunk& pc = job.c[job.n++]; pc.src = W; pc.ld = K; pc.k0 = 32 * c; pc.kvalid = 32; pc.nrows = N; pc.dst_off = (unsigned)c * N * 64; }
+  dim3 grid(4, job.n);
+  pack_chunks_kernel<<<grid, 256, 0, st>>>(job, static_cast<uint8_t*>(scratch));
+  NB_LAUNCH_OK("pack_chunks_kernel");
+  const size_t sm = 65536 + 16384 + 256 + 1024;
+  if (int rc = smem_optin((const void*)selftest_gemm_kernel, sm)) return rc;
+  selftest_gemm_kernel<<<1, 128, sm, st>>>(A, static_cast<const uint8_t*>(scratch), K, N, out);
+  NB_LAUNCH_OK("selftest_gemm_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,581 @@
+// fused_tc.cuh -- the production path: one persistent, warp-specialised sm_100a kernel per network
+// pass that computes  pts = o + d*z  ->  positional encoding  ->  8x256 MLP (+ heads)  ->
+// alpha compositing, with the MLP as tcgen05.mma tiles (fp16 operands, fp32 accumulate in TMEM).
+//
+// Replaces run_nerf.py:381-386 / :397-403 (pts, network_query_fn, raw2outputs), i.e. run_network
+// (:37-51), batchify (:27-34), Embedder.embed (run_nerf_helpers.py:36-45) and NeRF.forward
+// (:96-119).  sigma/rgb never leave the SM unless `raw` is requested.
+//
+// CTA = 768 threads, 1 CTA / SM, persistent over a contiguous range of whole rays:
+//   warp 0      : weight producer   -- streams the pre-swizzled fp16 weight chunks (K=32 x N) from
+//                                      L2 into a 3-stage ring with cp.async.bulk (TMA engine)
+//   warp 1      : MMA issuer        -- one thread issues tcgen05.mma (M=128, N=256|128, K=16)
+//   warp 2      : TMEM allocator
+//   warps 4-19  : epilogue          -- 2 tile slots x 8 warps: tcgen05.ld -> +bias -> ReLU -> fp16 ->
+//                                      st.shared into the next layer's A operand (128B swizzle);
+//                                      heads (alpha, rgb) on CUDA cores; warp-scan compositing
+//   warps 20-23 : sampler           -- o + d*z and sin/cos encoding for the NEXT 256-row super-tile
+// Two 128-row tiles (slots A, B) run in lock-step on the same weight chunk, each with its own
+// 128x256 fp32 accumulator (2 x 256 TMEM columns): the tensor pipe works on one tile while the
+// other tile's epilogue drains its accumulator.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace nb {
+
+constexpr int TC_THREADS = 768;
+constexpr int TC_W = 256;                 // hidden width supported by the tensor-core path
+constexpr int TC_MAXD = 8;                // pts layers supported (bias table lives in smem)
+constexpr int TC_TILE = 128;              // rows per MMA tile
+constexpr int TC_ST = 256;                // rows per super-tile (two tile slots)
+constexpr int TC_NST = 3;                 // weight ring stages
+constexpr int TC_CHUNK_K = 32;            // K per weight chunk
+constexpr uint32_t TC_STAGE_BYTES = 256 * TC_CHUNK_K * 2;   // 16 KB
+
+// shared-memory map (bytes, relative to a 1024-aligned base)
+constexpr uint32_t SM_ACT = 0;                                  // 2 x 64 KB  A operand (4 K-blocks x 16 KB)
+constexpr uint32_t SM_ENC = 131072;                             // 2 x 16 KB  encoded inputs (1 K-block)
+constexpr uint32_t SM_WRING = 163840;                           // 3 x 16 KB  weight ring
+constexpr uint32_t SM_BIAS = 212992;                            // (TC_MAXD+1) x 256 fp32
+constexpr uint32_t SM_HEADS = SM_BIAS + (TC_MAXD + 1) * 1024;   // 222208: head weights, 4128 B
+constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 226336: 2 x 128 x float4 partials
+constexpr uint32_t SM_BARS = SM_PART + 4096;                    // 230432: mbarriers
+constexpr uint32_t SM_MISC = SM_BARS + 256;                     // 230688: tmem ptr, compositing carry
+constexpr uint32_t SM_TOTAL = SM_MISC + 128;                    // 230816
+constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                  // + alignment slack = 231840 <= 232448
+
+// heads region (floats): viewdirs: alpha_w[256] rgb_w[3][128] alpha_b rgb_b[3]; else output_w[4][256] output_b[4]
+constexpr int HEADS_FLOATS = 1032;
+
+// ---------------------------------------------------------------------------------------------
+// packed weight buffer
+// ---------------------------------------------------------------------------------------------
+struct PackLayout {
+  int D, skip, use_viewdirs, IC, ICV, NL;
+  int n_chunks;
+  size_t off_chunks, chunk_bytes, off_bias, off_heads, off_vdir, total;
+};
+
+__host__ __device__ inline int tc_layer_chunks(int l, int D, int skip) {
+  if (l == 0) return 2;
+  if (l < D && skip >= 0 && l == skip + 1) return 10;
+  return 8;
+}
+__host__ __device__ inline uint32_t tc_layer_chunk_bytes(int l, int D) { return (l == D + 1) ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES; }
+
+static inline PackLayout make_pack_layout(const NerfNetParams& n) {
+  PackLayout L;
+  L.D = n.D; L.skip = n.skip; L.use_viewdirs = n.use_viewdirs; L.IC = n.input_ch; L.ICV = n.input_ch_views;
+  L.NL = n.D + (n.use_viewdirs ? 2 : 0);
+  L.n_chunks = 0; L.chunk_bytes = 0;
+  for (int l = 0; l < L.NL; ++l) { int c = tc_layer_chunks(l, n.D, n.skip); L.n_chunks += c; L.chunk_bytes += (size_t)c * tc_layer_chunk_bytes(l, n.D); }
+  L.off_chunks = 1024;
+  L.off_bias = L.off_chunks + L.chunk_bytes;
+  L.off_heads = L.off_bias + (size_t)(TC_MAXD + 1) * 1024;
+  L.off_vdir = L.off_heads + HEADS_FLOATS * 4;
+  L.total = L.off_vdir + (size_t)(128 * (n.input_ch_views > 0 ? n.input_ch_views : 1) + 128) * 4;
+  L.total = (L.total + 255) & ~(size_t)255;
+  return L;
+}
+
+struct PackChunk { const float* src; int ld, k0, kvalid, nrows; unsigned dst_off; };
+constexpr int PACK_MAX_CHUNKS = 96;
+struct PackJob { PackChunk c[PACK_MAX_CHUNKS]; int n; };
+
+// one thread per 16-byte unit (8 fp16 of one row) of the swizzled chunk image
+__global__ void pack_chunks_kernel(PackJob job, uint8_t* __restrict__ dst) {
+  const int ci = blockIdx.y;
+  if (ci >= job.n) return;
+  const PackChunk c = job.c[ci];
+  int u = blockIdx.x * blockDim.x + threadIdx.x;       // unit index: row * 4 + c16
+  if (u >= c.nrows * 4) return;
+  int row = u >> 2, c16 = u & 3;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int k = c16 * 8 + j;
+    v[j] = (k < c.kvalid) ? c.src[(size_t)row * c.ld + c.k0 + k] : 0.0f;
+  }
+  uint4 o;
+  o.x = ptx::cvt_f16x2(v[0], v[1]); o.y = ptx::cvt_f16x2(v[2], v[3]);
+  o.z = ptx::cvt_f16x2(v[4], v[5]); o.w = ptx::cvt_f16x2(v[6], v[7]);
+  // SWIZZLE_64B K-major: 8-row atoms of 512 B, 16B-chunk index ^= (row%8)>>1
+  unsigned off = c.dst_off + (row >> 3) * 512 + (row & 7) * 64 + ((c16 ^ ((row & 7) >> 1)) << 4);
+  *reinterpret_cast<uint4*>(dst + off) = o;
+}
+
+struct PackTables { NerfNetParams net; size_t off_bias, off_heads, off_vdir; };
+__global__ void pack_tables_kernel(PackTables t, uint8_t* __restrict__ dst) {
+  const NerfNetParams& n = t.net;
+  float* bias = reinterpret_cast<float*>(dst + t.off_bias);
+  float* heads = reinterpret_cast<float*>(dst + t.off_heads);
+  float* vdir = reinterpret_cast<float*>(dst + t.off_vdir);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = tid; i < (TC_MAXD + 1) * 256; i += nt) {
+    int l = i >> 8, c = i & 255;
+    float v = 0.0f;
+    if (l < n.D) v = n.pts_b[l][c];
+    else if (l == n.D && n.use_viewdirs) v = n.feature_b[c];
+    bias[i] = v;
+  }
+  if (n.use_viewdirs) {
+    for (int i = tid; i < 256; i += nt) heads[i] = n.alpha_w[i];
+    for (int i = tid; i < 384; i += nt) heads[256 + i] = n.rgb_w[i];
+    if (tid == 0) { heads[640] = n.alpha_b[0]; heads[641] = n.rgb_b[0]; heads[642] = n.rgb_b[1]; heads[643] = n.rgb_b[2]; }
+    const int ICV = n.input_ch_views;
+    for (int i = tid; i < 128 * ICV; i += nt) { int j = i / ICV, c = i % ICV; vdir[i] = n.views_w[(size_t)j * (256 + ICV) + 256 + c]; }
+    for (int i = tid; i < 128; i += nt) vdir[128 * ICV + i] = n.views_b[i];
+  } else {
+    for (int i = tid; i < 1024; i += nt) heads[i] = n.output_w[i];        // first 4 rows of output_linear
+    for (int i = tid; i < 4; i += nt) heads[1024 + i] = n.output_b[i];
+  }
+}
+
+// view-direction contribution of views_linears[0], once per ray (the reference recomputes it per
+// sample through the expand at run_nerf.py:44-46):  vb[n][j] = b[j] + sum_c W[j][256+c] * enc(v_n)[c]
+__global__ void view_bias_kernel(const float* __restrict__ dirs, int dir_stride, long long N, int Lv, int ICV,
+                                 const float* __restrict__ vdir, float* __restrict__ vb) {
+  __shared__ float s_enc[64];
+  const long long n = blockIdx.x;
+  const int j = threadIdx.x;
+  if (j < ICV) {
+    float v;
+    const float* d = dirs + n * dir_stride;
+    if (j < 3) v = d[j];
+    else { int f = (j - 3) / 6, q = (j - 3) % 6; float a = __fmul_rn(d[q % 3], exp2f((float)f)); v = (q < 3) ? sinf(a) : cosf(a); }
+    s_enc[j] = v;
+  }
+  __syncthreads();
+  float acc = vdir[128 * ICV + j];
+  for (int c = 0; c < ICV; ++c) acc = fmaf(vdir[j * ICV + c], s_enc[c], acc);
+  vb[n * 128 + j] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused march kernel
+// ---------------------------------------------------------------------------------------------
+struct MarchParams {
+  const float* rays; int ray_stride;      // [N, ray_stride]  (o,d,near,far[,viewdir]) or NULL in pts mode
+  const float* z_vals;                    // [N,S]
+  const float* pts;                       // [N*S,3] (pts mode: run_network) or NULL
+  const float* noise;                     // [N,S] or NULL
+  const float* vb;                        // [N,128] view bias (use_viewdirs)
+  long long N; int S; int rays_per_cta;
+  const uint8_t* chunks; const float* bias; const float* heads;
+  int D, skip, use_viewdirs, L, IC;
+  int white_bkgd, do_composite;
+  NerfPassOut out;
+};
+
+struct CompCarry { float T, r, g, b, depth, acc; int turn; int pad; };
+
+__device__ __forceinline__ uint32_t act_row_off(int r) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128); }
+
+// Epilogue of one 32-column batch: v[32] (fp32 accumulators of one row) -> +bias -> (ReLU) -> fp16 ->
+// 4 x 16-byte stores into the 128B-swizzled K-major A tile.
+template <bool RELU>
+__device__ __forceinline__ void store_act32(const float (&x)[32], uint32_t act_base, int r, int col0) {
+  const uint32_t kb = (uint32_t)(col0 >> 6) * 16384u;
+  const int c16_0 = (col0 & 63) >> 3;
+  const uint32_t row = act_base + kb + act_row_off(r);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t h0, h1, h2, h3;
+    if (RELU) {
+      h0 = ptx::cvt_relu_f16x2(x[g * 8 + 0], x[g * 8 + 1]); h1 = ptx::cvt_relu_f16x2(x[g * 8 + 2], x[g * 8 + 3]);
+      h2 = ptx::cvt_relu_f16x2(x[g * 8 + 4], x[g * 8 + 5]); h3 = ptx::cvt_relu_f16x2(x[g * 8 + 6], x[g * 8 + 7]);
+    } else {
+      h0 = ptx::cvt_f16x2(x[g * 8 + 0], x[g * 8 + 1]); h1 = ptx::cvt_f16x2(x[g * 8 + 2], x[g * 8 + 3]);
+      h2 = ptx::cvt_f16x2(x[g * 8 + 4], x[g * 8 + 5]); h3 = ptx::cvt_f16x2(x[g * 8 + 6], x[g * 8 + 7]);
+    }
+    ptx::st_shared_v4(row + (uint32_t)(((c16_0 + g) ^ (r & 7)) << 4), h0, h1, h2, h3);
+  }
+}
+
+// segmented (per-ray) inclusive scans over one warp; `s` = lane of the segment start at or before
+// this lane inside the warp, or -1 when the segment began in an earlier warp.
+__device__ __forceinline__ float seg_scan_mul(float v, int lane, int s) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o && lane - o >= s) v *= t; }
+  return v;
+}
+__device__ __forceinline__ float seg_scan_add(float v, int lane, int s) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o && lane - o >= s) v += t; }
+  return v;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float* s_heads = reinterpret_cast<float*>(smem + SM_HEADS);
+  float4* s_part = reinterpret_cast<float4*>(smem + SM_PART);
+  volatile CompCarry* s_carry = reinterpret_cast<volatile CompCarry*>(smem + SM_MISC + 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SM_MISC);
+
+  // mbarriers
+  const uint32_t bar_wfull = sb + SM_BARS;            // [3]
+  const uint32_t bar_wempty = sb + SM_BARS + 24;      // [3]
+  const uint32_t bar_dfull = sb + SM_BARS + 48;       // [2]
+  const uint32_t bar_act = sb + SM_BARS + 64;         // [2]
+  const uint32_t bar_encfull = sb + SM_BARS + 80;
+  const uint32_t bar_encfree = sb + SM_BARS + 88;
+
+  // this CTA's rays / rows
+  const long long ray0 = (long long)blockIdx.x * p.rays_per_cta;
+  const long long ray1 = (ray0 + p.rays_per_cta < p.N) ? ray0 + p.rays_per_cta : p.N;
+  const int nrows = (ray1 > ray0) ? (int)(ray1 - ray0) * p.S : 0;
+  const int nst = (nrows + TC_ST - 1) / TC_ST;
+  const long long row_begin = ray0 * p.S;
+  const int D = p.D, NL = p.D + (p.use_viewdirs ? 2 : 0);
+  const int last_enc_layer = (p.skip >= 0 && p.skip + 1 < D) ? p.skip + 1 : 0;
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i < (TC_MAXD + 1) * 256; i += TC_THREADS) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < HEADS_FLOATS; i += TC_THREADS) s_heads[i] = p.heads[i];
+  if (threadIdx.x == 0) {
+    s_carry->T = 1.0f; s_carry->r = 0; s_carry->g = 0; s_carry->b = 0; s_carry->depth = 0; s_carry->acc = 0; s_carry->turn = 0;
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); }
+    for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 256); }
+    ptx::mbar_init(bar_encfull, 128);
+    ptx::mbar_init(bar_encfree, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int st = 0; st < nst; ++st) {
+        const uint8_t* src = p.chunks;
+        for (int l = 0; l < NL; ++l) {
+          const int nch = tc_layer_chunks(l, D, p.skip);
+          const uint32_t cb = tc_layer_chunk_bytes(l, D);
+          for (int c = 0; c < nch; ++c, ++it) {
+            const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
+            ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
+            ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
+            ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
+            src += cb;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t it = 0, actph0 = 0, actph1 = 0;
+      for (int st = 0; st < nst; ++st) {
+        ptx::mbar_wait(bar_encfull, st & 1);
+        ptx::tc_fence_after();
+        for (int l = 0; l < NL; ++l) {
+          const int nch = tc_layer_chunks(l, D, p.skip);
+          const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
+          const int Nn = (l == D + 1) ? 128 : 256;
+          const uint32_t idesc = ptx::umma_idesc_f16(128, Nn);
+          for (int c = 0; c < nch; ++c, ++it) {
+            const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
+            ptx::mbar_wait(bar_wfull + 8 * stage, ph);
+            ptx::tc_fence_after();
+            const bool is_enc = (l == 0) || (skip_layer && c < 2);
+            const int kc = skip_layer ? c - 2 : c;
+            const uint32_t b_base = sb + SM_WRING + stage * TC_STAGE_BYTES;
+#pragma unroll
+            for (int X = 0; X < 2; ++X) {
+              if (c == 0) {
+                uint32_t& aph = X ? actph1 : actph0;
+                ptx::mbar_wait(bar_act + 8 * X, aph);
+                aph ^= 1;
+                ptx::tc_fence_after();
+              }
+              const uint32_t a_base = is_enc ? (sb + SM_ENC + X * 16384 + c * 64)
+                                             : (sb + SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                ptx::mma_f16_ss(tmem + X * 256, ptx::umma_desc(a_base + j * 32, 1024, ptx::UMMA_SW128),
+                                ptx::umma_desc(b_base + j * 32, 512, ptx::UMMA_SW64), idesc, (c > 0 || j > 0) ? 1u : 0u);
+              }
+              if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
+            }
+            ptx::mma_commit(bar_wempty + 8 * stage);
+            if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 20) {
+    // =========================== epilogue ===========================
+    const int X = (warp - 4) >> 3, e = (warp - 4) & 7, q = e & 3, ch = e >> 2;
+    const int r = 32 * q + lane;                                  // tile row == TMEM lane
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + X * 256;
+    const uint32_t act_base = sb + SM_ACT + X * 65536;
+    ptx::mbar_arrive(bar_act + 8 * X);                            // accumulator initially free
+    uint32_t dph = 0;
+    for (int st = 0; st < nst; ++st) {
+      float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f, hp3 = 0.f;           // head partial sums of this thread's columns
+      const int lr = st * TC_ST + X * TC_TILE + r;                // row index inside this CTA's range
+      const bool valid = lr < nrows;
+      const int rl = (valid ? lr : nrows - 1) / p.S;              // local ray
+      const long long n_ray = ray0 + rl;
+      for (int l = 0; l < NL; ++l) {
+        ptx::mbar_wait(bar_dfull + 8 * X, dph);
+        dph ^= 1;
+        ptx::tc_fence_after();
+        if (l <= D) {
+          // pts layer (ReLU) or feature layer (no activation): 128 columns per warp
+          const bool last_pts = (l == D - 1);
+          const bool write_act = !(last_pts && !p.use_viewdirs);
+#pragma unroll 1
+          for (int b = 0; b < 4; ++b) {
+            const int col0 = ch * 128 + b * 32;
+            uint32_t v[32];
+            ptx::tmem_ld_x32(t_lane + col0, v);
+            ptx::tmem_ld_wait();
+            float x[32];
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + l * 256 + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 bb = b4[j];
+              x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+              x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+            }
+            if (last_pts) {
+              if (p.use_viewdirs) {                               // alpha_linear (run_nerf_helpers.py:106)
+                const float4* w4 = reinterpret_cast<const float4*>(s_heads + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float4 w = w4[j];
+                  hp3 = fmaf(fmaxf(x[4 * j + 0], 0.f), w.x, hp3); hp3 = fmaf(fmaxf(x[4 * j + 1], 0.f), w.y, hp3);
+                  hp3 = fmaf(fmaxf(x[4 * j + 2], 0.f), w.z, hp3); hp3 = fmaf(fmaxf(x[4 * j + 3], 0.f), w.w, hp3);
+                }
+              } else {                                            // output_linear (:117)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float h = fmaxf(x[j], 0.f);
+                  hp0 = fmaf(h, s_heads[col0 + j], hp0); hp1 = fmaf(h, s_heads[256 + col0 + j], hp1);
+                  hp2 = fmaf(h, s_heads[512 + col0 + j], hp2); hp3 = fmaf(h, s_heads[768 + col0 + j], hp3);
+                }
+              }
+            }
+            if (write_act) {
+              if (l < D) store_act32<true>(x, act_base, r, col0);
+              else store_act32<false>(x, act_base, r, col0);
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(bar_act + 8 * X);
+        } else {
+          // views_linears[0] (N=128): 64 columns per warp; + per-ray view bias, ReLU, rgb_linear
+          const float* vbrow = p.vb + n_ray * 128;
+#pragma unroll 1
+          for (int b = 0; b < 2; ++b) {
+            const int col0 = ch * 64 + b * 32;
+            uint32_t v[32];
+            ptx::tmem_ld_x32(t_lane + col0, v);
+            ptx::tmem_ld_wait();
+            const float4* vb4 = reinterpret_cast<const float4*>(vbrow + col0);
+            const float* w0 = s_heads + 256 + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 bb = vb4[j];
+              float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
+              float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
+              float4 wr = *reinterpret_cast<const float4*>(w0 + 4 * j);
+              float4 wg = *reinterpret_cast<const float4*>(w0 + 128 + 4 * j);
+              float4 wb = *reinterpret_cast<const float4*>(w0 + 256 + 4 * j);
+              hp0 = fmaf(h0, wr.x, hp0); hp0 = fmaf(h1, wr.y, hp0); hp0 = fmaf(h2, wr.z, hp0); hp0 = fmaf(h3, wr.w, hp0);
+              hp1 = fmaf(h0, wg.x, hp1); hp1 = fmaf(h1, wg.y, hp1); hp1 = fmaf(h2, wg.z, hp1); hp1 = fmaf(h3, wg.w, hp1);
+              hp2 = fmaf(h0, wb.x, hp2); hp2 = fmaf(h1, wb.y, hp2); hp2 = fmaf(h2, wb.z, hp2); hp2 = fmaf(h3, wb.w, hp2);
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar_act + 8 * X);
+        }
+      }
+      // ---- heads: combine the two column halves, then raw -> compositing (ch == 0 warps) ----
+      if (ch == 1) s_part[X * 128 + r] = make_float4(hp0, hp1, hp2, hp3);
+      ptx::named_bar_sync(1 + X, 256);
+      if (ch == 0) {
+        const float4 o = s_part[X * 128 + r];
+        float4 raw4;
+        if (p.use_viewdirs) raw4 = make_float4(hp0 + o.x + s_heads[641], hp1 + o.y + s_heads[642], hp2 + o.z + s_heads[643], hp3 + o.w + s_heads[640]);
+        else raw4 = make_float4(hp0 + o.x + s_heads[1024], hp1 + o.y + s_heads[1025], hp2 + o.z + s_heads[1026], hp3 + o.w + s_heads[1027]);
+        const long long m = row_begin + lr;
+        if (valid && p.out.raw) reinterpret_cast<float4*>(p.out.raw)[m] = raw4;
+        if (p.do_composite) {
+          const int k = lr - rl * p.S;
+          float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, z = 0.f;
+          if (valid) {
+            const float* rd = p.rays + n_ray * p.ray_stride + 3;
+            const float norm = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);         // run_nerf.py:280
+            z = p.z_vals[m];
+            float dist = (k == p.S - 1) ? 1e10f : __fsub_rn(p.z_vals[m + 1], z);             // :277-278
+            dist = __fmul_rn(dist, norm);
+            const float s = raw4.w + (p.noise ? p.noise[m] : 0.0f);
+            alpha = __fsub_rn(1.0f, expf(-fmaxf(s, 0.0f) * dist));                            // :275
+            cr = sigmoidf_acc(raw4.x); cg = sigmoidf_acc(raw4.y); cb = sigmoidf_acc(raw4.z); // :282
+          }
+          const bool seg_start = valid && (k == 0), seg_end = valid && (k == p.S - 1);
+          const unsigned smask = __ballot_sync(0xffffffffu, seg_start);
+          const unsigned below = smask & ((lane == 31) ? 0xffffffffu : ((2u << lane) - 1u));
+          const int s = below ? (31 - __clz(below)) : -1;
+          const float qv = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;         // :295
+          const float pv = seg_scan_mul(qv, lane, s);
+          float ev = __shfl_up_sync(0xffffffffu, pv, 1);
+          if (lane == 0) ev = 1.0f;
+          // take the compositing turn: rows are consumed in order across warps / slots / super-tiles
+          const int ticket = (st * 2 + X) * 4 + q;
+          if (lane == 0) { while (s_carry->turn != ticket) { } }
+          __syncwarp();
+          const float Tin = s_carry->T;
+          const float c_r = s_carry->r, c_g = s_carry->g, c_b = s_carry->b, c_d = s_carry->depth, c_a = s_carry->acc;
+          const float T = (s == lane) ? 1.0f : ((s >= 0) ? ev : Tin * ev);
+          const float w = valid ? alpha * T : 0.0f;
+          float t_r = seg_scan_add(w * cr, lane, s), t_g = seg_scan_add(w * cg, lane, s), t_b = seg_scan_add(w * cb, lane, s);
+          float t_d = seg_scan_add(w * z, lane, s), t_a = seg_scan_add(w, lane, s);
+          if (s < 0) { t_r += c_r; t_g += c_g; t_b += c_b; t_d += c_d; t_a += c_a; }
+          if (valid && p.out.weights) p.out.weights[m] = w;
+          if (seg_end) {
+            float rr = t_r, gg = t_g, bb = t_b;
+            if (p.white_bkgd) { const float bg = 1.0f - t_a; rr += bg; gg += bg; bb += bg; }  // :302-303
+            if (p.out.rgb_map) { p.out.rgb_map[n_ray * 3] = rr; p.out.rgb_map[n_ray * 3 + 1] = gg; p.out.rgb_map[n_ray * 3 + 2] = bb; }
+            if (p.out.disp_map) {
+              const float ratio = t_d / t_a;
+              const float mm = (ratio != ratio) ? ratio : fmaxf(1e-10f, ratio);              // :299
+              p.out.disp_map[n_ray] = 1.0f / mm;
+            }
+            if (p.out.acc_map) p.out.acc_map[n_ray] = t_a;
+            if (p.out.depth_map) p.out.depth_map[n_ray] = t_d;
+          }
+          __syncwarp();
+          if (lane == 31) {
+            if (seg_end) { s_carry->T = 1.0f; s_carry->r = 0; s_carry->g = 0; s_carry->b = 0; s_carry->depth = 0; s_carry->acc = 0; }
+            else {
+              s_carry->T = (s >= 0) ? pv : Tin * pv;
+              s_carry->r = t_r; s_carry->g = t_g; s_carry->b = t_b; s_carry->depth = t_d; s_carry->acc = t_a;
+            }
+            __threadfence_block();
+            s_carry->turn = ticket + 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 20) {
+    // =========================== sampler ===========================
+    const int t = threadIdx.x - 640;                              // 0..127: tile row
+    for (int st = 0; st < nst; ++st) {
+      ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
+#pragma unroll 1
+      for (int X = 0; X < 2; ++X) {
+        const int lr = st * TC_ST + X * TC_TILE + t;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (lr < nrows) {
+          const long long m = row_begin + lr;
+          if (p.pts) { px = p.pts[m * 3]; py = p.pts[m * 3 + 1]; pz = p.pts[m * 3 + 2]; }
+          else {
+            const float* ry = p.rays + (ray0 + lr / p.S) * p.ray_stride;
+            const float z = p.z_vals[m];
+            px = __fadd_rn(ry[0], __fmul_rn(ry[3], z));                                       // run_nerf.py:381
+            py = __fadd_rn(ry[1], __fmul_rn(ry[4], z));
+            pz = __fadd_rn(ry[2], __fmul_rn(ry[5], z));
+          }
+        }
+        // 64 encoded channels (63 + zero pad), one fp16 store each into the 128B-swizzled K-block
+        const uint32_t row = sb + SM_ENC + X * 16384 + act_row_off(t);
+        auto put = [&](int c, float v) {
+          const uint32_t a = row + (uint32_t)((((c >> 3) ^ (t & 7)) << 4) + ((c & 7) << 1));
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
+        };
+        put(0, px); put(1, py); put(2, pz);
+#pragma unroll 1
+        for (int f = 0; f < 10; ++f) {
+          float s0 = 0.f, c0 = 0.f, s1 = 0.f, c1 = 0.f, s2 = 0.f, c2 = 0.f;
+          if (f < p.L) {
+            const float sc = (float)(1 << f);
+            sincosf(px * sc, &s0, &c0); sincosf(py * sc, &s1, &c1); sincosf(pz * sc, &s2, &c2);
+          }
+          const int c = 3 + 6 * f;
+          put(c + 0, s0); put(c + 1, s1); put(c + 2, s2); put(c + 3, c0); put(c + 4, c1); put(c + 5, c2);
+        }
+        put(63, 0.f);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(bar_encfull);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-test GEMM: out[128,N] = A[128,K] * W[N,K]^T through exactly the operand layouts, descriptors,
+// bulk copies and TMEM loads the march kernel uses (fp16 operands, fp32 accumulate).  1 CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ chunks,
+                                                             int K, int N, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
+  const uint32_t ACT = 0, WST = 65536, BAR = 65536 + 16384, TPTR = BAR + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TPTR);
+  if (threadIdx.x == 0) { ptx::mbar_init(sb + BAR, 1); ptx::mbar_init(sb + BAR + 8, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 256); ptx::tmem_relinquish(); }
+  // A -> fp16, 128B-swizzled K-major (thread r owns row r), K padded to a multiple of 32 by the caller
+  for (int c0 = 0; c0 < K; c0 += 32) {
+    float x[32];
+    for (int j = 0; j < 32; ++j) x[j] = A[(size_t)r * K + c0 + j];
+    store_act32<false>(x, sb + ACT, r, c0);
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t cb = (uint32_t)N * 64;
+    const uint32_t idesc = ptx::umma_idesc_f16(128, N);
+    for (int c = 0; c < K / 32; ++c) {
+      ptx::mbar_arrive_expect_tx(sb + BAR, cb);
+      ptx::bulk_g2s(sb + WST, chunks + (size_t)c * cb, cb, sb + BAR);
+      ptx::mbar_wait(sb + BAR, c & 1);
+      ptx::tc_fence_after();
+      const uint32_t a_base = sb + ACT + (c >> 1) * 16384 + (c & 1) * 64;
+      for (int j = 0; j < 2; ++j)
+        ptx::mma_f16_ss(tmem, ptx::umma_desc(a_base + j * 32, 1024, ptx::UMMA_SW128),
+                        ptx::umma_desc(sb + WST + j * 32, 512, ptx::UMMA_SW64), idesc, (c > 0 || j > 0) ? 1u : 0u);
+      ptx::mma_commit(sb + BAR + 8);
+      ptx::mbar_wait(sb + BAR + 8, c & 1);       // serialise: the single weight stage is reused
+    }
+  }
+  __syncthreads();
+  ptx::tc_fence_after();
+  for (int col0 = 0; col0 < N; col0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld_x32(tmem + ((uint32_t)(32 * warp) << 16) + col0, v);
+    ptx::tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(size_t)r * N + col0 + j] = __uint_as_float(v[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace nb

@@ -1,0 +1,305 @@
+// small_kernels.cuh -- the exactly-checkable per-ray kernels of the NeRF hot path:
+//   Embedder.embed, coarse z sampling, raw2outputs (+adjoint), sample_pdf, hierarchical z merge.
+// All fp32, one warp per ray where a ray-wide scan is needed.  Non-fused mul/add intrinsics are
+// used where the reference rounds twice (torch evaluates a*b+c as two ops), so z values and
+// sample positions agree with the reference to the last bit wherever the op order allows.
+#pragma once
+#include "common.cuh"
+
+namespace nb {
+
+// ---------------------------------------------------------------------------------------------
+// Embedder.embed  (run_nerf_helpers.py:36-45): out[m] = [x, sin(2^0 x), cos(2^0 x), ...]
+// ---------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const float* __restrict__ x, long long M, int L, float* __restrict__ out) {
+  const int C = 3 + 6 * L;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  long long m = i / C;
+  int c = (int)(i - m * C);
+  float v;
+  if (c < 3) {
+    v = x[m * 3 + c];
+  } else {
+    int f = (c - 3) / 6, r = (c - 3) % 6;
+    float a = __fmul_rn(x[m * 3 + (r % 3)], exp2f((float)f));   // exact power-of-two scaling (:32)
+    v = (r < 3) ? sinf(a) : cosf(a);
+  }
+  out[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarse z sampling  (run_nerf.py:357-379)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float coarse_z_at(float near, float far, float t, int lindisp) {
+  float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));                   // :359
+  float a = __fmul_rn(__fdiv_rn(1.0f, near), omt), b = __fmul_rn(__fdiv_rn(1.0f, far), t);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));                                                    // :361
+}
+
+__global__ void coarse_z_kernel(const float* __restrict__ rays, int ray_stride,
+                                const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                                long long N, int S, int lindisp, float* __restrict__ z_out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * S) return;
+  long long n = i / S;
+  int s = (int)(i - n * S);
+  float near = rays[n * ray_stride + 6], far = rays[n * ray_stride + 7];
+  float z = coarse_z_at(near, far, t_vals[s], lindisp);
+  if (t_rand != nullptr) {
+    float zl = (s > 0) ? coarse_z_at(near, far, t_vals[s - 1], lindisp) : z;
+    float zu = (s < S - 1) ? coarse_z_at(near, far, t_vals[s + 1], lindisp) : z;
+    float lower = (s > 0) ? __fmul_rn(0.5f, __fadd_rn(z, zl)) : z;                           // :367-369
+    float upper = (s < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zu, z)) : z;
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[i]));                      // :379
+  }
+  z_out[i] = z;
+}
+
+// pts = rays_o + rays_d * z  (run_nerf.py:381), exact-mode helper
+__global__ void pts_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z_vals,
+                           long long M, int S, float* __restrict__ pts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float* r = rays + (i / S) * ray_stride;
+  const float z = z_vals[i];
+  pts[i * 3 + 0] = __fadd_rn(r[0], __fmul_rn(r[3], z));
+  pts[i * 3 + 1] = __fadd_rn(r[1], __fmul_rn(r[4], z));
+  pts[i * 3 + 2] = __fadd_rn(r[2], __fmul_rn(r[5], z));
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw2outputs  (run_nerf.py:262-305), one warp per ray
+// ---------------------------------------------------------------------------------------------
+struct CompositeAcc { float r, g, b, depth, acc, T; };
+
+// Composite up to 32 consecutive samples held one per lane; carries transmittance in `a.T`.
+__device__ __forceinline__ float composite_chunk(float alpha, float cr, float cg, float cb, float z,
+                                                 bool valid, int lane, CompositeAcc& a) {
+  float q = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;                         // :295
+  float incl = warp_scan_mul(q, lane);
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.0f;
+  float T = a.T * excl;
+  float w = valid ? alpha * T : 0.0f;
+  a.r += w * cr; a.g += w * cg; a.b += w * cb; a.depth += w * z; a.acc += w;
+  a.T *= __shfl_sync(0xffffffffu, incl, 31);
+  return w;
+}
+
+__device__ __forceinline__ float disp_from(float depth, float acc) {
+  float ratio = depth / acc;                                   // 0/0 -> NaN, like the reference
+  float m = (ratio != ratio) ? ratio : fmaxf(1e-10f, ratio);   // torch.max propagates NaN (:299)
+  return 1.0f / m;
+}
+
+__global__ void raw2outputs_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                   const float* __restrict__ rays_d, int d_stride,
+                                   const float* __restrict__ noise, long long N, int S, int white_bkgd,
+                                   NerfPassOut out) {
+  const int lane = threadIdx.x & 31;
+  long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const float dx = rays_d[n * d_stride], dy = rays_d[n * d_stride + 1], dz = rays_d[n * d_stride + 2];
+  const float norm = sqrtf(dx * dx + dy * dy + dz * dz);                                      // :280
+  CompositeAcc a = {0, 0, 0, 0, 0, 1.0f};
+  for (int base = 0; base < S; base += 32) {
+    int k = base + lane;
+    bool valid = k < S;
+    float alpha = 0, cr = 0, cg = 0, cb = 0, z = 0;
+    if (valid) {
+      float4 r4 = reinterpret_cast<const float4*>(raw)[n * S + k];
+      z = z_vals[n * S + k];
+      float dist = (k == S - 1) ? 1e10f : __fsub_rn(z_vals[n * S + k + 1], z);               // :277-278
+      dist = __fmul_rn(dist, norm);
+      float s = r4.w + (noise ? noise[n * S + k] : 0.0f);
+      alpha = __fsub_rn(1.0f, expf(-fmaxf(s, 0.0f) * dist));                                  // :275
+      cr = sigmoidf_acc(r4.x); cg = sigmoidf_acc(r4.y); cb = sigmoidf_acc(r4.z);             // :282
+    }
+    float w = composite_chunk(alpha, cr, cg, cb, z, valid, lane, a);
+    if (valid && out.weights) out.weights[n * S + k] = w;
+  }
+  float r = warp_sum(a.r), g = warp_sum(a.g), b = warp_sum(a.b);
+  float depth = warp_sum(a.depth), acc = warp_sum(a.acc);
+  if (lane == 0) {
+    if (white_bkgd) { float bg = 1.0f - acc; r += bg; g += bg; b += bg; }                      // :302-303
+    if (out.rgb_map) { out.rgb_map[n * 3] = r; out.rgb_map[n * 3 + 1] = g; out.rgb_map[n * 3 + 2] = b; }
+    if (out.disp_map) out.disp_map[n] = disp_from(depth, acc);
+    if (out.acc_map) out.acc_map[n] = acc;
+    if (out.depth_map) out.depth_map[n] = depth;
+  }
+}
+
+// Adjoint of raw2outputs w.r.t. raw, given g = dL/drgb_map.  One warp per ray,
+// per-warp scratch of 4*S floats in dynamic shared memory.
+__global__ void raw2outputs_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                       const float* __restrict__ rays_d, int d_stride,
+                                       const float* __restrict__ noise, long long N, int S, int white_bkgd,
+                                       const float* __restrict__ g_rgb, float* __restrict__ d_raw) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  float* sT = smem + (size_t)wib * 4 * S;      // T_k e_k
+  float* sWE = sT + S;                         // w_k e_k
+  float* sQ = sWE + S;                         // q_k
+  float* sF = sQ + S;                          // dist * (1-alpha) * [s>0]
+  const float dx = rays_d[n * d_stride], dy = rays_d[n * d_stride + 1], dz = rays_d[n * d_stride + 2];
+  const float norm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float gr = g_rgb[n * 3], gg = g_rgb[n * 3 + 1], gb = g_rgb[n * 3 + 2];
+  float carryT = 1.0f;
+  for (int base = 0; base < S; base += 32) {
+    int k = base + lane;
+    bool valid = k < S;
+    float q = 1.0f, alpha = 0, e = 0, f = 0, cr = 0, cg = 0, cb = 0;
+    if (valid) {
+      float4 r4 = reinterpret_cast<const float4*>(raw)[n * S + k];
+      float z = z_vals[n * S + k];
+      float dist = (k == S - 1) ? 1e10f : __fsub_rn(z_vals[n * S + k + 1], z);
+      dist = __fmul_rn(dist, norm);
+      float s = r4.w + (noise ? noise[n * S + k] : 0.0f);
+      float oma = expf(-fmaxf(s, 0.0f) * dist);
+      alpha = __fsub_rn(1.0f, oma);
+      q = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      cr = sigmoidf_acc(r4.x); cg = sigmoidf_acc(r4.y); cb = sigmoidf_acc(r4.z);
+      float off = white_bkgd ? 1.0f : 0.0f;
+      e = gr * (cr - off) + gg * (cg - off) + gb * (cb - off);
+      f = (s > 0.0f) ? dist * oma : 0.0f;
+    }
+    float incl = warp_scan_mul(q, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    float T = carryT * excl;
+    carryT *= __shfl_sync(0xffffffffu, incl, 31);
+    if (valid) {
+      float w = alpha * T;
+      sT[k] = T * e; sWE[k] = w * e; sQ[k] = q; sF[k] = f;   // sT holds the first term of dL/dalpha
+      float* o = d_raw + (n * S + k) * 4;
+      o[0] = w * gr * cr * (1.0f - cr);
+      o[1] = w * gg * cg * (1.0f - cg);
+      o[2] = w * gb * cb * (1.0f - cb);
+    }
+  }
+  __syncwarp();
+  // reverse pass: suffix_k = sum_{j>k} w_j e_j
+  float carry = 0.0f;
+  const int nchunks = (S + 31) / 32;
+  for (int c = nchunks - 1; c >= 0; --c) {
+    int k = c * 32 + (31 - lane);                     // lane 0 holds the last sample of the chunk
+    bool valid = k < S;
+    float we = valid ? sWE[k] : 0.0f;
+    float incl = warp_scan_add(we, lane);             // sum of we over samples >= k within the chunk
+    float suffix = carry + incl - we;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+    if (valid) {
+      float* o = d_raw + (n * S + k) * 4;
+      float dalpha = sT[k] - suffix / sQ[k];
+      o[3] = dalpha * sF[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample_pdf  (run_nerf_helpers.py:196-239) on per-warp shared-memory rows
+// ---------------------------------------------------------------------------------------------
+// s_bins[B], s_w[B-1] in; s_cdf[B] scratch.  Writes n_samples values through `emit(j, value)`.
+template <class Emit>
+__device__ __forceinline__ void sample_pdf_row(const float* s_bins, const float* s_w, float* s_cdf, int B,
+                                               const float* __restrict__ u_row, int n_samples, int lane,
+                                               Emit emit) {
+  float part = 0.0f;
+  for (int i = lane; i < B - 1; i += 32) part += __fadd_rn(s_w[i], 1e-5f);                    // :198
+  const float total = warp_sum(part);                                                         // :199
+  if (lane == 0) {                                  // sequential cumsum, like torch/numpy (:200-201)
+    float c = 0.0f;
+    s_cdf[0] = 0.0f;
+    for (int i = 0; i < B - 1; ++i) { c = __fadd_rn(c, __fdiv_rn(__fadd_rn(s_w[i], 1e-5f), total)); s_cdf[i + 1] = c; }
+  }
+  __syncwarp();
+  for (int j = lane; j < n_samples; j += 32) {
+    const float u = u_row[j];
+    int lo = 0, hi = B;                               // first index with cdf > u  (right=True, :223)
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (s_cdf[mid] > u) hi = mid; else lo = mid + 1; }
+    const int below = max(0, lo - 1), above = min(B - 1, lo);                                 // :224-225
+    const float c0 = s_cdf[below], c1 = s_cdf[above], b0 = s_bins[below], b1 = s_bins[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < 1e-5f) denom = 1.0f;                                                          // :235
+    const float t = __fdiv_rn(__fsub_rn(u, c0), denom);                                       // :236
+    emit(j, __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0))));                                  // :237
+  }
+  __syncwarp();
+}
+
+__global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                  const float* __restrict__ u, long long u_row_stride, long long N, int B,
+                                  int n_samples, float* __restrict__ samples) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  float* s_bins = smem + (size_t)wib * 3 * B;
+  float* s_w = s_bins + B;
+  float* s_cdf = s_w + B;
+  for (int i = lane; i < B; i += 32) s_bins[i] = bins[n * B + i];
+  for (int i = lane; i < B - 1; i += 32) s_w[i] = weights[n * (B - 1) + i];
+  __syncwarp();
+  float* o = samples + n * n_samples;
+  sample_pdf_row(s_bins, s_w, s_cdf, B, u + n * u_row_stride, n_samples, lane,
+                 [&](int j, float v) { o[j] = v; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// hierarchical resampling of render_rays (run_nerf.py:392-396, :412): z_mid, sample_pdf on
+// weights[1:-1], sort(cat[z, z_samples]), std(z_samples).  One warp per ray.
+// ---------------------------------------------------------------------------------------------
+__global__ void fine_z_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights,
+                              const float* __restrict__ u, long long u_row_stride, long long N, int S,
+                              int n_imp, int P /*pow2 >= S+n_imp*/, float* __restrict__ z_fine,
+                              float* __restrict__ z_samples_out, float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const int B = S - 1;                                // bins = z_mid [S-1], weights[1:-1] = [S-2]
+  float* s_bins = smem + (size_t)wib * (3 * S + P);
+  float* s_w = s_bins + S;
+  float* s_cdf = s_w + S;
+  float* s_all = s_cdf + S;                           // [P] merged z
+  for (int i = lane; i < S; i += 32) s_all[i] = z_vals[n * S + i];
+  __syncwarp();
+  for (int i = lane; i < B; i += 32) s_bins[i] = __fmul_rn(0.5f, __fadd_rn(s_all[i + 1], s_all[i]));   // :392
+  for (int i = lane; i < S - 2; i += 32) s_w[i] = weights[n * S + i + 1];                               // :393
+  for (int i = S + n_imp + lane; i < P; i += 32) s_all[i] = __int_as_float(0x7f800000);                  // +inf pad
+  __syncwarp();
+  float* o = s_all + S;
+  sample_pdf_row(s_bins, s_w, s_cdf, B, u + n * u_row_stride, n_imp, lane, [&](int j, float v) { o[j] = v; });
+  // z_std = std(z_samples, unbiased=False) (:412): two-pass
+  float sum = 0.0f;
+  for (int j = lane; j < n_imp; j += 32) sum += o[j];
+  const float mean = warp_sum(sum) / (float)n_imp;
+  float var = 0.0f;
+  for (int j = lane; j < n_imp; j += 32) { float d = o[j] - mean; var += d * d; }
+  var = warp_sum(var) / (float)n_imp;
+  if (lane == 0 && z_std) z_std[n] = sqrtf(var);
+  if (z_samples_out) for (int j = lane; j < n_imp; j += 32) z_samples_out[n * n_imp + j] = o[j];
+  __syncwarp();
+  // bitonic sort of s_all[0..P) ascending (:396)
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          float a = s_all[i], b = s_all[ixj];
+          bool asc = ((i & k) == 0);
+          if ((a > b) == asc) { s_all[i] = b; s_all[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  const int SF = S + n_imp;
+  for (int i = lane; i < SF; i += 32) z_fine[n * SF + i] = s_all[i];
+}
+
+}  // namespace nb

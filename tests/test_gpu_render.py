@@ -1,0 +1,105 @@
+"""GPU parity tests of the whole path: render()/render_rays() through the C ABI vs the golden
+vectors generated from the unmodified reference, plus size-independent properties at full size."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["lego_det", "lego_sharp_det", "lego_perturb", "lego_coarse_only", "lego_lindisp", "fern_ndc_det", "fern_ndc_noise"]
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_common
+    return gpu_common
+
+
+def run_case(G, fx, prec):
+    nets = [G.make_net(G.synth.nerf_state(int(fx["seed_w"]), bool(fx["sharpen"])))]
+    Ni = int(fx["N_importance"])
+    nets.append(G.make_net(G.synth.nerf_state(int(fx["seed_w"]) + 1, bool(fx["sharpen"]))) if Ni > 0 else None)
+    G.nb.set_precision(prec)
+    try:
+        with torch.no_grad():
+            rgb, disp, acc, ex = G.nb.render(int(fx["H"]), int(fx["W"]), fx["K"], chunk=32768, rays=G.dev(fx["rays"]),
+                                             ndc=bool(fx["ndc"]), near=float(fx["near"]), far=float(fx["far"]), use_viewdirs=True,
+                                             network_fn=nets[0], network_fine=nets[1], network_query_fn=G.query_fn(),
+                                             N_samples=64, N_importance=Ni, perturb=float(fx["perturb"]), lindisp=bool(fx["lindisp"]),
+                                             white_bkgd=bool(fx["white_bkgd"]), raw_noise_std=float(fx["raw_noise_std"]),
+                                             retraw=True, pytest=bool(float(fx["perturb"]) > 0 or float(fx["raw_noise_std"]) > 0))
+    finally:
+        G.nb.set_precision("tc_fp16")
+    out = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}
+    out.update(ex)
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+# fp32 exact mode: fp32 rounding only.  tc_fp16: fp16 operand rounding (hard part 1: rgb_map 4e-5,
+# disp 3e-4); the north-star bar is rgb_map <= 1e-4 rel-L2 on the lego shape.
+TOL = {"fp32": {"rgb_map": 1e-5, "acc_map": 1e-5, "rgb0": 1e-5, "acc0": 1e-5, "z_std": 5e-5, "disp": 2e-3},
+       "tc_fp16": {"rgb_map": 1e-4, "acc_map": 1e-4, "rgb0": 1e-4, "acc0": 1e-4, "z_std": 2e-3, "disp": 5e-3}}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tc_fp16"])
+@pytest.mark.parametrize("name", CASES)
+def test_render_matches_reference(G, name, prec):
+    fx = load_golden(name)
+    got = run_case(G, fx, prec)
+    tol = dict(TOL[prec])
+    if bool(fx["sharpen"]) and prec == "tc_fp16":
+        # saturated heads: the 1e10 last interval makes alpha_last a step function of sign(sigma)
+        # (SURVEY 7 hard part 2); fp16 operands flip a few signs -> documented 1e-2 budget on rgb0
+        tol.update(rgb0=2e-2, rgb_map=2e-3, acc0=2e-2, acc_map=2e-3, z_std=2e-2)
+    assert set(got) >= {k for k in ("rgb_map", "disp_map", "acc_map", "raw", "rgb0", "disp0", "acc0", "z_std") if k in fx}
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0", "z_std"):
+        if k in fx:
+            if np.linalg.norm(fx[k]) == 0:                      # fern coarse pass: all sigma <= 0
+                assert np.abs(got[k]).max() < 1e-6
+            else:
+                assert rel_l2(got[k], fx[k]) < tol[k], (name, prec, k, rel_l2(got[k], fx[k]))
+    for k in ("disp_map", "disp0"):
+        if k in fx:
+            assert np.array_equal(np.isnan(got[k]), np.isnan(fx[k])), (name, k)
+            assert rel_l2(got[k], fx[k]) < tol["disp"], (name, prec, k, rel_l2(got[k], fx[k]))
+    assert got["raw"].shape == fx["raw"].shape
+
+
+def test_full_size_properties(G):
+    """BASELINE config 2 (4096 rays x 64+128): chunking invariance (run_nerf.py:78-79), weights >= 0,
+    acc in [0,1], white background identity rgb_white = rgb_black + (1 - acc), parity with the oracle."""
+    sb = G.synth.ray_batch("lego", 4096, seed=1)
+    pc, pf = G.synth.nerf_state(0), G.synth.nerf_state(1)
+    nets = [G.make_net(pc), G.make_net(pf)]
+    kw = dict(ndc=False, near=2., far=6., use_viewdirs=True, network_fn=nets[0], network_fine=nets[1],
+              network_query_fn=G.query_fn(), N_samples=64, N_importance=128, perturb=0., raw_noise_std=0.)
+    rays = G.dev(sb["rays"])
+    with torch.no_grad():
+        a = G.nb.render(400, 400, sb["K"], chunk=32768, rays=rays, white_bkgd=True, **kw)
+        b = G.nb.render(400, 400, sb["K"], chunk=1000, rays=rays, white_bkgd=True, **kw)    # ragged chunks
+        c = G.nb.render(400, 400, sb["K"], chunk=32768, rays=rays, white_bkgd=False, **kw)
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)                                  # bit-identical under re-chunking
+    acc = a[2]
+    assert float(acc.min()) >= 0 and float(acc.max()) <= 1 + 1e-5
+    torch.testing.assert_close(a[0], c[0] + (1 - c[2][:, None]), rtol=1e-5, atol=1e-6)
+    packed = G.O.pack_rays(400, 400, sb["K"], sb["rays"][0], sb["rays"][1], False, 2.0, 6.0, True)
+    ref = G.O.render_rays(packed[:1024], pc, 64, p_fine=pf, N_importance=128, white_bkgd=True)
+    assert rel_l2(a[0][:1024].cpu().numpy(), ref["rgb_map"]) < 1e-4
+    assert rel_l2(a[2][:1024].cpu().numpy(), ref["acc_map"]) < 1e-4
+
+
+def test_empty_and_single_ray(G):
+    pc = G.synth.nerf_state(0)
+    net = G.make_net(pc)
+    q = G.query_fn()
+    r0 = G.nb.render_rays(torch.empty((0, 11), device=G.DEV), net, q, 64, N_importance=128, network_fine=net)
+    assert r0["rgb_map"].shape == (0, 3) and r0["z_std"].shape == (0,)
+    sb = G.synth.ray_batch("lego", 1, seed=2)
+    packed = G.O.pack_rays(400, 400, sb["K"], sb["rays"][0], sb["rays"][1], False, 2.0, 6.0, True)
+    with torch.no_grad():
+        r1 = G.nb.render_rays(G.dev(packed), net, q, 64, N_importance=128, network_fine=None, white_bkgd=True)   # fine None -> coarse net (:399)
+    ref = G.O.render_rays(packed, pc, 64, p_fine=None, N_importance=128, white_bkgd=True)
+    assert rel_l2(r1["rgb_map"].cpu().numpy(), ref["rgb_map"]) < 2e-4
