@@ -163,6 +163,14 @@ size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S);
 int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch,
                             size_t scratch_bytes, void* stream);
 
+/* ---- device-time accounting of the dominant kernel (march_tc_kernel) for bench.py's roofline:
+ *      when enabled, every launch is bracketed by CUDA events on its own stream; read() synchronises
+ *      those events, returns the summed kernel time [ms], the launch count and the algorithmic
+ *      FLOPs those launches performed (2 x MACs of the reference layers x rows), and
+ *      resets the accumulators. ------------------------------------------------------------------- */
+int nerf_b200_timing_enable(int on);
+int nerf_b200_timing_read(double* kernel_ms, int64_t* launches, double* algorithmic_flops);
+
 /* ---- number of kernels launched by this library since load (bench.py's gpu_launches) ---------- */
 int64_t nerf_b200_launch_count(void);
 

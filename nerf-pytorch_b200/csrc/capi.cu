@@ -16,6 +16,21 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- optional device-time accounting of march_tc_kernel launches (bench.py roofline) ----
+struct TimedLaunch { cudaEvent_t a, b; double flops; };
+static bool g_timing = false;
+static TimedLaunch g_timed[4096];
+static int g_ntimed = 0;
+
+static double net_macs_per_row(const NerfNetParams& n) {
+  // MACs of the reference's Linear layers per sample row
+  double m = (double)n.input_ch * n.W;
+  for (int i = 1; i < n.D; ++i) m += (double)((n.skip >= 0 && i == n.skip + 1) ? n.W + n.input_ch : n.W) * n.W;
+  if (n.use_viewdirs) m += (double)n.W * n.W + n.W + (double)(n.W + n.input_ch_views) * (n.W / 2) + 3.0 * (n.W / 2);
+  else m += (double)n.W * n.output_ch;
+  return m;
+}
+
 static int check_tc_net(const NerfNetParams* net) {
   NB_CHECK_ARG(net != nullptr, "net is NULL");
   NB_CHECK_ARG(net->W == TC_W, "tensor-core path supports netwidth == 256 (got %d); use precision=FP32", net->W);
@@ -80,7 +95,15 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   NB_CHECK_ARG((long long)p.rays_per_cta * S < (1ll << 30), "rays_per_cta * S overflows");
   static bool optin = false;
   if (!optin) { if (int rc = smem_optin((const void*)march_tc_kernel, SM_ALLOC)) return rc; optin = true; }
+  TimedLaunch* tl = nullptr;
+  if (g_timing && g_ntimed < 4096) {
+    tl = &g_timed[g_ntimed++];
+    cudaEventCreate(&tl->a); cudaEventCreate(&tl->b);
+    tl->flops = 2.0 * net_macs_per_row(*net) * (double)rows;
+    cudaEventRecord(tl->a, st);
+  }
   march_tc_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
+  if (tl) cudaEventRecord(tl->b, st);
   NB_LAUNCH_OK("march_tc_kernel");
   return 0;
 }
@@ -94,6 +117,23 @@ extern "C" {
 int nerf_b200_abi_version(void) { return NERF_B200_ABI_VERSION; }
 const char* nerf_b200_last_error(void) { return g_err; }
 int64_t nerf_b200_launch_count(void) { return g_launches; }
+
+int nerf_b200_timing_enable(int on) { g_timing = on != 0; return 0; }
+int nerf_b200_timing_read(double* kernel_ms, int64_t* launches, double* algorithmic_flops) {
+  double ms = 0, fl = 0;
+  for (int i = 0; i < g_ntimed; ++i) {
+    NB_CUDA(cudaEventSynchronize(g_timed[i].b));
+    float t = 0;
+    NB_CUDA(cudaEventElapsedTime(&t, g_timed[i].a, g_timed[i].b));
+    ms += t; fl += g_timed[i].flops;
+    cudaEventDestroy(g_timed[i].a); cudaEventDestroy(g_timed[i].b);
+  }
+  if (kernel_ms) *kernel_ms = ms;
+  if (launches) *launches = g_ntimed;
+  if (algorithmic_flops) *algorithmic_flops = fl;
+  g_ntimed = 0;
+  return 0;
+}
 
 int nerf_b200_embed(const float* x, int64_t M, int L, float* out, void* stream) {
   NB_CHECK_ARG(x && out, "NULL pointer");

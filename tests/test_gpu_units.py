@@ -103,7 +103,9 @@ def test_coarse_z_and_fine_z(G):
     w = rng.random((N, 64), dtype=np.float32) ** 3
     u = rng.random((N, 128), dtype=np.float32)
     zf = torch.empty((N, 192), device=G.DEV); zs = torch.empty((N, 128), device=G.DEV); zstd = torch.empty(N, device=G.DEV)
-    G._lib.check(lib.nerf_b200_fine_z(G.ptr(G.dev(zc)), G.ptr(G.dev(w)), G.ptr(G.dev(u)), 128, N, 64, 128, G.ptr(zf), G.ptr(zs), G.ptr(zstd), G.stream()), "fine_z")
+    d_zc, d_w, d_u = G.dev(zc), G.dev(w), G.dev(u)          # keep the inputs alive across the call
+    G._lib.check(lib.nerf_b200_fine_z(G.ptr(d_zc), G.ptr(d_w), G.ptr(d_u), 128, N, 64, 128, G.ptr(zf), G.ptr(zs), G.ptr(zstd), G.stream()), "fine_z")
+    torch.cuda.synchronize()
     mid = 0.5 * (zc[:, 1:] + zc[:, :-1])
     ref_s = G.O.sample_pdf(mid, w[:, 1:-1], 128, u=u)
     bad = np.abs(zs.cpu().numpy() - ref_s) > 5e-6
