@@ -163,6 +163,11 @@ size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S);
 int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch,
                             size_t scratch_bytes, void* stream);
 
+/* ---- debug hooks (not part of the drop-in surface): clock64 trace of CTA 0 / super-tile 1 of the next
+ *      march launches into a device buffer of 4096 int64 (NULL disables); tcgen05.mma issue-rate probe */
+int nerf_b200_debug_set_trace(void* dev_buf_4096_i64);
+int nerf_b200_debug_mma_rate(int reps, int N, int b_sw64, void* out_2_i64, void* stream);
+
 /* ---- device-time accounting of the dominant kernel (march_tc_kernel) for bench.py's roofline:
  *      when enabled, every launch is bracketed by CUDA events on its own stream; read() synchronises
  *      those events, returns the summed kernel time [ms], the launch count and the algorithmic

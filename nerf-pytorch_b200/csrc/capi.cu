@@ -31,6 +31,8 @@ static double net_macs_per_row(const NerfNetParams& n) {
   return m;
 }
 
+static long long* g_trace = nullptr;      // debug: device buffer of 4096 int64 clock stamps (or NULL)
+
 static int check_tc_net(const NerfNetParams* net) {
   NB_CHECK_ARG(net != nullptr, "net is NULL");
   NB_CHECK_ARG(net->W == TC_W, "tensor-core path supports netwidth == 256 (got %d); use precision=FP32", net->W);
@@ -95,6 +97,7 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   NB_CHECK_ARG((long long)p.rays_per_cta * S < (1ll << 30), "rays_per_cta * S overflows");
   static bool optin = false;
   if (!optin) { if (int rc = smem_optin((const void*)march_tc_kernel, SM_ALLOC)) return rc; optin = true; }
+  p.trace = g_trace;
   TimedLaunch* tl = nullptr;
   if (g_timing && g_ntimed < 4096) {
     tl = &g_timed[g_ntimed++];
@@ -335,6 +338,16 @@ size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S) { (void)N; (void)S;
 int nerf_b200_march_bwd(const float*, const float*, const float*, int64_t, int, const NerfNetParams*, const void*,
                         const NerfRenderCfg*, const float*, const NerfNetGrads*, void*, size_t, void*) {
   return nb::set_error(-6, "nerf_b200_march_bwd: not built yet");
+}
+
+int nerf_b200_debug_set_trace(void* dev_buf_4096_i64) { g_trace = static_cast<long long*>(dev_buf_4096_i64); return 0; }
+
+int nerf_b200_debug_mma_rate(int reps, int N, int b_sw64, void* out_2_i64, void* stream) {
+  const size_t sm = 65536 + 32768 + 256 + 1024;
+  if (int rc = smem_optin((const void*)mma_rate_kernel, sm)) return rc;
+  mma_rate_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(reps, N, b_sw64, static_cast<long long*>(out_2_i64));
+  NB_LAUNCH_OK("mma_rate_kernel");
+  return 0;
 }
 
 int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch, size_t scratch_bytes, void* stream) {

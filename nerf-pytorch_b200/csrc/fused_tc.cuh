@@ -166,6 +166,7 @@ struct MarchParams {
   int D, skip, use_viewdirs, L, IC;
   int white_bkgd, do_composite;
   NerfPassOut out;
+  long long* trace;                       // debug: clock64 timestamps of CTA 0, super-tile 1 (or NULL)
 };
 
 struct CompCarry { float T, r, g, b, depth, acc; int turn; int pad; };
@@ -265,7 +266,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           const uint32_t cb = tc_layer_chunk_bytes(l, D);
           for (int c = 0; c < nch; ++c, ++it) {
             const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
+            const bool tr = p.trace && blockIdx.x == 0 && st == 1;
+            const int ci = (int)(src - p.chunks) / 8192;
+            if (tr) p.trace[1024 + 2 * ci] = clock64();
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
+            if (tr) p.trace[1024 + 2 * ci + 1] = clock64();
             ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
             ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
             src += cb;
@@ -288,7 +293,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           const uint32_t idesc = ptx::umma_idesc_f16(128, Nn);
           for (int c = 0; c < nch; ++c, ++it) {
             const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
+            const bool tr = p.trace && blockIdx.x == 0 && st == 1;
+            long long* trp = p.trace + 4 * (l * 10 + c);
+            if (tr) trp[0] = clock64();
             ptx::mbar_wait(bar_wfull + 8 * stage, ph);
+            if (tr) trp[1] = clock64();
             ptx::tc_fence_after();
             const bool is_enc = (l == 0) || (skip_layer && c < 2);
             const int kc = skip_layer ? c - 2 : c;
@@ -300,6 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
                 ptx::mbar_wait(bar_act + 8 * X, aph);
                 aph ^= 1;
                 ptx::tc_fence_after();
+                if (tr && X == 1) trp[2] = clock64();
               }
               const uint32_t a_base = is_enc ? (sb + SM_ENC + X * 16384 + c * 64)
                                              : (sb + SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
@@ -311,6 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
               if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
             }
             ptx::mma_commit(bar_wempty + 8 * stage);
+            if (tr) trp[3] = clock64();
             if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
           }
         }
@@ -332,9 +343,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       const int rl = (valid ? lr : nrows - 1) / p.S;              // local ray
       const long long n_ray = ray0 + rl;
       for (int l = 0; l < NL; ++l) {
+        const bool tr = p.trace && blockIdx.x == 0 && st == 1 && e == 0 && lane == 0;
+        long long* trp = p.trace + 2048 + 4 * (X * 16 + l);
+        if (tr) trp[0] = clock64();
         ptx::mbar_wait(bar_dfull + 8 * X, dph);
         dph ^= 1;
         ptx::tc_fence_after();
+        if (tr) trp[1] = clock64();
         if (l <= D) {
           // pts layer (ReLU) or feature layer (no activation): 128 columns per warp
           const bool last_pts = (l == D - 1);
@@ -379,6 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(bar_act + 8 * X);
+          if (tr) trp[2] = clock64();
         } else {
           // views_linears[0] (N=128): 64 columns per warp; + per-ray view bias, ReLU, rgb_linear
           const float* vbrow = p.vb + n_ray * 128;
@@ -576,6 +592,43 @@ __global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __re
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+// MMA issue-rate microbenchmark: `reps` x (M=128, N, K=16) tcgen05.mma on resident (garbage) operands,
+// alternating between two accumulators; out[0] = cycles from first issue to completion of the last.
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int reps, int N, int b_sw64, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t BAR = 65536 + 32768, TPTR = BAR + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TPTR);
+  for (int i = threadIdx.x; i < (65536 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+  if (threadIdx.x == 0) { ptx::mbar_init(sb + BAR, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::umma_idesc_f16(128, N);
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      const uint32_t a = sb + ((i >> 1) & 3) * 16384 + (i & 1) * 32;
+      const uint64_t bd = b_sw64 ? ptx::umma_desc(sb + 65536 + (i & 1) * 32, 512, ptx::UMMA_SW64)
+                                 : ptx::umma_desc(sb + 65536 + (i & 3) * 32, 1024, ptx::UMMA_SW128);
+      ptx::mma_f16_ss(tmem + (i & 1) * 256, ptx::umma_desc(a, 1024, ptx::UMMA_SW128), bd, idesc, 1u);
+    }
+    const long long t1 = clock64();
+    ptx::mma_commit(sb + BAR);
+    ptx::mbar_wait(sb + BAR, 0);
+    const long long t2 = clock64();
+    out[0] = t2 - t0; out[1] = t1 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace nb
