@@ -6,15 +6,15 @@
 // (:37-51), batchify (:27-34), Embedder.embed (run_nerf_helpers.py:36-45) and NeRF.forward
 // (:96-119).  sigma/rgb never leave the SM unless `raw` is requested.
 //
-// CTA = 768 threads, 1 CTA / SM, persistent over a contiguous range of whole rays:
+// CTA = 640 threads, 1 CTA / SM, persistent over a contiguous range of whole rays:
 //   warp 0      : weight producer   -- streams the pre-swizzled fp16 weight chunks (K=32 x N) from
 //                                      L2 into a 3-stage ring with cp.async.bulk (TMA engine)
 //   warp 1      : MMA issuer        -- one thread issues tcgen05.mma (M=128, N=256|128, K=16)
-//   warp 2      : TMEM allocator
+//   warps 2-3   : sampler           -- o + d*z and sin/cos encoding for the NEXT 256-row super-tile
+//                                      (warp 2 also owns the TMEM allocation)
 //   warps 4-19  : epilogue          -- 2 tile slots x 8 warps: tcgen05.ld -> +bias -> ReLU -> fp16 ->
 //                                      st.shared into the next layer's A operand (128B swizzle);
 //                                      heads (alpha, rgb) on CUDA cores; warp-scan compositing
-//   warps 20-23 : sampler           -- o + d*z and sin/cos encoding for the NEXT 256-row super-tile
 // Two 128-row tiles (slots A, B) run in lock-step on the same weight chunk, each with its own
 // 128x256 fp32 accumulator (2 x 256 TMEM columns): the tensor pipe works on one tile while the
 // other tile's epilogue drains its accumulator.
@@ -24,7 +24,8 @@
 
 namespace nb {
 
-constexpr int TC_THREADS = 768;
+constexpr int TC_THREADS = 640;              // 2 control + 2 sampler + 16 epilogue warps
+constexpr int TC_SAMPLER_THREADS = 64;
 constexpr int TC_W = 256;                 // hidden width supported by the tensor-core path
 constexpr int TC_MAXD = 8;                // pts layers supported (bias table lives in smem)
 constexpr int TC_TILE = 128;              // rows per MMA tile
@@ -169,12 +170,35 @@ struct MarchParams {
   long long* trace;                       // debug: clock64 timestamps of CTA 0, super-tile 1 (or NULL)
 };
 
-struct CompCarry { float T, r, g, b, depth, acc; int turn; int pad; };
+// compositing carry of the ray that is still open at a warp boundary (shared memory, 32 B)
+constexpr uint32_t CARRY_T = 0, CARRY_R = 4, CARRY_G = 8, CARRY_B = 12, CARRY_D = 16, CARRY_A = 20, CARRY_TURN = 24;
 
 __device__ __forceinline__ uint32_t act_row_off(int r) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128); }
 
-// Epilogue of one 32-column batch: v[32] (fp32 accumulators of one row) -> +bias -> (ReLU) -> fp16 ->
-// 4 x 16-byte stores into the 128B-swizzled K-major A tile.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// (a, b) += (c, d) as one packed FADD2
+__device__ __forceinline__ void add2(float& a, float& b, float c, float d) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(a), "+f"(b) : "f"(c), "f"(d));
+}
+
+// v[32] (fp32 accumulators of one row, bias already added) -> (ReLU) -> fp16 -> 4 x 16-byte stores
+// into the 128B-swizzled K-major A tile.
 template <bool RELU>
 __device__ __forceinline__ void store_act32(const float (&x)[32], uint32_t act_base, int r, int col0) {
   const uint32_t kb = (uint32_t)(col0 >> 6) * 16384u;
@@ -207,17 +231,30 @@ __device__ __forceinline__ float seg_scan_add(float v, int lane, int s) {
   return v;
 }
 
+// One 32-column batch of a hidden-layer epilogue: x = acc + bias (packed FADD2, bias via LDS.128)
+__device__ __forceinline__ void add_bias32(const uint32_t (&v)[32], uint32_t bias_addr, float (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bb = lds128(bias_addr + 16 * j);
+    x[4 * j + 0] = __uint_as_float(v[4 * j + 0]); x[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+    x[4 * j + 2] = __uint_as_float(v[4 * j + 2]); x[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+    add2(x[4 * j + 0], x[4 * j + 1], bb.x, bb.y);
+    add2(x[4 * j + 2], x[4 * j + 3], bb.z, bb.w);
+  }
+}
+
+extern __shared__ __align__(1024) uint8_t tc_smem[];
+
 __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sb & 1023u) != 0) __trap();                    // swizzle atoms need the 1024-byte alignment
 
   float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
   float* s_heads = reinterpret_cast<float*>(smem + SM_HEADS);
-  float4* s_part = reinterpret_cast<float4*>(smem + SM_PART);
-  volatile CompCarry* s_carry = reinterpret_cast<volatile CompCarry*>(smem + SM_MISC + 16);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SM_MISC);
+  const uint32_t a_bias = sb + SM_BIAS, a_heads = sb + SM_HEADS, a_part = sb + SM_PART, a_carry = sb + SM_MISC + 16;
 
   // mbarriers
   const uint32_t bar_wfull = sb + SM_BARS;            // [3]
@@ -240,12 +277,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
   for (int i = threadIdx.x; i < (TC_MAXD + 1) * 256; i += TC_THREADS) s_bias[i] = p.bias[i];
   for (int i = threadIdx.x; i < HEADS_FLOATS; i += TC_THREADS) s_heads[i] = p.heads[i];
   if (threadIdx.x == 0) {
-    s_carry->T = 1.0f; s_carry->r = 0; s_carry->g = 0; s_carry->b = 0; s_carry->depth = 0; s_carry->acc = 0; s_carry->turn = 0;
+    sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
+    sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f); st_release_shared(a_carry + CARRY_TURN, 0u);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); }
     for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 256); }
-    ptx::mbar_init(bar_encfull, 128);
+    ptx::mbar_init(bar_encfull, TC_SAMPLER_THREADS);
     ptx::mbar_init(bar_encfree, 1);
     ptx::fence_mbar_init();
   }
@@ -266,11 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           const uint32_t cb = tc_layer_chunk_bytes(l, D);
           for (int c = 0; c < nch; ++c, ++it) {
             const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
-            const bool tr = p.trace && blockIdx.x == 0 && st == 1;
-            const int ci = (int)(src - p.chunks) / 8192;
-            if (tr) p.trace[1024 + 2 * ci] = clock64();
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
-            if (tr) p.trace[1024 + 2 * ci + 1] = clock64();
             ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
             ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
             src += cb;
@@ -283,25 +317,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       uint32_t it = 0, actph0 = 0, actph1 = 0;
+      // descriptor templates; only the 14-bit start-address field changes (added in 16-byte units)
+      const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
+      const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
       for (int st = 0; st < nst; ++st) {
+        const bool tr = p.trace && blockIdx.x == 0 && st == 1;
         ptx::mbar_wait(bar_encfull, st & 1);
         ptx::tc_fence_after();
         for (int l = 0; l < NL; ++l) {
           const int nch = tc_layer_chunks(l, D, p.skip);
           const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
-          const int Nn = (l == D + 1) ? 128 : 256;
-          const uint32_t idesc = ptx::umma_idesc_f16(128, Nn);
+          const uint32_t idesc = ptx::umma_idesc_f16(128, (l == D + 1) ? 128 : 256);
           for (int c = 0; c < nch; ++c, ++it) {
             const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
-            const bool tr = p.trace && blockIdx.x == 0 && st == 1;
             long long* trp = p.trace + 4 * (l * 10 + c);
             if (tr) trp[0] = clock64();
             ptx::mbar_wait(bar_wfull + 8 * stage, ph);
-            if (tr) trp[1] = clock64();
             ptx::tc_fence_after();
+            if (tr) trp[1] = clock64();
             const bool is_enc = (l == 0) || (skip_layer && c < 2);
             const int kc = skip_layer ? c - 2 : c;
-            const uint32_t b_base = sb + SM_WRING + stage * TC_STAGE_BYTES;
+            const uint64_t bd = bdesc0 + ((SM_WRING + stage * TC_STAGE_BYTES) >> 4);
+            const uint32_t a_off = is_enc ? (SM_ENC + c * 64) : (SM_ACT + (kc >> 1) * 16384 + (kc & 1) * 64);
+            const uint32_t a_step = is_enc ? 16384u : 65536u;
 #pragma unroll
             for (int X = 0; X < 2; ++X) {
               if (c == 0) {
@@ -311,24 +349,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
                 ptx::tc_fence_after();
                 if (tr && X == 1) trp[2] = clock64();
               }
-              const uint32_t a_base = is_enc ? (sb + SM_ENC + X * 16384 + c * 64)
-                                             : (sb + SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                ptx::mma_f16_ss(tmem + X * 256, ptx::umma_desc(a_base + j * 32, 1024, ptx::UMMA_SW128),
-                                ptx::umma_desc(b_base + j * 32, 512, ptx::UMMA_SW64), idesc, (c > 0 || j > 0) ? 1u : 0u);
-              }
+              const uint64_t ad = adesc0 + ((a_off + X * a_step) >> 4);
+              ptx::mma_f16_ss(tmem + X * 256, ad, bd, idesc, (c > 0) ? 1u : 0u);
+              ptx::mma_f16_ss(tmem + X * 256, ad + 2, bd + 2, idesc, 1u);
               if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
             }
             ptx::mma_commit(bar_wempty + 8 * stage);
-            if (tr) trp[3] = clock64();
             if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
+            if (tr) trp[3] = clock64();
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < 20) {
+  } else if (warp >= 4) {
     // =========================== epilogue ===========================
     const int X = (warp - 4) >> 3, e = (warp - 4) & 7, q = e & 3, ch = e >> 2;
     const int r = 32 * q + lane;                                  // tile row == TMEM lane
@@ -351,38 +385,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
         ptx::tc_fence_after();
         if (tr) trp[1] = clock64();
         if (l <= D) {
-          // pts layer (ReLU) or feature layer (no activation): 128 columns per warp
+          // pts layer (ReLU) or feature layer (no activation): 128 columns per warp in 4 batches,
+          // the TMEM load of batch b+1 in flight while batch b is converted and stored
           const bool last_pts = (l == D - 1);
           const bool write_act = !(last_pts && !p.use_viewdirs);
-#pragma unroll 1
-          for (int b = 0; b < 4; ++b) {
-            const int col0 = ch * 128 + b * 32;
-            uint32_t v[32];
-            ptx::tmem_ld_x32(t_lane + col0, v);
-            ptx::tmem_ld_wait();
-            float x[32];
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + l * 256 + col0);
+          const int colw = ch * 128;
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld_x32(t_lane + colw, va);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 bb = b4[j];
-              x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-              x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
-            }
+          for (int b = 0; b < 4; ++b) {
+            const int col0 = colw + b * 32;
+            uint32_t (&v)[32] = (b & 1) ? vb : va;
+            uint32_t (&vn)[32] = (b & 1) ? va : vb;
+            ptx::tmem_ld_wait();
+            if (b < 3) ptx::tmem_ld_x32(t_lane + col0 + 32, vn);
+            float x[32];
+            add_bias32(v, a_bias + (uint32_t)(l * 256 + col0) * 4u, x);
             if (last_pts) {
               if (p.use_viewdirs) {                               // alpha_linear (run_nerf_helpers.py:106)
-                const float4* w4 = reinterpret_cast<const float4*>(s_heads + col0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  float4 w = w4[j];
+                  const float4 w = lds128(a_heads + (uint32_t)(col0 + 4 * j) * 4u);
                   hp3 = fmaf(fmaxf(x[4 * j + 0], 0.f), w.x, hp3); hp3 = fmaf(fmaxf(x[4 * j + 1], 0.f), w.y, hp3);
                   hp3 = fmaf(fmaxf(x[4 * j + 2], 0.f), w.z, hp3); hp3 = fmaf(fmaxf(x[4 * j + 3], 0.f), w.w, hp3);
                 }
               } else {                                            // output_linear (:117)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float h = fmaxf(x[j], 0.f);
-                  hp0 = fmaf(h, s_heads[col0 + j], hp0); hp1 = fmaf(h, s_heads[256 + col0 + j], hp1);
-                  hp2 = fmaf(h, s_heads[512 + col0 + j], hp2); hp3 = fmaf(h, s_heads[768 + col0 + j], hp3);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w0 = lds128(a_heads + (uint32_t)(col0 + 4 * j) * 4u), w1 = lds128(a_heads + (uint32_t)(256 + col0 + 4 * j) * 4u);
+                  const float4 w2 = lds128(a_heads + (uint32_t)(512 + col0 + 4 * j) * 4u), w3 = lds128(a_heads + (uint32_t)(768 + col0 + 4 * j) * 4u);
+                  const float h0 = fmaxf(x[4 * j + 0], 0.f), h1 = fmaxf(x[4 * j + 1], 0.f), h2 = fmaxf(x[4 * j + 2], 0.f), h3 = fmaxf(x[4 * j + 3], 0.f);
+                  hp0 = fmaf(h0, w0.x, hp0); hp0 = fmaf(h1, w0.y, hp0); hp0 = fmaf(h2, w0.z, hp0); hp0 = fmaf(h3, w0.w, hp0);
+                  hp1 = fmaf(h0, w1.x, hp1); hp1 = fmaf(h1, w1.y, hp1); hp1 = fmaf(h2, w1.z, hp1); hp1 = fmaf(h3, w1.w, hp1);
+                  hp2 = fmaf(h0, w2.x, hp2); hp2 = fmaf(h1, w2.y, hp2); hp2 = fmaf(h2, w2.z, hp2); hp2 = fmaf(h3, w2.w, hp2);
+                  hp3 = fmaf(h0, w3.x, hp3); hp3 = fmaf(h1, w3.y, hp3); hp3 = fmaf(h2, w3.z, hp3); hp3 = fmaf(h3, w3.w, hp3);
                 }
               }
             }
@@ -398,39 +434,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
         } else {
           // views_linears[0] (N=128): 64 columns per warp; + per-ray view bias, ReLU, rgb_linear
           const float* vbrow = p.vb + n_ray * 128;
-#pragma unroll 1
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld_x32(t_lane + ch * 64, va);
+          ptx::tmem_ld_x32(t_lane + ch * 64 + 32, vb);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar_act + 8 * X);                      // accumulator drained: next super-tile may start
+#pragma unroll
           for (int b = 0; b < 2; ++b) {
             const int col0 = ch * 64 + b * 32;
-            uint32_t v[32];
-            ptx::tmem_ld_x32(t_lane + col0, v);
-            ptx::tmem_ld_wait();
+            const uint32_t (&v)[32] = b ? vb : va;
             const float4* vb4 = reinterpret_cast<const float4*>(vbrow + col0);
-            const float* w0 = s_heads + 256 + col0;
+            const uint32_t w0 = a_heads + (uint32_t)(256 + col0) * 4u;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float4 bb = vb4[j];
-              float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
-              float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
-              float4 wr = *reinterpret_cast<const float4*>(w0 + 4 * j);
-              float4 wg = *reinterpret_cast<const float4*>(w0 + 128 + 4 * j);
-              float4 wb = *reinterpret_cast<const float4*>(w0 + 256 + 4 * j);
+              const float4 bb = vb4[j];
+              const float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
+              const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
+              const float4 wr = lds128(w0 + 16 * j), wg = lds128(w0 + 512 + 16 * j), wb = lds128(w0 + 1024 + 16 * j);
               hp0 = fmaf(h0, wr.x, hp0); hp0 = fmaf(h1, wr.y, hp0); hp0 = fmaf(h2, wr.z, hp0); hp0 = fmaf(h3, wr.w, hp0);
               hp1 = fmaf(h0, wg.x, hp1); hp1 = fmaf(h1, wg.y, hp1); hp1 = fmaf(h2, wg.z, hp1); hp1 = fmaf(h3, wg.w, hp1);
               hp2 = fmaf(h0, wb.x, hp2); hp2 = fmaf(h1, wb.y, hp2); hp2 = fmaf(h2, wb.z, hp2); hp2 = fmaf(h3, wb.w, hp2);
             }
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(bar_act + 8 * X);
         }
       }
       // ---- heads: combine the two column halves, then raw -> compositing (ch == 0 warps) ----
-      if (ch == 1) s_part[X * 128 + r] = make_float4(hp0, hp1, hp2, hp3);
+      const uint32_t part = a_part + (uint32_t)(X * 128 + r) * 16u;
+      if (ch == 1) sts128(part, make_float4(hp0, hp1, hp2, hp3));
       ptx::named_bar_sync(1 + X, 256);
       if (ch == 0) {
-        const float4 o = s_part[X * 128 + r];
+        const float4 o = lds128(part);
         float4 raw4;
-        if (p.use_viewdirs) raw4 = make_float4(hp0 + o.x + s_heads[641], hp1 + o.y + s_heads[642], hp2 + o.z + s_heads[643], hp3 + o.w + s_heads[640]);
-        else raw4 = make_float4(hp0 + o.x + s_heads[1024], hp1 + o.y + s_heads[1025], hp2 + o.z + s_heads[1026], hp3 + o.w + s_heads[1027]);
+        if (p.use_viewdirs) raw4 = make_float4(hp0 + o.x + lds32(a_heads + 641 * 4), hp1 + o.y + lds32(a_heads + 642 * 4),
+                                               hp2 + o.z + lds32(a_heads + 643 * 4), hp3 + o.w + lds32(a_heads + 640 * 4));
+        else raw4 = make_float4(hp0 + o.x + lds32(a_heads + 1024 * 4), hp1 + o.y + lds32(a_heads + 1025 * 4),
+                                hp2 + o.z + lds32(a_heads + 1026 * 4), hp3 + o.w + lds32(a_heads + 1027 * 4));
         const long long m = row_begin + lr;
         if (valid && p.out.raw) reinterpret_cast<float4*>(p.out.raw)[m] = raw4;
         if (p.do_composite) {
@@ -442,10 +481,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
             z = p.z_vals[m];
             float dist = (k == p.S - 1) ? 1e10f : __fsub_rn(p.z_vals[m + 1], z);             // :277-278
             dist = __fmul_rn(dist, norm);
-            const float s = raw4.w + (p.noise ? p.noise[m] : 0.0f);
-            alpha = __fsub_rn(1.0f, expf(-fmaxf(s, 0.0f) * dist));                            // :275
+            const float sg = raw4.w + (p.noise ? p.noise[m] : 0.0f);
+            alpha = __fsub_rn(1.0f, expf(-fmaxf(sg, 0.0f) * dist));                           // :275
             cr = sigmoidf_acc(raw4.x); cg = sigmoidf_acc(raw4.y); cb = sigmoidf_acc(raw4.z); // :282
           }
+          // warp-local part (independent of the carry): transmittance / weights relative to
+          // max(ray start, warp start) and their segmented sums
           const bool seg_start = valid && (k == 0), seg_end = valid && (k == p.S - 1);
           const unsigned smask = __ballot_sync(0xffffffffu, seg_start);
           const unsigned below = smask & ((lane == 31) ? 0xffffffffu : ((2u << lane) - 1u));
@@ -453,19 +494,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           const float qv = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;         // :295
           const float pv = seg_scan_mul(qv, lane, s);
           float ev = __shfl_up_sync(0xffffffffu, pv, 1);
-          if (lane == 0) ev = 1.0f;
-          // take the compositing turn: rows are consumed in order across warps / slots / super-tiles
-          const int ticket = (st * 2 + X) * 4 + q;
-          if (lane == 0) { while (s_carry->turn != ticket) { } }
+          if (lane == 0 || s == lane) ev = 1.0f;
+          const float wl = valid ? alpha * ev : 0.0f;
+          float t_r = seg_scan_add(wl * cr, lane, s), t_g = seg_scan_add(wl * cg, lane, s), t_b = seg_scan_add(wl * cb, lane, s);
+          float t_d = seg_scan_add(wl * z, lane, s), t_a = seg_scan_add(wl, lane, s);
+          // take the compositing turn: rows are consumed in order across warps / slots / super-tiles;
+          // only the few flops that thread the carry through this warp sit on the serial chain
+          const uint32_t ticket = (uint32_t)((st * 2 + X) * 4 + q);
+          if (lane == 0) { while (ld_acquire_shared(a_carry + CARRY_TURN) != ticket) { } }
           __syncwarp();
-          const float Tin = s_carry->T;
-          const float c_r = s_carry->r, c_g = s_carry->g, c_b = s_carry->b, c_d = s_carry->depth, c_a = s_carry->acc;
-          const float T = (s == lane) ? 1.0f : ((s >= 0) ? ev : Tin * ev);
-          const float w = valid ? alpha * T : 0.0f;
-          float t_r = seg_scan_add(w * cr, lane, s), t_g = seg_scan_add(w * cg, lane, s), t_b = seg_scan_add(w * cb, lane, s);
-          float t_d = seg_scan_add(w * z, lane, s), t_a = seg_scan_add(w, lane, s);
-          if (s < 0) { t_r += c_r; t_g += c_g; t_b += c_b; t_d += c_d; t_a += c_a; }
-          if (valid && p.out.weights) p.out.weights[m] = w;
+          const float Tin = lds32(a_carry + CARRY_T);
+          const float c_r = lds32(a_carry + CARRY_R), c_g = lds32(a_carry + CARRY_G), c_b = lds32(a_carry + CARRY_B);
+          const float c_d = lds32(a_carry + CARRY_D), c_a = lds32(a_carry + CARRY_A);
+          __syncwarp();
+          if (s < 0) { t_r = fmaf(Tin, t_r, c_r); t_g = fmaf(Tin, t_g, c_g); t_b = fmaf(Tin, t_b, c_b); t_d = fmaf(Tin, t_d, c_d); t_a = fmaf(Tin, t_a, c_a); }
+          if (lane == 31) {
+            if (seg_end) {
+              sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
+              sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f);
+            } else {
+              sts32(a_carry + CARRY_T, (s >= 0) ? pv : Tin * pv);
+              sts32(a_carry + CARRY_R, t_r); sts32(a_carry + CARRY_G, t_g); sts32(a_carry + CARRY_B, t_b);
+              sts32(a_carry + CARRY_D, t_d); sts32(a_carry + CARRY_A, t_a);
+            }
+            st_release_shared(a_carry + CARRY_TURN, ticket + 1u);
+          }
+          // off the chain: weights and per-ray outputs
+          if (valid && p.out.weights) p.out.weights[m] = (s < 0) ? Tin * wl : wl;
           if (seg_end) {
             float rr = t_r, gg = t_g, bb = t_b;
             if (p.white_bkgd) { const float bg = 1.0f - t_a; rr += bg; gg += bg; bb += bg; }  // :302-303
@@ -478,27 +533,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
             if (p.out.acc_map) p.out.acc_map[n_ray] = t_a;
             if (p.out.depth_map) p.out.depth_map[n_ray] = t_d;
           }
-          __syncwarp();
-          if (lane == 31) {
-            if (seg_end) { s_carry->T = 1.0f; s_carry->r = 0; s_carry->g = 0; s_carry->b = 0; s_carry->depth = 0; s_carry->acc = 0; }
-            else {
-              s_carry->T = (s >= 0) ? pv : Tin * pv;
-              s_carry->r = t_r; s_carry->g = t_g; s_carry->b = t_b; s_carry->depth = t_d; s_carry->acc = t_a;
-            }
-            __threadfence_block();
-            s_carry->turn = ticket + 1;
-          }
         }
       }
     }
-  } else if (warp >= 20) {
-    // =========================== sampler ===========================
-    const int t = threadIdx.x - 640;                              // 0..127: tile row
+  } else {
+    // =========================== sampler (warps 2-3) ===========================
+    const int t = threadIdx.x - 64;                               // 0..63
     for (int st = 0; st < nst; ++st) {
       ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
 #pragma unroll 1
-      for (int X = 0; X < 2; ++X) {
-        const int lr = st * TC_ST + X * TC_TILE + t;
+      for (int i = 0; i < 4; ++i) {
+        const int X = i >> 1, tr_ = t + 64 * (i & 1);             // tile slot, tile row
+        const int lr = st * TC_ST + X * TC_TILE + tr_;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (lr < nrows) {
           const long long m = row_begin + lr;
@@ -512,9 +558,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           }
         }
         // 64 encoded channels (63 + zero pad), one fp16 store each into the 128B-swizzled K-block
-        const uint32_t row = sb + SM_ENC + X * 16384 + act_row_off(t);
+        const uint32_t row = sb + SM_ENC + X * 16384 + act_row_off(tr_);
         auto put = [&](int c, float v) {
-          const uint32_t a = row + (uint32_t)((((c >> 3) ^ (t & 7)) << 4) + ((c & 7) << 1));
+          const uint32_t a = row + (uint32_t)((((c >> 3) ^ (tr_ & 7)) << 4) + ((c & 7) << 1));
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
         };
         put(0, px); put(1, py); put(2, pz);
@@ -625,6 +671,100 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int reps, int N, int b
     ptx::mbar_wait(sb + BAR, 0);
     const long long t2 = clock64();
     out[0] = t2 - t0; out[1] = t1 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+// Epilogue-rate microbenchmark: 8 warps drain a 128x256 fp32 accumulator `reps` times the way the
+// march kernel does (mode 0: tcgen05.ld only; 1: + bias/ReLU/convert; 2: + st.shared of the A tile),
+// optionally while another warp keeps the tensor pipe busy on the other accumulator (mma != 0).
+// out[0] = cycles for `reps` tile-layer epilogues (warp 4 lane 0).
+__global__ void __launch_bounds__(384, 1) epi_rate_kernel(int reps, int mode, int mma, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ACT = 0, OPS = 65536, BIAS = 65536 + 49152, BAR = BIAS + 1024, TPTR = BAR + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TPTR);
+  float* s_bias = reinterpret_cast<float*>(smem + BIAS);
+  volatile int* s_stop = reinterpret_cast<volatile int*>(smem + TPTR + 16);
+  for (int i = threadIdx.x; i < (65536 + 49152) / 4; i += 384) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x < 256) s_bias[threadIdx.x] = 0.5f;
+  if (threadIdx.x == 0) { ptx::mbar_init(sb + BAR, 1); ptx::fence_mbar_init(); *s_stop = 0; }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  if (warp == 1) {
+    if (lane == 0 && mma) {
+      const uint32_t idesc = ptx::umma_idesc_f16(128, 256);
+      int i = 0;
+      while (!*s_stop) {
+        for (int j = 0; j < 8; ++j, ++i)
+          ptx::mma_f16_ss(tmem + 256, ptx::umma_desc(sb + OPS + (i & 1) * 32, 1024, ptx::UMMA_SW128),
+                          ptx::umma_desc(sb + OPS + 16384 + (i & 1) * 32, 512, ptx::UMMA_SW64), idesc, 1u);
+        ptx::mma_commit(sb + BAR);
+        ptx::mbar_wait(sb + BAR, (i / 8 - 1) & 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int e = warp - 4, q = e & 3, ch = e >> 2, r = 32 * q + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    float sink = 0.f;
+    const int math = mode & 3;
+    const bool no_pfence = mode & 4, no_tfence = mode & 8, no_bar = mode & 16, dual = mode & 32;
+    long long ldw = 0;
+    ptx::named_bar_sync(1, 256);
+    const long long t0 = clock64();
+    for (int it = 0; it < reps; ++it) {
+      if (dual) {
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+          const int col0 = ch * 128 + b * 64;
+          uint32_t v[32], w[32];
+          const long long c0 = clock64();
+          ptx::tmem_ld_x32(t_lane + col0, v);
+          ptx::tmem_ld_x32(t_lane + col0 + 32, w);
+          ptx::tmem_ld_wait();
+          ldw += clock64() - c0;
+          sink += __uint_as_float(v[it & 31]) + __uint_as_float(w[it & 31]);
+        }
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          const int col0 = ch * 128 + b * 32;
+          uint32_t v[32];
+          const long long c0 = clock64();
+          ptx::tmem_ld_x32(t_lane + col0, v);
+          ptx::tmem_ld_wait();
+          ldw += clock64() - c0;
+          if (math == 0) { sink += __uint_as_float(v[it & 31]); continue; }
+          float x[32];
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bb = b4[j];
+            x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+            x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+          }
+          if (math == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) sink += __uint_as_float(ptx::cvt_relu_f16x2(x[j], x[j + 1]));
+          } else store_act32<true>(x, sb + ACT, r, col0);
+        }
+      }
+      if (!no_tfence) ptx::tc_fence_before();
+      if (!no_pfence) ptx::fence_proxy_async_smem();
+      if (!no_bar) ptx::named_bar_sync(1, 256);
+    }
+    const long long t1 = clock64();
+    if (e == 0 && lane == 0) { out[0] = t1 - t0; out[1] = ldw; *s_stop = 1; }
+    if (sink == 123.456f) out[1] = 1;
   }
   ptx::tc_fence_before();
   __syncthreads();
