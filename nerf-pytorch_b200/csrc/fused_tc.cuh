@@ -296,18 +296,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
   if (warp == 0) {
     // =========================== weight producer ===========================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t stage = 0, ph = 0;
       for (int st = 0; st < nst; ++st) {
         const uint8_t* src = p.chunks;
         for (int l = 0; l < NL; ++l) {
           const int nch = tc_layer_chunks(l, D, p.skip);
           const uint32_t cb = tc_layer_chunk_bytes(l, D);
-          for (int c = 0; c < nch; ++c, ++it) {
-            const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
+          for (int c = 0; c < nch; ++c) {
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
             ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
             ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
             src += cb;
+            if (++stage == TC_NST) { stage = 0; ph ^= 1; }
           }
         }
       }
@@ -315,47 +315,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    // tcgen05.mma issue blocks while the previous MMA is still executing (the queue is ~1 deep), so
+    // everything else this thread does is interleaved BETWEEN the four MMA issues of a chunk, where it
+    // hides under the MMA in flight: in particular the wait for the NEXT chunk's weights.
     if (lane == 0) {
-      uint32_t it = 0, actph0 = 0, actph1 = 0;
+      uint32_t stage = 0, ph = 0, actph0 = 0, actph1 = 0;
+      bool waited = false;
       // descriptor templates; only the 14-bit start-address field changes (added in 16-byte units)
       const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
       const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
       for (int st = 0; st < nst; ++st) {
         const bool tr = p.trace && blockIdx.x == 0 && st == 1;
         ptx::mbar_wait(bar_encfull, st & 1);
-        ptx::tc_fence_after();
         for (int l = 0; l < NL; ++l) {
           const int nch = tc_layer_chunks(l, D, p.skip);
           const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
           const uint32_t idesc = ptx::umma_idesc_f16(128, (l == D + 1) ? 128 : 256);
-          for (int c = 0; c < nch; ++c, ++it) {
-            const uint32_t stage = it % TC_NST, ph = (it / TC_NST) & 1;
+          const bool last_layer = (st == nst - 1) && (l == NL - 1);
+          for (int c = 0; c < nch; ++c) {
             long long* trp = p.trace + 4 * (l * 10 + c);
             if (tr) trp[0] = clock64();
-            ptx::mbar_wait(bar_wfull + 8 * stage, ph);
+            if (!waited) ptx::mbar_wait(bar_wfull + 8 * stage, ph);
             ptx::tc_fence_after();
             if (tr) trp[1] = clock64();
             const bool is_enc = (l == 0) || (skip_layer && c < 2);
             const int kc = skip_layer ? c - 2 : c;
             const uint64_t bd = bdesc0 + ((SM_WRING + stage * TC_STAGE_BYTES) >> 4);
             const uint32_t a_off = is_enc ? (SM_ENC + c * 64) : (SM_ACT + (kc >> 1) * 16384 + (kc & 1) * 64);
-            const uint32_t a_step = is_enc ? 16384u : 65536u;
-#pragma unroll
-            for (int X = 0; X < 2; ++X) {
-              if (c == 0) {
-                uint32_t& aph = X ? actph1 : actph0;
-                ptx::mbar_wait(bar_act + 8 * X, aph);
-                aph ^= 1;
-                ptx::tc_fence_after();
-                if (tr && X == 1) trp[2] = clock64();
-              }
-              const uint64_t ad = adesc0 + ((a_off + X * a_step) >> 4);
-              ptx::mma_f16_ss(tmem + X * 256, ad, bd, idesc, (c > 0) ? 1u : 0u);
-              ptx::mma_f16_ss(tmem + X * 256, ad + 2, bd + 2, idesc, 1u);
-              if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
-            }
+            const uint64_t ad0 = adesc0 + (a_off >> 4);
+            const uint64_t ad1 = ad0 + ((is_enc ? 16384u : 65536u) >> 4);
+            const uint32_t nstage = (stage + 1 == TC_NST) ? 0 : stage + 1, nph = (stage + 1 == TC_NST) ? ph ^ 1 : ph;
+            if (c == 0) { ptx::mbar_wait(bar_act, actph0); actph0 ^= 1; ptx::tc_fence_after(); }
+            ptx::mma_f16_ss(tmem, ad0, bd, idesc, (c > 0) ? 1u : 0u);
+            waited = !(last_layer && c == nch - 1);
+            if (waited) ptx::mbar_wait(bar_wfull + 8 * nstage, nph);          // next chunk's weights
+            ptx::mma_f16_ss(tmem, ad0 + 2, bd + 2, idesc, 1u);
+            if (c == nch - 1) ptx::mma_commit(bar_dfull);
+            if (c == 0) { ptx::mbar_wait(bar_act + 8, actph1); actph1 ^= 1; ptx::tc_fence_after(); if (tr) trp[2] = clock64(); }
+            ptx::mma_f16_ss(tmem + 256, ad1, bd, idesc, (c > 0) ? 1u : 0u);
+            ptx::mma_f16_ss(tmem + 256, ad1 + 2, bd + 2, idesc, 1u);
+            if (c == nch - 1) ptx::mma_commit(bar_dfull + 8);
             ptx::mma_commit(bar_wempty + 8 * stage);
             if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
+            stage = nstage; ph = nph;
             if (tr) trp[3] = clock64();
           }
         }
