@@ -6,13 +6,13 @@
 // (:37-51), batchify (:27-34), Embedder.embed (run_nerf_helpers.py:36-45) and NeRF.forward
 // (:96-119).  sigma/rgb never leave the SM unless `raw` is requested.
 //
-// CTA = 640 threads, 1 CTA / SM, persistent over a contiguous range of whole rays:
+// CTA = 672 threads, 1 CTA / SM, persistent over a contiguous range of whole rays:
 //   warp 0      : weight producer   -- streams the pre-swizzled fp16 weight chunks (K=32 x N) from
 //                                      L2 into a 3-stage ring with cp.async.bulk (TMA engine)
-//   warp 1      : MMA issuer        -- one thread issues tcgen05.mma (M=128, N=256|128, K=16)
-//   warps 2-3   : sampler           -- o + d*z and sin/cos encoding for the NEXT 256-row super-tile
-//                                      (warp 2 also owns the TMEM allocation)
-//   warps 4-19  : epilogue          -- 2 tile slots x 8 warps: tcgen05.ld -> +bias -> ReLU -> fp16 ->
+//   warps 1-2   : MMA issuers       -- one thread per tile slot issues tcgen05.mma (M=128, N=256|128,
+//                                      K=16); warp 2 also owns the TMEM allocation
+//   warps 3-4   : sampler           -- o + d*z and sin/cos encoding for the NEXT 256-row super-tile
+//   warps 5-20  : epilogue          -- 2 tile slots x 8 warps: tcgen05.ld -> +bias -> ReLU -> fp16 ->
 //                                      st.shared into the next layer's A operand (128B swizzle);
 //                                      heads (alpha, rgb) on CUDA cores; warp-scan compositing
 // Two 128-row tiles (slots A, B) run in lock-step on the same weight chunk, each with its own
@@ -24,7 +24,7 @@
 
 namespace nb {
 
-constexpr int TC_THREADS = 640;              // 2 control + 2 sampler + 16 epilogue warps
+constexpr int TC_THREADS = 672;              // producer + 2 MMA issuers + 2 sampler + 16 epilogue warps
 constexpr int TC_SAMPLER_THREADS = 64;
 constexpr int TC_W = 256;                 // hidden width supported by the tensor-core path
 constexpr int TC_MAXD = 8;                // pts layers supported (bias table lives in smem)
@@ -245,7 +245,7 @@ __device__ __forceinline__ void add_bias32(const uint32_t (&v)[32], uint32_t bia
 
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
-__global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchParams p) {
+__global__ void __maxnreg__(96) march_tc_kernel(const MarchParams p) {
   uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f); st_release_shared(a_carry + CARRY_TURN, 0u);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < TC_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); }
+    for (int i = 0; i < TC_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 2); }
     for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 256); }
     ptx::mbar_init(bar_encfull, TC_SAMPLER_THREADS);
-    ptx::mbar_init(bar_encfree, 1);
+    ptx::mbar_init(bar_encfree, 2);
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
@@ -313,60 +313,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    // tcgen05.mma issue blocks while the previous MMA is still executing (the queue is ~1 deep), so
-    // everything else this thread does is interleaved BETWEEN the four MMA issues of a chunk, where it
-    // hides under the MMA in flight: in particular the wait for the NEXT chunk's weights.
+  } else if (warp == 1 || warp == 2) {
+    // =========================== MMA issuers (one per tile slot) ===========================
+    // A warp cannot overlap its own bookkeeping (mbarrier waits, commits) with its tcgen05.mma issue
+    // (measured: issue time is additive), so each tile slot has its own issuing warp: while one warp
+    // waits / commits, the other warp's MMAs keep the tensor pipe busy.  Accumulation order inside a
+    // slot is preserved because one thread issues all MMAs of that slot's accumulator.
     if (lane == 0) {
-      uint32_t stage = 0, ph = 0, actph0 = 0, actph1 = 0;
-      bool waited = false;
-      // descriptor templates; only the 14-bit start-address field changes (added in 16-byte units)
+      const int X = warp - 1;
+      uint32_t stage = 0, ph = 0, actph = 0;
       const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
       const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
+      const uint32_t d_tmem = tmem + X * 256;
       for (int st = 0; st < nst; ++st) {
-        const bool tr = p.trace && blockIdx.x == 0 && st == 1;
+        const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0;
         ptx::mbar_wait(bar_encfull, st & 1);
         for (int l = 0; l < NL; ++l) {
           const int nch = tc_layer_chunks(l, D, p.skip);
           const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
           const uint32_t idesc = ptx::umma_idesc_f16(128, (l == D + 1) ? 128 : 256);
-          const bool last_layer = (st == nst - 1) && (l == NL - 1);
           for (int c = 0; c < nch; ++c) {
             long long* trp = p.trace + 4 * (l * 10 + c);
             if (tr) trp[0] = clock64();
-            if (!waited) ptx::mbar_wait(bar_wfull + 8 * stage, ph);
-            ptx::tc_fence_after();
+            ptx::mbar_wait(bar_wfull + 8 * stage, ph);
             if (tr) trp[1] = clock64();
+            if (c == 0) { ptx::mbar_wait(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
+            ptx::tc_fence_after();
             const bool is_enc = (l == 0) || (skip_layer && c < 2);
             const int kc = skip_layer ? c - 2 : c;
             const uint64_t bd = bdesc0 + ((SM_WRING + stage * TC_STAGE_BYTES) >> 4);
-            const uint32_t a_off = is_enc ? (SM_ENC + c * 64) : (SM_ACT + (kc >> 1) * 16384 + (kc & 1) * 64);
-            const uint64_t ad0 = adesc0 + (a_off >> 4);
-            const uint64_t ad1 = ad0 + ((is_enc ? 16384u : 65536u) >> 4);
-            const uint32_t nstage = (stage + 1 == TC_NST) ? 0 : stage + 1, nph = (stage + 1 == TC_NST) ? ph ^ 1 : ph;
-            if (c == 0) { ptx::mbar_wait(bar_act, actph0); actph0 ^= 1; ptx::tc_fence_after(); }
-            ptx::mma_f16_ss(tmem, ad0, bd, idesc, (c > 0) ? 1u : 0u);
-            waited = !(last_layer && c == nch - 1);
-            if (waited) ptx::mbar_wait(bar_wfull + 8 * nstage, nph);          // next chunk's weights
-            ptx::mma_f16_ss(tmem, ad0 + 2, bd + 2, idesc, 1u);
-            if (c == nch - 1) ptx::mma_commit(bar_dfull);
-            if (c == 0) { ptx::mbar_wait(bar_act + 8, actph1); actph1 ^= 1; ptx::tc_fence_after(); if (tr) trp[2] = clock64(); }
-            ptx::mma_f16_ss(tmem + 256, ad1, bd, idesc, (c > 0) ? 1u : 0u);
-            ptx::mma_f16_ss(tmem + 256, ad1 + 2, bd + 2, idesc, 1u);
-            if (c == nch - 1) ptx::mma_commit(bar_dfull + 8);
+            const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
+            const uint64_t ad = adesc0 + (a_off >> 4);
+            ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (c > 0) ? 1u : 0u);
+            ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
             ptx::mma_commit(bar_wempty + 8 * stage);
             if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
-            stage = nstage; ph = nph;
+            if (++stage == TC_NST) { stage = 0; ph ^= 1; }
             if (tr) trp[3] = clock64();
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 5) {
     // =========================== epilogue ===========================
-    const int X = (warp - 4) >> 3, e = (warp - 4) & 7, q = e & 3, ch = e >> 2;
+    // TMEM lane quadrant is fixed by (warp id % 4); any 4 consecutive warps cover all quadrants
+    const int X = (warp - 5) >> 3, e = (warp - 5) & 7, q = warp & 3, ch = e >> 2;
     const int r = 32 * q + lane;                                  // tile row == TMEM lane
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + X * 256;
     const uint32_t act_base = sb + SM_ACT + X * 65536;
@@ -539,8 +532,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       }
     }
   } else {
-    // =========================== sampler (warps 2-3) ===========================
-    const int t = threadIdx.x - 64;                               // 0..63
+    // =========================== sampler (warps 3-4) ===========================
+    const int t = threadIdx.x - 96;                               // 0..63
     for (int st = 0; st < nst; ++st) {
       ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
 #pragma unroll 1
