@@ -6,13 +6,13 @@
 // (:37-51), batchify (:27-34), Embedder.embed (run_nerf_helpers.py:36-45) and NeRF.forward
 // (:96-119).  sigma/rgb never leave the SM unless `raw` is requested.
 //
-// CTA = 672 threads, 1 CTA / SM, persistent over a contiguous range of whole rays:
+// CTA = 640 threads, 1 CTA / SM, persistent over a contiguous range of whole rays:
 //   warp 0      : weight producer   -- streams the pre-swizzled fp16 weight chunks (K=32 x N) from
 //                                      L2 into a 3-stage ring with cp.async.bulk (TMA engine)
 //   warps 1-2   : MMA issuers       -- one thread per tile slot issues tcgen05.mma (M=128, N=256|128,
 //                                      K=16); warp 2 also owns the TMEM allocation
-//   warps 3-4   : sampler           -- o + d*z and sin/cos encoding for the NEXT 256-row super-tile
-//   warps 5-20  : epilogue          -- 2 tile slots x 8 warps: tcgen05.ld -> +bias -> ReLU -> fp16 ->
+//   warp 3      : sampler           -- o + d*z and sin/cos encoding for the NEXT 256-row super-tile
+//   warps 4-19  : epilogue          -- 2 tile slots x 8 warps: tcgen05.ld -> +bias -> ReLU -> fp16 ->
 //                                      st.shared into the next layer's A operand (128B swizzle);
 //                                      heads (alpha, rgb) on CUDA cores; warp-scan compositing
 // Two 128-row tiles (slots A, B) run in lock-step on the same weight chunk, each with its own
@@ -24,8 +24,8 @@
 
 namespace nb {
 
-constexpr int TC_THREADS = 672;              // producer + 2 MMA issuers + 2 sampler + 16 epilogue warps
-constexpr int TC_SAMPLER_THREADS = 64;
+constexpr int TC_THREADS = 640;              // producer + 2 MMA issuers + 1 sampler + 16 epilogue warps
+constexpr int TC_SAMPLER_THREADS = 32;       // (register allocation is per 4 warps: 20 warps x 96 regs fit)
 constexpr int TC_W = 256;                 // hidden width supported by the tensor-core path
 constexpr int TC_MAXD = 8;                // pts layers supported (bias table lives in smem)
 constexpr int TC_TILE = 128;              // rows per MMA tile
@@ -245,7 +245,7 @@ __device__ __forceinline__ void add_bias32(const uint32_t (&v)[32], uint32_t bia
 
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
-__global__ void __maxnreg__(96) march_tc_kernel(const MarchParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchParams p) {
   uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -356,10 +356,10 @@ __global__ void __maxnreg__(96) march_tc_kernel(const MarchParams p) {
       }
     }
     __syncwarp();
-  } else if (warp >= 5) {
+  } else if (warp >= 4) {
     // =========================== epilogue ===========================
-    // TMEM lane quadrant is fixed by (warp id % 4); any 4 consecutive warps cover all quadrants
-    const int X = (warp - 5) >> 3, e = (warp - 5) & 7, q = warp & 3, ch = e >> 2;
+    // TMEM lane quadrant is fixed by (warp id % 4)
+    const int X = (warp - 4) >> 3, e = (warp - 4) & 7, q = warp & 3, ch = e >> 2;
     const int r = 32 * q + lane;                                  // tile row == TMEM lane
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + X * 256;
     const uint32_t act_base = sb + SM_ACT + X * 65536;
@@ -532,13 +532,13 @@ __global__ void __maxnreg__(96) march_tc_kernel(const MarchParams p) {
       }
     }
   } else {
-    // =========================== sampler (warps 3-4) ===========================
-    const int t = threadIdx.x - 96;                               // 0..63
+    // =========================== sampler (warp 3) ===========================
+    const int t = threadIdx.x - 96;                               // 0..31
     for (int st = 0; st < nst; ++st) {
       ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int X = i >> 1, tr_ = t + 64 * (i & 1);             // tile slot, tile row
+      for (int i = 0; i < 8; ++i) {
+        const int X = i >> 2, tr_ = t + 32 * (i & 3);             // tile slot, tile row
         const int lr = st * TC_ST + X * TC_TILE + tr_;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (lr < nrows) {
