@@ -358,6 +358,14 @@ int nerf_b200_debug_epi_rate(int reps, int mode, int mma, void* out_2_i64, void*
   return 0;
 }
 
+int nerf_b200_debug_ldtm_rate(int reps, int shape, int nwarps, int mma, void* out_2_i64, void* stream) {
+  const size_t sm = 49152 + 256 + 1024;
+  if (int rc = smem_optin((const void*)ldtm_rate_kernel, sm)) return rc;
+  ldtm_rate_kernel<<<1, 384, sm, (cudaStream_t)stream>>>(reps, shape, nwarps, mma, static_cast<long long*>(out_2_i64));
+  NB_LAUNCH_OK("ldtm_rate_kernel");
+  return 0;
+}
+
 int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch, size_t scratch_bytes, void* stream) {
   NB_CHECK_ARG(A && W && out && scratch, "NULL pointer");
   NB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 256 && (N == 128 || N == 256), "bad K/N");

@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     if (lane == 0) {
       const int X = warp - 1;
       uint32_t stage = 0, ph = 0, actph = 0;
+      bool ready = false;                                // w_full of the current chunk already observed
       const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
       const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
       const uint32_t d_tmem = tmem + X * 256;
@@ -332,10 +333,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           const int nch = tc_layer_chunks(l, D, p.skip);
           const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
           const uint32_t idesc = ptx::umma_idesc_f16(128, (l == D + 1) ? 128 : 256);
+          const bool last_layer = (st == nst - 1) && (l == NL - 1);
           for (int c = 0; c < nch; ++c) {
             long long* trp = p.trace + 4 * (l * 10 + c);
             if (tr) trp[0] = clock64();
-            ptx::mbar_wait(bar_wfull + 8 * stage, ph);
+            if (!ready) ptx::mbar_wait(bar_wfull + 8 * stage, ph);
             if (tr) trp[1] = clock64();
             if (c == 0) { ptx::mbar_wait(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
             ptx::tc_fence_after();
@@ -344,12 +346,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
             const uint64_t bd = bdesc0 + ((SM_WRING + stage * TC_STAGE_BYTES) >> 4);
             const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
             const uint64_t ad = adesc0 + (a_off >> 4);
+            const uint32_t nstage = (stage + 1 == TC_NST) ? 0u : stage + 1, nph = (stage + 1 == TC_NST) ? ph ^ 1u : ph;
+            // probe the NEXT chunk's weights now; the answer arrives while the MMAs below are issued
+            const bool nready = !(last_layer && c == nch - 1) && ptx::mbar_try_wait(bar_wfull + 8 * nstage, nph);
             ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (c > 0) ? 1u : 0u);
             ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
             if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
             ptx::mma_commit(bar_wempty + 8 * stage);
             if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
-            if (++stage == TC_NST) { stage = 0; ph ^= 1; }
+            stage = nstage; ph = nph; ready = nready;
             if (tr) trp[3] = clock64();
           }
         }
@@ -760,6 +765,103 @@ __global__ void __launch_bounds__(384, 1) epi_rate_kernel(int reps, int mode, in
     const long long t1 = clock64();
     if (e == 0 && lane == 0) { out[0] = t1 - t0; out[1] = ldw; *s_stop = 1; }
     if (sink == 123.456f) out[1] = 1;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+// TMEM -> register load-rate probe.  `nwarps` warps (4 or 8) each drain their share of a 128-lane x 256-column
+// fp32 accumulator `reps` times with the given tcgen05.ld shape; values are xor-folded so nothing spills.
+//   shape 0: 32x32b.x32 (one load in flight)   1: 32x32b.x32, two loads per wait   2: 32x32b.x64
+//   shape 3: 16x256b.x8 (two per 32-lane group) 4: 16x128b.x16                     5: 32x32b.x16, 4 per wait
+#define NB_LDTM(SHAPE, NREG, ...) asm volatile("tcgen05.ld.sync.aligned." SHAPE ".b32 {" __VA_ARGS__ "}, [%" #NREG "];"
+__device__ __forceinline__ uint32_t fold32(const uint32_t (&v)[32]) { uint32_t a = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) a ^= v[i]; return a; }
+__device__ __forceinline__ void ldtm_16x256b_x8(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void ldtm_16x128b_x16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void ldtm_32x32b_x16(uint32_t taddr, uint32_t (&v)[32], int o) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]),
+        "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])
+      : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(384, 1) ldtm_rate_kernel(int reps, int shape, int nwarps, int mma, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t OPS = 0, BAR = 49152, TPTR = BAR + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TPTR);
+  volatile int* s_stop = reinterpret_cast<volatile int*>(smem + TPTR + 16);
+  for (int i = threadIdx.x; i < 49152 / 4; i += 384) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { ptx::mbar_init(sb + BAR, 1); ptx::fence_mbar_init(); *s_stop = 0; }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  if (warp == 1) {
+    if (lane == 0 && mma) {
+      const uint32_t idesc = ptx::umma_idesc_f16(128, 256);
+      int i = 0;
+      while (!*s_stop) {
+        for (int j = 0; j < 8; ++j, ++i)
+          ptx::mma_f16_ss(tmem + 256, ptx::umma_desc(sb + OPS + (i & 1) * 32, 1024, ptx::UMMA_SW128),
+                          ptx::umma_desc(sb + OPS + 16384 + (i & 1) * 32, 512, ptx::UMMA_SW64), idesc, 1u);
+        ptx::mma_commit(sb + BAR);
+        ptx::mbar_wait(sb + BAR, (i / 8 - 1) & 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 4 + nwarps) {
+    const int e = warp - 4, q = warp & 3, ch = e >> 2;
+    const int ncol = (nwarps == 8) ? 128 : 256, col_base = (nwarps == 8) ? ch * 128 : 0;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + col_base;
+    uint32_t acc = 0;
+    ptx::named_bar_sync(1, nwarps * 32);
+    const long long t0 = clock64();
+    for (int it = 0; it < reps; ++it) {
+      if (shape == 0) {
+#pragma unroll 1
+        for (int c = 0; c < ncol; c += 32) { uint32_t v[32]; ptx::tmem_ld_x32(t_lane + c, v); ptx::tmem_ld_wait(); acc ^= fold32(v); }
+      } else if (shape == 1) {
+#pragma unroll 1
+        for (int c = 0; c < ncol; c += 64) { uint32_t v[32], w[32]; ptx::tmem_ld_x32(t_lane + c, v); ptx::tmem_ld_x32(t_lane + c + 32, w); ptx::tmem_ld_wait(); acc ^= fold32(v) ^ fold32(w); }
+      } else if (shape == 3) {
+#pragma unroll 1
+        for (int c = 0; c < ncol; c += 64) { uint32_t v[32], w[32]; ldtm_16x256b_x8(t_lane + c, v); ldtm_16x256b_x8(t_lane + (16u << 16) + c, w); ptx::tmem_ld_wait(); acc ^= fold32(v) ^ fold32(w); }
+      } else if (shape == 4) {
+#pragma unroll 1
+        for (int c = 0; c < ncol; c += 64) { uint32_t v[32], w[32]; ldtm_16x128b_x16(t_lane + c, v); ldtm_16x128b_x16(t_lane + (16u << 16) + c, w); ptx::tmem_ld_wait(); acc ^= fold32(v) ^ fold32(w); }
+      } else if (shape == 5) {
+#pragma unroll 1
+        for (int c = 0; c < ncol; c += 64) { uint32_t v[32], w[32]; ldtm_32x32b_x16(t_lane + c, v, 0); ldtm_32x32b_x16(t_lane + c + 16, v, 16); ldtm_32x32b_x16(t_lane + c + 32, w, 0); ldtm_32x32b_x16(t_lane + c + 48, w, 16); ptx::tmem_ld_wait(); acc ^= fold32(v) ^ fold32(w); }
+      }
+    }
+    const long long t1 = clock64();
+    ptx::named_bar_sync(1, nwarps * 32);
+    if (e == 0 && lane == 0) { out[0] = t1 - t0; *s_stop = 1; }
+    if (acc == 0x12345u) out[1] = acc;
   }
   ptx::tc_fence_before();
   __syncthreads();
