@@ -218,6 +218,26 @@ __device__ __forceinline__ void store_act32(const float (&x)[32], uint32_t act_b
   }
 }
 
+// Same, with the 8 swizzled 16-byte-chunk addresses of this thread's row precomputed once
+// (sw[c] = tile base + row offset + ((c ^ (r & 7)) << 4)): every store is [register + immediate].
+template <bool RELU, int COL0>
+__device__ __forceinline__ void store_act32_pre(const float (&x)[32], const uint32_t (&sw)[8]) {
+  constexpr uint32_t kb = (uint32_t)(COL0 >> 6) * 16384u;
+  constexpr int c16_0 = (COL0 & 63) >> 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t h0, h1, h2, h3;
+    if (RELU) {
+      h0 = ptx::cvt_relu_f16x2(x[g * 8 + 0], x[g * 8 + 1]); h1 = ptx::cvt_relu_f16x2(x[g * 8 + 2], x[g * 8 + 3]);
+      h2 = ptx::cvt_relu_f16x2(x[g * 8 + 4], x[g * 8 + 5]); h3 = ptx::cvt_relu_f16x2(x[g * 8 + 6], x[g * 8 + 7]);
+    } else {
+      h0 = ptx::cvt_f16x2(x[g * 8 + 0], x[g * 8 + 1]); h1 = ptx::cvt_f16x2(x[g * 8 + 2], x[g * 8 + 3]);
+      h2 = ptx::cvt_f16x2(x[g * 8 + 4], x[g * 8 + 5]); h3 = ptx::cvt_f16x2(x[g * 8 + 6], x[g * 8 + 7]);
+    }
+    ptx::st_shared_v4(sw[c16_0 + g] + kb, h0, h1, h2, h3);
+  }
+}
+
 // segmented (per-ray) inclusive scans over one warp; `s` = lane of the segment start at or before
 // this lane inside the warp, or -1 when the segment began in an earlier warp.
 __device__ __forceinline__ float seg_scan_mul(float v, int lane, int s) {
@@ -370,6 +390,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     const uint32_t act_base = sb + SM_ACT + X * 65536;
     ptx::mbar_arrive(bar_act + 8 * X);                            // accumulator initially free
     uint32_t dph = 0;
+    // swizzled 16-byte-chunk addresses of this thread's row in the two K-blocks of its column half
+    uint32_t swk[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) swk[c] = act_base + (uint32_t)(ch * 2) * 16384u + act_row_off(r) + (uint32_t)((c ^ (r & 7)) << 4);
     for (int st = 0; st < nst; ++st) {
       float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f, hp3 = 0.f;           // head partial sums of this thread's columns
       const int lr = st * TC_ST + X * TC_TILE + r;                // row index inside this CTA's range
@@ -423,8 +447,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
               }
             }
             if (write_act) {
-              if (l < D) store_act32<true>(x, act_base, r, col0);
-              else store_act32<false>(x, act_base, r, col0);
+              // (b & 1) selects the K-block inside the column half; ch selects the half: the
+              // immediate part of the address is compile-time, the row/swizzle part is in sw[]
+              if (l < D) {
+                if (b == 0) store_act32_pre<true, 0>(x, swk); else if (b == 1) store_act32_pre<true, 32>(x, swk);
+                else if (b == 2) store_act32_pre<true, 64>(x, swk); else store_act32_pre<true, 96>(x, swk);
+              } else {
+                if (b == 0) store_act32_pre<false, 0>(x, swk); else if (b == 1) store_act32_pre<false, 32>(x, swk);
+                else if (b == 2) store_act32_pre<false, 64>(x, swk); else store_act32_pre<false, 96>(x, swk);
+              }
             }
           }
           ptx::tc_fence_before();
