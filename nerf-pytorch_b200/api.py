@@ -408,7 +408,7 @@ def _grad_buffers(net: NeRF):
 
 class _RenderRays(torch.autograd.Function):
     """Forward: nerf_b200_render_rays_fwd (coarse z -> fused pass -> resample -> fused pass).
-    Backward: nerf_b200_march_bwd per pass (recompute), gradients w.r.t. rgb_map and rgb0 only --
+    Backward: nerf_b200_march_bwd per pass (fp32 recompute + GEMM backprop), gradients w.r.t. rgb_map and rgb0 only --
     exactly the terms of the reference's loss (run_nerf.py:765-772); z_samples is detached in the
     reference (:394) so nothing flows through the resampling."""
 
@@ -493,7 +493,7 @@ class _RenderRays(torch.autograd.Function):
             ws_bytes = lib.nerf_b200_march_bwd_workspace_bytes(N, S)
             ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=z.device)
             check(lib.nerf_b200_march_bwd(_ptr(ray_batch), _ptr(z), _ptr(noise if noise.numel() else None), N, S,
-                                          C.byref(n), _ptr(net.packed()), C.byref(cfg), _ptr(g_rgb.contiguous().float()),
+                                          C.byref(n), _ptr(None), C.byref(cfg), _ptr(g_rgb.contiguous().float()),
                                           C.byref(gs), _ptr(ws), ws_bytes, _stream(z)), "march_bwd")
         out = [None] * 8
         out += [grads_c[k] for k, _ in net_c.named_parameters()]

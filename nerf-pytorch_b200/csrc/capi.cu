@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include "common.cuh"
 #include "small_kernels.cuh"
+#include "bwd_simt.cuh"
 #include "mlp_simt.cuh"
 #include "fused_tc.cuh"
 
@@ -200,7 +201,7 @@ int nerf_b200_run_network(const float* pts, const float* viewdirs, int64_t N, in
     const long long M = N * (long long)S;
     const size_t sm = simt_smem_bytes(*net);
     if (int rc = smem_optin((const void*)mlp_simt_kernel, sm)) return rc;
-    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, viewdirs, 3, M, S, *net, multires, multires_views, raw);
+    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, viewdirs, 3, M, S, *net, multires, multires_views, raw, SimtSave{});
     NB_LAUNCH_OK("mlp_simt_kernel");
     return 0;
   }
@@ -297,7 +298,7 @@ int nerf_b200_march(const float* rays, const float* z_vals, const float* noise, 
     NB_LAUNCH_OK("pts_kernel");
     const size_t sm = simt_smem_bytes(*net);
     if (int rc = smem_optin((const void*)mlp_simt_kernel, sm)) return rc;
-    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, rays + 8, cfg->ray_stride, M, S, *net, cfg->multires, cfg->multires_views, raw);
+    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, rays + 8, cfg->ray_stride, M, S, *net, cfg->multires, cfg->multires_views, raw, SimtSave{});
     NB_LAUNCH_OK("mlp_simt_kernel");
     raw2outputs_kernel<<<cdiv(N * 32, 256), 256, 0, st>>>(raw, z_vals, rays + 3, cfg->ray_stride, noise, N, S, cfg->white_bkgd, *out);
     NB_LAUNCH_OK("raw2outputs_kernel");
@@ -334,10 +335,112 @@ int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg*
   return nerf_b200_march(rays, z_fine, noise1, N, Sc + Ni, nf, pf, cfg, fine, workspace, workspace_bytes, stream);
 }
 
-size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S) { (void)N; (void)S; return 0; }
-int nerf_b200_march_bwd(const float*, const float*, const float*, int64_t, int, const NerfNetParams*, const void*,
-                        const NerfRenderCfg*, const float*, const NerfNetGrads*, void*, size_t, void*) {
-  return nb::set_error(-6, "nerf_b200_march_bwd: not built yet");
+// ---- exact-mode backward of one pass (see bwd_simt.cuh) -------------------------------------------
+static const int BWD_RAYS_PER_SLAB = 512;     // rays recomputed + back-propagated per slab (bounds the workspace)
+
+size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S) {
+  const long long rows = (long long)(N < BWD_RAYS_PER_SLAB ? N : BWD_RAYS_PER_SLAB) * S;
+  return (size_t)rows * (63 + 63 + 16 * 256 + 256 + 128 + 8 + 512 + 128 + 3) * 4 + 1024;   // upper bound over supported nets
+}
+
+static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int N, int K, int beta, cudaStream_t st) {
+  dim3 grid(cdiv(M, GT), cdiv(N, GT));
+  sgemm_nn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, beta);
+  NB_LAUNCH_OK("sgemm_nn_kernel");
+  return 0;
+}
+static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int K1, int N, cudaStream_t st) {
+  const int slab = 2048;
+  dim3 grid(cdiv(K1, GT), cdiv(N, GT), cdiv(M, slab));
+  sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, K1, N, slab);
+  NB_LAUNCH_OK("sgemm_tn_kernel");
+  return 0;
+}
+static int mask_colsum(float* d, int ldd, const float* h, int ldh, long long M, int C, float* colsum, cudaStream_t st) {
+  const int rpb = 256;
+  dim3 grid(cdiv(M, rpb), cdiv(C, 64));
+  relu_mask_colsum_kernel<<<grid, 64, 0, st>>>(d, ldd, h, ldh, M, C, colsum, rpb);
+  NB_LAUNCH_OK("relu_mask_colsum_kernel");
+  return 0;
+}
+#define NB_TRY(expr) do { if (int rc__ = (expr)) return rc__; } while (0)
+
+int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
+                        const void* packed, const NerfRenderCfg* cfg, const float* g_rgb, const NerfNetGrads* grads,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  (void)packed;
+  NB_CHECK_ARG(rays && z_vals && net && cfg && g_rgb && grads, "NULL pointer");
+  NB_CHECK_ARG(net->use_viewdirs, "backward is implemented for use_viewdirs networks (the reference's shipped configs)");
+  NB_CHECK_ARG(net->W <= SIMT_THREADS && net->W % 4 == 0 && net->D <= NERF_B200_MAX_D, "unsupported network shape");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = net->W, W2 = W / 2, IC = net->input_ch, ICV = net->input_ch_views, D = net->D, rs = cfg->ray_stride;
+  NB_CHECK_ARG(workspace && workspace_bytes >= nerf_b200_march_bwd_workspace_bytes(N, S), "march_bwd workspace too small");
+  for (int64_t n0 = 0; n0 < N; n0 += BWD_RAYS_PER_SLAB) {
+    const int64_t nn = (N - n0 < BWD_RAYS_PER_SLAB) ? N - n0 : BWD_RAYS_PER_SLAB;
+    const long long M = nn * (long long)S;
+    const float* ry = rays + n0 * rs;
+    const float* zz = z_vals + n0 * S;
+    const float* nz = noise ? noise + n0 * S : nullptr;
+    float* p = static_cast<float*>(workspace);
+    float* pts = p;        p += M * 3;
+    SimtSave sv;
+    sv.enc = p;            p += M * IC;
+    sv.encv = p;           p += M * ICV;
+    sv.h = p;              p += (size_t)D * M * W;
+    sv.feat = p;           p += M * W;
+    sv.hv = p;             p += M * W2;
+    float* raw = p;        p += M * 4;
+    float* d_raw = p;      p += M * 4;
+    float* dh0 = p;        p += M * W;
+    float* dh1 = p;        p += M * W;
+    float* d_hv = p;       p += M * W2;
+    // 1. recompute the pass in fp32 with saved activations
+    pts_kernel<<<cdiv(M, 256), 256, 0, st>>>(ry, rs, zz, M, S, pts);
+    NB_LAUNCH_OK("pts_kernel");
+    const size_t sm = simt_smem_bytes(*net);
+    NB_TRY(smem_optin((const void*)mlp_simt_kernel, sm));
+    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, ry + 8, rs, M, S, *net, cfg->multires, cfg->multires_views, raw, sv);
+    NB_LAUNCH_OK("mlp_simt_kernel");
+    // 2. compositing adjoint -> dL/draw
+    NB_TRY(nerf_b200_raw2outputs_bwd(raw, zz, ry + 3, rs, nz, nn, S, cfg->white_bkgd, g_rgb + n0 * 3, d_raw, stream));
+    const float* h_last = sv.h + (size_t)(D - 1) * M * W;
+    // 3. rgb_linear (run_nerf_helpers.py:114)
+    NB_TRY(gemm_tn(d_raw, 4, sv.hv, W2, grads->rgb_w, W2, M, 3, W2, st));
+    NB_TRY(mask_colsum(d_raw, 4, nullptr, 0, M, 3, grads->rgb_b, st));
+    NB_TRY(gemm_nn(d_raw, 4, net->rgb_w, W2, d_hv, W2, M, W2, 3, 0, st));
+    // 4. views_linears[0] on cat([feature, input_views]) (:108-112)
+    NB_TRY(mask_colsum(d_hv, W2, sv.hv, W2, M, W2, grads->views_b, st));
+    NB_TRY(gemm_tn(d_hv, W2, sv.feat, W, grads->views_w, W + ICV, M, W2, W, st));
+    NB_TRY(gemm_tn(d_hv, W2, sv.encv, ICV, grads->views_w + W, W + ICV, M, W2, ICV, st));
+    NB_TRY(gemm_nn(d_hv, W2, net->views_w, W + ICV, dh0, W, M, W, W2, 0, st));                // d_feature
+    // 5. feature_linear and alpha_linear both read the last hidden layer (:106-107)
+    NB_TRY(gemm_tn(dh0, W, h_last, W, grads->feature_w, W, M, W, W, st));
+    NB_TRY(mask_colsum(dh0, W, nullptr, 0, M, W, grads->feature_b, st));
+    NB_TRY(gemm_tn(d_raw + 3, 4, h_last, W, grads->alpha_w, W, M, 1, W, st));
+    NB_TRY(mask_colsum(d_raw + 3, 4, nullptr, 0, M, 1, grads->alpha_b, st));
+    NB_TRY(gemm_nn(dh0, W, net->feature_w, W, dh1, W, M, W, W, 0, st));
+    NB_TRY(gemm_nn(d_raw + 3, 4, net->alpha_w, W, dh1, W, M, W, 1, 1, st));
+    // 6. pts_linears, last to first (:99-103); skip layer input = cat([input_pts, h])
+    float* dcur = dh1;
+    float* dnext = dh0;
+    for (int l = D - 1; l >= 0; --l) {
+      NB_TRY(mask_colsum(dcur, W, sv.h + (size_t)l * M * W, W, M, W, grads->pts_b[l], st));
+      const bool after_skip = (l > 0) && (l - 1 == net->skip);
+      const int Kl = (l == 0) ? IC : (after_skip ? W + IC : W);
+      if (l == 0) {
+        NB_TRY(gemm_tn(dcur, W, sv.enc, IC, grads->pts_w[0], Kl, M, W, IC, st));
+      } else {
+        const float* hprev = sv.h + (size_t)(l - 1) * M * W;
+        const int off = after_skip ? IC : 0;
+        if (after_skip) NB_TRY(gemm_tn(dcur, W, sv.enc, IC, grads->pts_w[l], Kl, M, W, IC, st));
+        NB_TRY(gemm_tn(dcur, W, hprev, W, grads->pts_w[l] + off, Kl, M, W, W, st));
+        NB_TRY(gemm_nn(dcur, W, net->pts_w[l] + off, Kl, dnext, W, M, W, W, 0, st));
+        float* t = dcur; dcur = dnext; dnext = t;
+      }
+    }
+  }
+  return 0;
 }
 
 int nerf_b200_debug_set_trace(void* dev_buf_4096_i64) { g_trace = static_cast<long long*>(dev_buf_4096_i64); return 0; }

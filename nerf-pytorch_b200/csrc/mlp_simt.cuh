@@ -3,6 +3,7 @@
 // validation / "exact" path (NERF_B200_PREC_FP32); the production path is fused_tc.cuh.
 #pragma once
 #include "common.cuh"
+#include "bwd_simt.cuh"
 
 namespace nb {
 
@@ -38,7 +39,7 @@ __device__ __forceinline__ void simt_store(const float (&acc)[SIMT_ROWS], float*
 // pts [M,3] (M = N*S), viewdirs [N,3] or NULL, raw [M,4]
 __global__ void __launch_bounds__(SIMT_THREADS)
 mlp_simt_kernel(const float* __restrict__ pts, const float* __restrict__ viewdirs, int dir_stride, long long M, int S,
-                NerfNetParams net, int L, int Lv, float* __restrict__ raw) {
+                NerfNetParams net, int L, int Lv, float* __restrict__ raw, SimtSave sv) {
   extern __shared__ __align__(16) float smem[];
   const int W = net.W, IC = net.input_ch, ICV = net.input_ch_views;
   float* s_enc = smem;                                  // [IC][ROWS]
@@ -47,6 +48,14 @@ mlp_simt_kernel(const float* __restrict__ pts, const float* __restrict__ viewdir
   float* s_h1 = s_h0 + W * SIMT_ROWS;                   // [W][ROWS]
   const int tid = threadIdx.x;
   const long long row0 = (long long)blockIdx.x * SIMT_ROWS;
+  // save a [C][ROWS] shared-memory block as rows of a row-major [M, C] global matrix (training only)
+  auto save_rows = [&](float* dst, const float* s_src, int C) {
+    if (dst == nullptr) return;
+    for (int i = tid; i < C * SIMT_ROWS; i += SIMT_THREADS) {
+      int r = i / C, c = i - r * C;
+      if (row0 + r < M) dst[(row0 + r) * C + c] = s_src[c * SIMT_ROWS + r];
+    }
+  };
 
   // ---- positional encoding (run_nerf_helpers.py:36-45) ----
   for (int i = tid; i < IC * SIMT_ROWS; i += SIMT_THREADS) {
@@ -71,6 +80,8 @@ mlp_simt_kernel(const float* __restrict__ pts, const float* __restrict__ viewdir
     s_encv[i] = v;
   }
   __syncthreads();
+  save_rows(sv.enc, s_enc, IC);
+  save_rows(sv.encv, s_encv, ICV);
 
   float acc[SIMT_ROWS];
   float* h_in = s_h0;
@@ -91,6 +102,7 @@ mlp_simt_kernel(const float* __restrict__ pts, const float* __restrict__ viewdir
       simt_store(acc, h_out + n * SIMT_ROWS, true);
     }
     __syncthreads();
+    save_rows(sv.h ? sv.h + (size_t)i * M * W : nullptr, h_out, W);
     float* t = h_in; h_in = h_out; h_out = t;
   }
   // h_in now holds h of the last pts layer
@@ -110,6 +122,7 @@ mlp_simt_kernel(const float* __restrict__ pts, const float* __restrict__ viewdir
       simt_store(acc, h_out + n * SIMT_ROWS, false);
     }
     __syncthreads();
+    save_rows(sv.feat, h_out, W);
     // views_linears[0] on cat([feature, input_views]) (:108-112)
     const int W2 = W / 2;
     if (n < W2) {
@@ -122,6 +135,7 @@ mlp_simt_kernel(const float* __restrict__ pts, const float* __restrict__ viewdir
       simt_store(acc, h_in + n * SIMT_ROWS, true);       // h_in is free (alpha/feature already read) ...
     }
     __syncthreads();
+    save_rows(sv.hv, h_in, W2);
     // rgb (:114) and output cat([rgb, alpha]) (:115)
     if (tid < SIMT_ROWS) {
       long long m = row0 + tid;
