@@ -1,0 +1,82 @@
+"""2-GPU NCCL tests (skipped on a single-GPU box): ray-sharded render == single-GPU render bit for bit,
+data-parallel all-reduced gradients == single-GPU gradients on the concatenated batch."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import nerf_pytorch_b200 as nb
+    from nerf_pytorch_b200 import dist as nd
+    from nerf_pytorch_b200.api import _QueryFn
+    from oracle import synth
+    dev = torch.device("cuda", rank)
+    def nets():
+        out = []
+        for seed in (0, 1):
+            m = nb.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.nerf_state(seed).items()}); out.append(m.to(dev))
+        return out
+    e, _ = nb.get_embedder(10, 0); ed, _ = nb.get_embedder(4, 0); q_fn = _QueryFn(e, ed, 65536, 10, 4, 0)
+    N = 512
+    sb = synth.ray_batch("lego", N, seed=9)
+    rays = torch.from_numpy(sb["rays"]).to(dev)
+    n1 = nets()
+    kw = dict(H=400, W=400, K=sb["K"], ndc=False, near=2., far=6., use_viewdirs=True, network_fn=n1[0], network_fine=n1[1],
+              network_query_fn=q_fn, N_samples=64, N_importance=128, perturb=0., white_bkgd=True, raw_noise_std=0.)
+    with torch.no_grad():
+        full = nb.render(rays=rays, **kw)
+        rgb, disp, acc, _ = nd.render_sharded(lambda rays, **k: nb.render(rays=rays, **k), rays, **kw)
+    ok_render = torch.equal(rgb, full[0]) and torch.equal(acc, full[2])
+    # data parallel: each rank takes N/world rays, local mean loss, one flat all-reduce (averaged)
+    target = torch.from_numpy(np.random.default_rng(1).random((N, 3), dtype=np.float32)).to(dev)
+    lo, hi = nd.shard_bounds(N, rank, world)
+    rgb_l, _, _, ex = nb.render(rays=rays[:, lo:hi], **kw)
+    loss = nb.img2mse(rgb_l, target[lo:hi]) + nb.img2mse(ex["rgb0"], target[lo:hi])
+    loss.backward()
+    params = list(n1[0].parameters()) + list(n1[1].parameters())
+    nd.allreduce_grads(params, average=True)
+    n2 = nets()
+    kw2 = dict(kw); kw2.update(network_fn=n2[0], network_fine=n2[1])
+    rgb_f, _, _, exf = nb.render(rays=rays, **kw2)
+    (nb.img2mse(rgb_f, target) + nb.img2mse(exf["rgb0"], target)).backward()
+    worst = 0.0
+    for a, b in zip(params, list(n2[0].parameters()) + list(n2[1].parameters())):
+        worst = max(worst, float((a.grad - b.grad).norm() / (b.grad.norm() + 1e-30)))
+    q.put((rank, ok_render, worst))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_render_and_dp_gradients():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    for rank, ok_render, worst in res:
+        assert ok_render, f"rank {rank}: sharded render differs from the single-GPU render"
+        assert worst < 2e-4, f"rank {rank}: all-reduced gradients differ ({worst})"      # fp32 atomics / reduction order
