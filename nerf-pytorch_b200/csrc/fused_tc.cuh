@@ -38,13 +38,14 @@ constexpr uint32_t TC_STAGE_BYTES = 256 * TC_CHUNK_K * 2;   // 16 KB
 constexpr uint32_t SM_ACT = 0;                                  // 2 x 64 KB  A operand (4 K-blocks x 16 KB)
 constexpr uint32_t SM_ENC = 131072;                             // 2 x 16 KB  encoded inputs (1 K-block)
 constexpr uint32_t SM_WRING = 163840;                           // 3 x 16 KB  weight ring
-constexpr uint32_t SM_BIAS = 212992;                            // (TC_MAXD+1) x 256 fp32
-constexpr uint32_t SM_HEADS = SM_BIAS + (TC_MAXD + 1) * 1024;   // 222208: head weights, 4128 B
-constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 226336: 2 x 128 x float4 partials
-constexpr uint32_t SM_BARS = SM_PART + 4096;                    // 230432: mbarriers
-constexpr uint32_t SM_MISC = SM_BARS + 256;                     // 230688: tmem ptr, compositing carry
-constexpr uint32_t SM_TOTAL = SM_MISC + 128;                    // 230816
-constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                  // + alignment slack = 231840 <= 232448
+constexpr uint32_t SM_ONES = 212992;                            // 4 KB: 128 rows x K=16 constant A slab [1,1,0..] (SWIZZLE_32B)
+constexpr uint32_t SM_HEADS = SM_ONES + 4096;                   // 217088: head weights, 4128 B
+constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 221216: 2 x 128 x float4 partials
+constexpr uint32_t SM_BARS = SM_PART + 4096;                    // 225312: mbarriers
+constexpr uint32_t SM_MISC = SM_BARS + 256;                     // 225568: tmem ptr, compositing carry
+constexpr uint32_t SM_TOTAL = SM_MISC + 128;                    // 225696
+constexpr uint32_t SM_ALLOC = SM_TOTAL;                         // dynamic smem base is 1024-aligned (checked at run time)
+constexpr uint32_t TC_BIAS_CHUNK_BYTES = 256 * 32;              // [256 rows x K=16] fp16 bias chunk (hi, lo, 0...)
 
 // heads region (floats): viewdirs: alpha_w[256] rgb_w[3][128] alpha_b rgb_b[3]; else output_w[4][256] output_b[4]
 constexpr int HEADS_FLOATS = 1032;
@@ -64,13 +65,20 @@ __host__ __device__ inline int tc_layer_chunks(int l, int D, int skip) {
   return 8;
 }
 __host__ __device__ inline uint32_t tc_layer_chunk_bytes(int l, int D) { return (l == D + 1) ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES; }
+// every layer but the view layer (whose bias is per ray) starts with a bias chunk: one K=16 MMA of a
+// constant-one A slab against [bias_hi, bias_lo, 0...] initialises the accumulator with the bias
+__host__ __device__ inline bool tc_layer_has_bias(int l, int D) { return l != D + 1; }
 
 static inline PackLayout make_pack_layout(const NerfNetParams& n) {
   PackLayout L;
   L.D = n.D; L.skip = n.skip; L.use_viewdirs = n.use_viewdirs; L.IC = n.input_ch; L.ICV = n.input_ch_views;
   L.NL = n.D + (n.use_viewdirs ? 2 : 0);
   L.n_chunks = 0; L.chunk_bytes = 0;
-  for (int l = 0; l < L.NL; ++l) { int c = tc_layer_chunks(l, n.D, n.skip); L.n_chunks += c; L.chunk_bytes += (size_t)c * tc_layer_chunk_bytes(l, n.D); }
+  for (int l = 0; l < L.NL; ++l) {
+    int c = tc_layer_chunks(l, n.D, n.skip);
+    L.n_chunks += c;
+    L.chunk_bytes += (size_t)c * tc_layer_chunk_bytes(l, n.D) + (tc_layer_has_bias(l, n.D) ? TC_BIAS_CHUNK_BYTES : 0);
+  }
   L.off_chunks = 1024;
   L.off_bias = L.off_chunks + L.chunk_bytes;
   L.off_heads = L.off_bias + (size_t)(TC_MAXD + 1) * 1024;
@@ -104,6 +112,21 @@ __global__ void pack_chunks_kernel(PackJob job, uint8_t* __restrict__ dst) {
   // SWIZZLE_64B K-major: 8-row atoms of 512 B, 16B-chunk index ^= (row%8)>>1
   unsigned off = c.dst_off + (row >> 3) * 512 + (row & 7) * 64 + ((c16 ^ ((row & 7) >> 1)) << 4);
   *reinterpret_cast<uint4*>(dst + off) = o;
+}
+
+// bias chunk: [256 rows x 16 K] fp16, K-major SWIZZLE_32B (rows of 32 B, 8-row atoms of 256 B): k0 = hi, k1 = lo
+struct PackBiasJob { const float* src[TC_MAXD + 2]; unsigned dst_off[TC_MAXD + 2]; int n; };
+__global__ void pack_bias_kernel(PackBiasJob job, uint8_t* __restrict__ dst) {
+  const int li = blockIdx.x, row = threadIdx.x;        // 256 threads = 256 output rows
+  if (li >= job.n) return;
+  const float b = job.src[li][row];
+  const __half hi = __float2half_rn(b);
+  const __half lo = __float2half_rn(b - __half2float(hi));
+  uint4 c0 = make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
+  uint8_t* base = dst + job.dst_off[li] + (row >> 3) * 256 + (row & 7) * 32;
+  const int sw = ((row & 7) >> 2) & 1;                 // Swizzle<1,4,3>: 16-byte chunk index ^= bit 7 of the byte address
+  *reinterpret_cast<uint4*>(base + ((0 ^ sw) << 4)) = c0;
+  *reinterpret_cast<uint4*>(base + ((1 ^ sw) << 4)) = c1;
 }
 
 struct PackTables { NerfNetParams net; size_t off_bias, off_heads, off_vdir; };
@@ -251,16 +274,10 @@ __device__ __forceinline__ float seg_scan_add(float v, int lane, int s) {
   return v;
 }
 
-// One 32-column batch of a hidden-layer epilogue: x = acc + bias (packed FADD2, bias via LDS.128)
-__device__ __forceinline__ void add_bias32(const uint32_t (&v)[32], uint32_t bias_addr, float (&x)[32]) {
+// One 32-column batch of a hidden-layer epilogue: the bias is already in the accumulator (bias chunk)
+__device__ __forceinline__ void as_float32(const uint32_t (&v)[32], float (&x)[32]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 bb = lds128(bias_addr + 16 * j);
-    x[4 * j + 0] = __uint_as_float(v[4 * j + 0]); x[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
-    x[4 * j + 2] = __uint_as_float(v[4 * j + 2]); x[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
-    add2(x[4 * j + 0], x[4 * j + 1], bb.x, bb.y);
-    add2(x[4 * j + 2], x[4 * j + 3], bb.z, bb.w);
-  }
+  for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
 }
 
 extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -271,10 +288,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((sb & 1023u) != 0) __trap();                    // swizzle atoms need the 1024-byte alignment
 
-  float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
   float* s_heads = reinterpret_cast<float*>(smem + SM_HEADS);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SM_MISC);
-  const uint32_t a_bias = sb + SM_BIAS, a_heads = sb + SM_HEADS, a_part = sb + SM_PART, a_carry = sb + SM_MISC + 16;
+  const uint32_t a_heads = sb + SM_HEADS, a_part = sb + SM_PART, a_carry = sb + SM_MISC + 16;
 
   // mbarriers
   const uint32_t bar_wfull = sb + SM_BARS;            // [3]
@@ -294,7 +310,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
   const int last_enc_layer = (p.skip >= 0 && p.skip + 1 < D) ? p.skip + 1 : 0;
 
   // ---- one-time setup ----
-  for (int i = threadIdx.x; i < (TC_MAXD + 1) * 256; i += TC_THREADS) s_bias[i] = p.bias[i];
+  if (threadIdx.x < 128) {                              // constant-one A slab: row r = [1, 1, 0 x 14] (SWIZZLE_32B K-major)
+    const int r = threadIdx.x, sw = ((r & 7) >> 2) & 1;
+    const uint32_t a = sb + SM_ONES + (uint32_t)((r >> 3) * 256 + (r & 7) * 32);
+    ptx::st_shared_v4(a + ((0 ^ sw) << 4), 0x3c003c00u, 0u, 0u, 0u);
+    ptx::st_shared_v4(a + ((1 ^ sw) << 4), 0u, 0u, 0u, 0u);
+  }
+  ptx::fence_proxy_async_smem();
   for (int i = threadIdx.x; i < HEADS_FLOATS; i += TC_THREADS) s_heads[i] = p.heads[i];
   if (threadIdx.x == 0) {
     sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
@@ -320,9 +342,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       for (int st = 0; st < nst; ++st) {
         const uint8_t* src = p.chunks;
         for (int l = 0; l < NL; ++l) {
-          const int nch = tc_layer_chunks(l, D, p.skip);
-          const uint32_t cb = tc_layer_chunk_bytes(l, D);
-          for (int c = 0; c < nch; ++c) {
+          const int hb = tc_layer_has_bias(l, D) ? 1 : 0;
+          const int nj = tc_layer_chunks(l, D, p.skip) + hb;             // stream chunks of this layer (bias chunk first)
+          for (int j = 0; j < nj; ++j) {
+            const uint32_t cb = (hb && j == 0) ? TC_BIAS_CHUNK_BYTES : tc_layer_chunk_bytes(l, D);
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
             ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
             ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
@@ -342,39 +365,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     if (lane == 0) {
       const int X = warp - 1;
       uint32_t stage = 0, ph = 0, actph = 0;
-      bool ready = false;                                // w_full of the current chunk already observed
       const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
       const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
+      const uint64_t ones_desc = ptx::umma_desc(sb + SM_ONES, 256, ptx::UMMA_SW32);
+      const uint64_t bias_desc0 = ptx::umma_desc(sb, 256, ptx::UMMA_SW32);
       const uint32_t d_tmem = tmem + X * 256;
+      // issue the MMAs of stream chunk j of layer l (bias chunk: one K=16 MMA that initialises D with the bias)
+      auto issue = [&](int l, int j, int hb, bool skip_layer, uint32_t idesc, uint32_t stg) {
+        const uint32_t wofs = (SM_WRING + stg * TC_STAGE_BYTES) >> 4;
+        if (hb && j == 0) { ptx::mma_f16_ss(d_tmem, ones_desc, bias_desc0 + wofs, idesc, 0u); return; }
+        const int c = j - hb;
+        const bool is_enc = (l == 0) || (skip_layer && c < 2);
+        const int kc = skip_layer ? c - 2 : c;
+        const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
+        const uint64_t ad = adesc0 + (a_off >> 4), bd = bdesc0 + wofs;
+        ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (j > 0) ? 1u : 0u);
+        ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+      };
       for (int st = 0; st < nst; ++st) {
         const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0;
         ptx::mbar_wait(bar_encfull, st & 1);
         for (int l = 0; l < NL; ++l) {
-          const int nch = tc_layer_chunks(l, D, p.skip);
+          const int hb = tc_layer_has_bias(l, D) ? 1 : 0;
+          const int nj = tc_layer_chunks(l, D, p.skip) + hb;
           const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
           const uint32_t idesc = ptx::umma_idesc_f16(128, (l == D + 1) ? 128 : 256);
-          const bool last_layer = (st == nst - 1) && (l == NL - 1);
-          for (int c = 0; c < nch; ++c) {
-            long long* trp = p.trace + 4 * (l * 10 + c);
+          // index (in stream chunks, bias included) of the last chunk that reads the encoded inputs
+          const int enc_last_j = (l == last_enc_layer) ? hb + 1 : -1;
+          for (int j = 0; j < nj; j += 2) {
+            // two stream chunks per hand-off: their MMAs are issued back to back so the tensor pipe never
+            // waits on this thread's bookkeeping while the other issuer is busy with its own
+            const bool two = (j + 1 < nj);
+            const uint32_t s0 = stage, p0 = ph;
+            const uint32_t s1 = (s0 + 1 == TC_NST) ? 0u : s0 + 1, p1 = (s0 + 1 == TC_NST) ? p0 ^ 1u : p0;
+            long long* trp = p.trace + 4 * (l * 10 + j);
             if (tr) trp[0] = clock64();
-            if (!ready) ptx::mbar_wait(bar_wfull + 8 * stage, ph);
+            ptx::mbar_wait(bar_wfull + 8 * s0, p0);
+            if (two) ptx::mbar_wait(bar_wfull + 8 * s1, p1);
             if (tr) trp[1] = clock64();
-            if (c == 0) { ptx::mbar_wait(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
+            if (j == 0) { ptx::mbar_wait(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
             ptx::tc_fence_after();
-            const bool is_enc = (l == 0) || (skip_layer && c < 2);
-            const int kc = skip_layer ? c - 2 : c;
-            const uint64_t bd = bdesc0 + ((SM_WRING + stage * TC_STAGE_BYTES) >> 4);
-            const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
-            const uint64_t ad = adesc0 + (a_off >> 4);
-            const uint32_t nstage = (stage + 1 == TC_NST) ? 0u : stage + 1, nph = (stage + 1 == TC_NST) ? ph ^ 1u : ph;
-            // probe the NEXT chunk's weights now; the answer arrives while the MMAs below are issued
-            const bool nready = !(last_layer && c == nch - 1) && ptx::mbar_try_wait(bar_wfull + 8 * nstage, nph);
-            ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (c > 0) ? 1u : 0u);
-            ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
-            if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
-            ptx::mma_commit(bar_wempty + 8 * stage);
-            if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
-            stage = nstage; ph = nph; ready = nready;
+            issue(l, j, hb, skip_layer, idesc, s0);
+            if (two) issue(l, j + 1, hb, skip_layer, idesc, s1);
+            ptx::mma_commit(bar_wempty + 8 * s0);
+            if (two) ptx::mma_commit(bar_wempty + 8 * s1);
+            if (j + 2 >= nj) ptx::mma_commit(bar_dfull + 8 * X);
+            if (enc_last_j == j || (two && enc_last_j == j + 1)) ptx::mma_commit(bar_encfree);
+            if (two) { stage = (s1 + 1 == TC_NST) ? 0u : s1 + 1; ph = (s1 + 1 == TC_NST) ? p1 ^ 1u : p1; }
+            else { stage = s1; ph = p1; }
             if (tr) trp[3] = clock64();
           }
         }
@@ -424,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
             ptx::tmem_ld_wait();
             if (b < 3) ptx::tmem_ld_x32(t_lane + col0 + 32, vn);
             float x[32];
-            add_bias32(v, a_bias + (uint32_t)(l * 256 + col0) * 4u, x);
+            as_float32(v, x);
             if (last_pts) {
               if (p.use_viewdirs) {                               // alpha_linear (run_nerf_helpers.py:106)
 #pragma unroll

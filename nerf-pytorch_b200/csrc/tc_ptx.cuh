@@ -81,7 +81,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // shared-memory matrix descriptor, K-major canonical layouts:
 //   SWIZZLE_128B: rows of 128 B (64 fp16), 8-row atoms of 1024 B, SBO = 1024, layout_type = 2
 //   SWIZZLE_64B : rows of  64 B (32 fp16), 8-row atoms of  512 B, SBO =  512, layout_type = 4
-constexpr uint64_t UMMA_SW128 = 2, UMMA_SW64 = 4;
+constexpr uint64_t UMMA_SW128 = 2, UMMA_SW64 = 4, UMMA_SW32 = 6;
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint64_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address  [0,14)
