@@ -73,6 +73,7 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   p.N = N; p.S = S;
   p.chunks = pk + PL.off_chunks; p.bias = reinterpret_cast<const float*>(pk + PL.off_bias);
   p.heads = reinterpret_cast<const float*>(pk + PL.off_heads);
+  p.biasb = pk + PL.off_biasb;
   p.D = net->D; p.skip = net->skip; p.use_viewdirs = net->use_viewdirs; p.L = L; p.IC = net->input_ch;
   p.white_bkgd = white_bkgd; p.do_composite = do_composite;
   if (out) p.out = *out;
@@ -171,11 +172,7 @@ int nerf_b200_pack_weights(const NerfNetParams* net, void* packed, size_t packed
   PackBiasJob bj;
   bj.n = 0;
   for (int l = 0; l < PL.NL; ++l) {
-    if (tc_layer_has_bias(l, net->D)) {                   // bias chunk first (stream order == MMA order)
-      bj.src[bj.n] = (l < net->D) ? net->pts_b[l] : net->feature_b;
-      bj.dst_off[bj.n++] = off;
-      off += TC_BIAS_CHUNK_BYTES;
-    }
+    if (tc_layer_has_bias(l, net->D)) bj.src[bj.n++] = (l < net->D) ? net->pts_b[l] : net->feature_b;
     if (l == 0) { add(net->pts_w[0], IC, 0, IC, 256); add(net->pts_w[0], IC, 32, IC - 32, 256); }
     else if (l < net->D) {
       const bool sk = (net->skip >= 0 && l == net->skip + 1);
@@ -186,7 +183,8 @@ int nerf_b200_pack_weights(const NerfNetParams* net, void* packed, size_t packed
     else { for (int c = 0; c < 8; ++c) add(net->views_w, W + net->input_ch_views, 32 * c, 32, 128); }
   }
   NB_CHECK_ARG(job.n == PL.n_chunks && off == PL.off_chunks + PL.chunk_bytes, "internal: chunk table mismatch");
-  pack_bias_kernel<<<bj.n, 256, 0, st>>>(bj, static_cast<uint8_t*>(packed));
+  bj.dst_off = (unsigned)PL.off_biasb;
+  pack_bias_kernel<<<1, 256, 0, st>>>(bj, static_cast<uint8_t*>(packed));
   NB_LAUNCH_OK("pack_bias_kernel");
   dim3 grid(4, job.n);
   pack_chunks_kernel<<<grid, 256, 0, st>>>(job, static_cast<uint8_t*>(packed));

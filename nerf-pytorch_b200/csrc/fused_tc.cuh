@@ -38,14 +38,25 @@ constexpr uint32_t TC_STAGE_BYTES = 256 * TC_CHUNK_K * 2;   // 16 KB
 constexpr uint32_t SM_ACT = 0;                                  // 2 x 64 KB  A operand (4 K-blocks x 16 KB)
 constexpr uint32_t SM_ENC = 131072;                             // 2 x 16 KB  encoded inputs (1 K-block)
 constexpr uint32_t SM_WRING = 163840;                           // 3 x 16 KB  weight ring
-constexpr uint32_t SM_ONES = 212992;                            // 4 KB: 128 rows x K=16 constant A slab [1,1,0..] (SWIZZLE_32B)
-constexpr uint32_t SM_HEADS = SM_ONES + 4096;                   // 217088: head weights, 4128 B
-constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 221216: 2 x 128 x float4 partials
-constexpr uint32_t SM_BARS = SM_PART + 4096;                    // 225312: mbarriers
-constexpr uint32_t SM_MISC = SM_BARS + 256;                     // 225568: tmem ptr, compositing carry
-constexpr uint32_t SM_TOTAL = SM_MISC + 128;                    // 225696
+constexpr uint32_t SM_ONES = 212992;                            // 256 B: ONE 8-row atom of the bias-selector A slab (K=16, SWIZZLE_32B,
+                                                                //        SBO = 0: all 128 rows read the same atom)
+constexpr uint32_t SM_BIASB = SM_ONES + 256;                    // 213248: 8 KB resident B operand [256 x K=16]: all layers' biases
+constexpr uint32_t SM_HEADS = SM_BIASB + 8192;                  // 221440: head weights, 4128 B
+constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 225568: 2 x 128 x float4 partials
+constexpr uint32_t SM_BARS = SM_PART + 4096;                    // 229664: mbarriers
+constexpr uint32_t SM_MISC = SM_BARS + 256;                     // 229920: tmem ptr, compositing carry
+constexpr uint32_t SM_TOTAL = SM_MISC + 128;                    // 230048
 constexpr uint32_t SM_ALLOC = SM_TOTAL;                         // dynamic smem base is 1024-aligned (checked at run time)
-constexpr uint32_t TC_BIAS_CHUNK_BYTES = 256 * 32;              // [256 rows x K=16] fp16 bias chunk (hi, lo, 0...)
+constexpr uint32_t TC_BIAS_CHUNK_BYTES = 256 * 32;              // [256 rows x K=16] fp16: column pair (2l, 2l+1) = (hi, lo) of layer l's bias
+
+// K columns of the resident bias operand used by bias layer `li` of `nb`: (hi, lo) pairs while 16 columns
+// suffice, hi only for the last 2*nb-16 layers.  Returns hi column; *lo = lo column or -1.
+__host__ __device__ inline int tc_bias_cols(int li, int nb, int* lo) {
+  const int n_single = (2 * nb > 16) ? 2 * nb - 16 : 0, n_pair = nb - n_single;
+  if (li < n_pair) { *lo = 2 * li + 1; return 2 * li; }
+  *lo = -1;
+  return 2 * n_pair + (li - n_pair);
+}
 
 // heads region (floats): viewdirs: alpha_w[256] rgb_w[3][128] alpha_b rgb_b[3]; else output_w[4][256] output_b[4]
 constexpr int HEADS_FLOATS = 1032;
@@ -56,7 +67,7 @@ constexpr int HEADS_FLOATS = 1032;
 struct PackLayout {
   int D, skip, use_viewdirs, IC, ICV, NL;
   int n_chunks;
-  size_t off_chunks, chunk_bytes, off_bias, off_heads, off_vdir, total;
+  size_t off_chunks, chunk_bytes, off_bias, off_heads, off_vdir, off_biasb, total;
 };
 
 __host__ __device__ inline int tc_layer_chunks(int l, int D, int skip) {
@@ -77,14 +88,15 @@ static inline PackLayout make_pack_layout(const NerfNetParams& n) {
   for (int l = 0; l < L.NL; ++l) {
     int c = tc_layer_chunks(l, n.D, n.skip);
     L.n_chunks += c;
-    L.chunk_bytes += (size_t)c * tc_layer_chunk_bytes(l, n.D) + (tc_layer_has_bias(l, n.D) ? TC_BIAS_CHUNK_BYTES : 0);
+    L.chunk_bytes += (size_t)c * tc_layer_chunk_bytes(l, n.D);
   }
   L.off_chunks = 1024;
   L.off_bias = L.off_chunks + L.chunk_bytes;
   L.off_heads = L.off_bias + (size_t)(TC_MAXD + 1) * 1024;
   L.off_vdir = L.off_heads + HEADS_FLOATS * 4;
-  L.total = L.off_vdir + (size_t)(128 * (n.input_ch_views > 0 ? n.input_ch_views : 1) + 128) * 4;
-  L.total = (L.total + 255) & ~(size_t)255;
+  L.off_biasb = L.off_vdir + (size_t)(128 * (n.input_ch_views > 0 ? n.input_ch_views : 1) + 128) * 4;
+  L.off_biasb = (L.off_biasb + 255) & ~(size_t)255;
+  L.total = L.off_biasb + TC_BIAS_CHUNK_BYTES;
   return L;
 }
 
@@ -114,19 +126,30 @@ __global__ void pack_chunks_kernel(PackJob job, uint8_t* __restrict__ dst) {
   *reinterpret_cast<uint4*>(dst + off) = o;
 }
 
-// bias chunk: [256 rows x 16 K] fp16, K-major SWIZZLE_32B (rows of 32 B, 8-row atoms of 256 B): k0 = hi, k1 = lo
-struct PackBiasJob { const float* src[TC_MAXD + 2]; unsigned dst_off[TC_MAXD + 2]; int n; };
+// resident bias operand: [256 rows x 16 K] fp16, K-major SWIZZLE_32B (rows of 32 B, 8-row atoms of 256 B)
+struct PackBiasJob { const float* src[TC_MAXD + 2]; int n; unsigned dst_off; };
 __global__ void pack_bias_kernel(PackBiasJob job, uint8_t* __restrict__ dst) {
-  const int li = blockIdx.x, row = threadIdx.x;        // 256 threads = 256 output rows
-  if (li >= job.n) return;
-  const float b = job.src[li][row];
-  const __half hi = __float2half_rn(b);
-  const __half lo = __float2half_rn(b - __half2float(hi));
-  uint4 c0 = make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
-  uint8_t* base = dst + job.dst_off[li] + (row >> 3) * 256 + (row & 7) * 32;
+  const int row = threadIdx.x;                         // 256 threads = 256 output rows
+  __half h[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) h[k] = __float2half_rn(0.0f);
+  for (int li = 0; li < job.n; ++li) {
+    const float b = job.src[li][row];
+    int lo;
+    const int hi = tc_bias_cols(li, job.n, &lo);
+    const __half bh = __float2half_rn(b);
+    h[hi] = bh;
+    if (lo >= 0) h[lo] = __float2half_rn(b - __half2float(bh));
+  }
+  uint8_t* base = dst + job.dst_off + (row >> 3) * 256 + (row & 7) * 32;
   const int sw = ((row & 7) >> 2) & 1;                 // Swizzle<1,4,3>: 16-byte chunk index ^= bit 7 of the byte address
-  *reinterpret_cast<uint4*>(base + ((0 ^ sw) << 4)) = c0;
-  *reinterpret_cast<uint4*>(base + ((1 ^ sw) << 4)) = c1;
+  uint4 c[2];
+  for (int q = 0; q < 2; ++q) {
+    const unsigned short* u = reinterpret_cast<const unsigned short*>(h + 8 * q);
+    c[q] = make_uint4(u[0] | (u[1] << 16), u[2] | (u[3] << 16), u[4] | (u[5] << 16), u[6] | (u[7] << 16));
+  }
+  *reinterpret_cast<uint4*>(base + ((0 ^ sw) << 4)) = c[0];
+  *reinterpret_cast<uint4*>(base + ((1 ^ sw) << 4)) = c[1];
 }
 
 struct PackTables { NerfNetParams net; size_t off_bias, off_heads, off_vdir; };
@@ -186,7 +209,7 @@ struct MarchParams {
   const float* noise;                     // [N,S] or NULL
   const float* vb;                        // [N,128] view bias (use_viewdirs)
   long long N; int S; int rays_per_cta;
-  const uint8_t* chunks; const float* bias; const float* heads;
+  const uint8_t* chunks; const float* bias; const float* heads; const uint8_t* biasb;
   int D, skip, use_viewdirs, L, IC;
   int white_bkgd, do_composite;
   NerfPassOut out;
@@ -280,6 +303,19 @@ __device__ __forceinline__ void as_float32(const uint32_t (&v)[32], float (&x)[3
   for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
 }
 
+// Row `r` (0..7) of the 8-row bias-selector A atom for bias layer `li`: 1.0 in that layer's K columns.
+__device__ __forceinline__ void write_bias_selector(uint32_t slab, int r, int li, int nb) {
+  int lo;
+  const int hi = tc_bias_cols(li, nb, &lo);
+  uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // 16 halves as 8 words
+  w[hi >> 1] |= (hi & 1) ? 0x3c000000u : 0x00003c00u;
+  if (lo >= 0) w[lo >> 1] |= (lo & 1) ? 0x3c000000u : 0x00003c00u;
+  const int sw = (r >> 2) & 1;
+  const uint32_t a = slab + (uint32_t)(r * 32);
+  ptx::st_shared_v4(a + ((0 ^ sw) << 4), w[0], w[1], w[2], w[3]);
+  ptx::st_shared_v4(a + ((1 ^ sw) << 4), w[4], w[5], w[6], w[7]);
+}
+
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
 __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchParams p) {
@@ -310,12 +346,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
   const int last_enc_layer = (p.skip >= 0 && p.skip + 1 < D) ? p.skip + 1 : 0;
 
   // ---- one-time setup ----
-  if (threadIdx.x < 128) {                              // constant-one A slab: row r = [1, 1, 0 x 14] (SWIZZLE_32B K-major)
-    const int r = threadIdx.x, sw = ((r & 7) >> 2) & 1;
-    const uint32_t a = sb + SM_ONES + (uint32_t)((r >> 3) * 256 + (r & 7) * 32);
-    ptx::st_shared_v4(a + ((0 ^ sw) << 4), 0x3c003c00u, 0u, 0u, 0u);
-    ptx::st_shared_v4(a + ((1 ^ sw) << 4), 0u, 0u, 0u, 0u);
-  }
+  const int n_bias = D + (p.use_viewdirs ? 1 : 0);      // layers whose bias rides in the GEMM (all but the view layer)
+  if (threadIdx.x < 8) write_bias_selector(sb + SM_ONES, threadIdx.x, 0, n_bias);
+  for (int i = threadIdx.x; i < (int)(TC_BIAS_CHUNK_BYTES / 16); i += TC_THREADS)
+    reinterpret_cast<uint4*>(smem + SM_BIASB)[i] = reinterpret_cast<const uint4*>(p.biasb)[i];
   ptx::fence_proxy_async_smem();
   for (int i = threadIdx.x; i < HEADS_FLOATS; i += TC_THREADS) s_heads[i] = p.heads[i];
   if (threadIdx.x == 0) {
@@ -342,10 +376,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       for (int st = 0; st < nst; ++st) {
         const uint8_t* src = p.chunks;
         for (int l = 0; l < NL; ++l) {
-          const int hb = tc_layer_has_bias(l, D) ? 1 : 0;
-          const int nj = tc_layer_chunks(l, D, p.skip) + hb;             // stream chunks of this layer (bias chunk first)
-          for (int j = 0; j < nj; ++j) {
-            const uint32_t cb = (hb && j == 0) ? TC_BIAS_CHUNK_BYTES : tc_layer_chunk_bytes(l, D);
+          const int nch = tc_layer_chunks(l, D, p.skip);
+          const uint32_t cb = tc_layer_chunk_bytes(l, D);
+          for (int c = 0; c < nch; ++c) {
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
             ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
             ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
@@ -365,54 +398,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     if (lane == 0) {
       const int X = warp - 1;
       uint32_t stage = 0, ph = 0, actph = 0;
+      bool ready = false;                                // w_full of the current chunk already observed
       const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
       const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
-      const uint64_t ones_desc = ptx::umma_desc(sb + SM_ONES, 256, ptx::UMMA_SW32);
-      const uint64_t bias_desc0 = ptx::umma_desc(sb, 256, ptx::UMMA_SW32);
+      const uint64_t sel_desc = ptx::umma_desc(sb + SM_ONES, 0, ptx::UMMA_SW32);      // SBO = 0: one atom for all rows
+      const uint64_t bias_desc = ptx::umma_desc(sb + SM_BIASB, 256, ptx::UMMA_SW32);
       const uint32_t d_tmem = tmem + X * 256;
-      // issue the MMAs of stream chunk j of layer l (bias chunk: one K=16 MMA that initialises D with the bias)
-      auto issue = [&](int l, int j, int hb, bool skip_layer, uint32_t idesc, uint32_t stg) {
-        const uint32_t wofs = (SM_WRING + stg * TC_STAGE_BYTES) >> 4;
-        if (hb && j == 0) { ptx::mma_f16_ss(d_tmem, ones_desc, bias_desc0 + wofs, idesc, 0u); return; }
-        const int c = j - hb;
-        const bool is_enc = (l == 0) || (skip_layer && c < 2);
-        const int kc = skip_layer ? c - 2 : c;
-        const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
-        const uint64_t ad = adesc0 + (a_off >> 4), bd = bdesc0 + wofs;
-        ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (j > 0) ? 1u : 0u);
-        ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
-      };
       for (int st = 0; st < nst; ++st) {
         const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0;
         ptx::mbar_wait(bar_encfull, st & 1);
         for (int l = 0; l < NL; ++l) {
-          const int hb = tc_layer_has_bias(l, D) ? 1 : 0;
-          const int nj = tc_layer_chunks(l, D, p.skip) + hb;
+          const int nch = tc_layer_chunks(l, D, p.skip);
           const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
+          const bool has_bias = tc_layer_has_bias(l, D);
           const uint32_t idesc = ptx::umma_idesc_f16(128, (l == D + 1) ? 128 : 256);
-          // index (in stream chunks, bias included) of the last chunk that reads the encoded inputs
-          const int enc_last_j = (l == last_enc_layer) ? hb + 1 : -1;
-          for (int j = 0; j < nj; j += 2) {
-            // two stream chunks per hand-off: their MMAs are issued back to back so the tensor pipe never
-            // waits on this thread's bookkeeping while the other issuer is busy with its own
-            const bool two = (j + 1 < nj);
-            const uint32_t s0 = stage, p0 = ph;
-            const uint32_t s1 = (s0 + 1 == TC_NST) ? 0u : s0 + 1, p1 = (s0 + 1 == TC_NST) ? p0 ^ 1u : p0;
-            long long* trp = p.trace + 4 * (l * 10 + j);
+          const bool last_layer = (st == nst - 1) && (l == NL - 1);
+          for (int c = 0; c < nch; ++c) {
+            long long* trp = p.trace + 4 * (l * 10 + c);
             if (tr) trp[0] = clock64();
-            ptx::mbar_wait(bar_wfull + 8 * s0, p0);
-            if (two) ptx::mbar_wait(bar_wfull + 8 * s1, p1);
+            if (!ready) ptx::mbar_wait(bar_wfull + 8 * stage, ph);
             if (tr) trp[1] = clock64();
-            if (j == 0) { ptx::mbar_wait(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
+            if (c == 0) { ptx::mbar_wait(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
             ptx::tc_fence_after();
-            issue(l, j, hb, skip_layer, idesc, s0);
-            if (two) issue(l, j + 1, hb, skip_layer, idesc, s1);
-            ptx::mma_commit(bar_wempty + 8 * s0);
-            if (two) ptx::mma_commit(bar_wempty + 8 * s1);
-            if (j + 2 >= nj) ptx::mma_commit(bar_dfull + 8 * X);
-            if (enc_last_j == j || (two && enc_last_j == j + 1)) ptx::mma_commit(bar_encfree);
-            if (two) { stage = (s1 + 1 == TC_NST) ? 0u : s1 + 1; ph = (s1 + 1 == TC_NST) ? p1 ^ 1u : p1; }
-            else { stage = s1; ph = p1; }
+            const bool is_enc = (l == 0) || (skip_layer && c < 2);
+            const int kc = skip_layer ? c - 2 : c;
+            const uint64_t bd = bdesc0 + ((SM_WRING + stage * TC_STAGE_BYTES) >> 4);
+            const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
+            const uint64_t ad = adesc0 + (a_off >> 4);
+            const uint32_t nstage = (stage + 1 == TC_NST) ? 0u : stage + 1, nph = (stage + 1 == TC_NST) ? ph ^ 1u : ph;
+            // probe the NEXT chunk's weights now; the answer arrives while the MMAs below are issued
+            const bool nready = !(last_layer && c == nch - 1) && ptx::mbar_try_wait(bar_wfull + 8 * nstage, nph);
+            // the layer's first MMA initialises the accumulator with the bias: D = selector(1.0 in this
+            // layer's K columns) x resident bias operand
+            if (c == 0 && has_bias) ptx::mma_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
+            ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (c > 0 || has_bias) ? 1u : 0u);
+            ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
+            ptx::mma_commit(bar_wempty + 8 * stage);
+            if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
+            stage = nstage; ph = nph; ready = nready;
             if (tr) trp[3] = clock64();
           }
         }
@@ -496,6 +520,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
               }
             }
           }
+          // bias selector for the NEXT layer (both slots write identical bytes)
+          {
+            const int nxt = (l + 1 < n_bias) ? l + 1 : ((l == NL - 1) ? 0 : -1);
+            if (q == 0 && ch == 0 && lane < 8 && nxt >= 0) write_bias_selector(sb + SM_ONES, lane, nxt, n_bias);
+          }
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(bar_act + 8 * X);
@@ -507,7 +536,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           ptx::tmem_ld_x32(t_lane + ch * 64, va);
           ptx::tmem_ld_x32(t_lane + ch * 64 + 32, vb);
           ptx::tmem_ld_wait();
+          if (q == 0 && ch == 0 && lane < 8) write_bias_selector(sb + SM_ONES, lane, 0, n_bias);   // next super-tile, layer 0
           ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(bar_act + 8 * X);                      // accumulator drained: next super-tile may start
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
