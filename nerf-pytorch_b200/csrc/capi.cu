@@ -476,6 +476,14 @@ int nerf_b200_debug_ldtm_rate(int reps, int shape, int nwarps, int mma, void* ou
   return 0;
 }
 
+int nerf_b200_debug_issue_probe(int reps, int nmma, int flags, void* out_2_i64, void* stream) {
+  const size_t sm = 65536 + 32768 + 256 + 1024;
+  if (int rc = smem_optin((const void*)issue_probe_kernel, sm)) return rc;
+  issue_probe_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(reps, nmma, flags, static_cast<long long*>(out_2_i64));
+  NB_LAUNCH_OK("issue_probe_kernel");
+  return 0;
+}
+
 int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch, size_t scratch_bytes, void* stream) {
   NB_CHECK_ARG(A && W && out && scratch, "NULL pointer");
   NB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 256 && (N == 128 || N == 256), "bad K/N");

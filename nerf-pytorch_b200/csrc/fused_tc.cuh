@@ -371,7 +371,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
 
   if (warp == 0) {
     // =========================== weight producer ===========================
-    if (lane == 0) {
+    // (warp-uniform control flow; one elected lane issues the bulk copies)
+    {
       uint32_t stage = 0, ph = 0;
       for (int st = 0; st < nst; ++st) {
         const uint8_t* src = p.chunks;
@@ -380,22 +381,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           const uint32_t cb = tc_layer_chunk_bytes(l, D);
           for (int c = 0; c < nch; ++c) {
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
-            ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
-            ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, cb);
+              ptx::bulk_g2s(sb + SM_WRING + stage * TC_STAGE_BYTES, src, cb, bar_wfull + 8 * stage);
+            }
+            __syncwarp();
             src += cb;
             if (++stage == TC_NST) { stage = 0; ph ^= 1; }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1 || warp == 2) {
     // =========================== MMA issuers (one per tile slot) ===========================
     // A warp cannot overlap its own bookkeeping (mbarrier waits, commits) with its tcgen05.mma issue
     // (measured: issue time is additive), so each tile slot has its own issuing warp: while one warp
     // waits / commits, the other warp's MMAs keep the tensor pipe busy.  Accumulation order inside a
     // slot is preserved because one thread issues all MMAs of that slot's accumulator.
-    if (lane == 0) {
+    // Control flow is warp-uniform (all 32 lanes run the loops and the mbarrier waits); only the tcgen05
+    // instructions are issued by one elected lane.  That keeps descriptors and addresses in uniform
+    // registers -- issued from a divergent `if (lane == 0)` region every UTCHMMA is wrapped in an
+    // ELECT / R2UR.BROADCAST waterfall loop that costs ~100 cycles per MMA (profiles/r01 issue probe).
+    {
       const int X = warp - 1;
       uint32_t stage = 0, ph = 0, actph = 0;
       bool ready = false;                                // w_full of the current chunk already observed
@@ -403,9 +410,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
       const uint64_t sel_desc = ptx::umma_desc(sb + SM_ONES, 0, ptx::UMMA_SW32);      // SBO = 0: one atom for all rows
       const uint64_t bias_desc = ptx::umma_desc(sb + SM_BIASB, 256, ptx::UMMA_SW32);
-      const uint32_t d_tmem = tmem + X * 256;
+      const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem, 0) + X * 256;
       for (int st = 0; st < nst; ++st) {
-        const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0;
+        const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0 && lane == 0;
         ptx::mbar_wait(bar_encfull, st & 1);
         for (int l = 0; l < NL; ++l) {
           const int nch = tc_layer_chunks(l, D, p.skip);
@@ -426,17 +433,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
             const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
             const uint64_t ad = adesc0 + (a_off >> 4);
             const uint32_t nstage = (stage + 1 == TC_NST) ? 0u : stage + 1, nph = (stage + 1 == TC_NST) ? ph ^ 1u : ph;
-            // probe the NEXT chunk's weights now; the answer arrives while the MMAs below are issued
-            const bool nready = !(last_layer && c == nch - 1) && ptx::mbar_try_wait(bar_wfull + 8 * nstage, nph);
-            // the layer's first MMA initialises the accumulator with the bias: D = selector(1.0 in this
-            // layer's K columns) x resident bias operand
-            if (c == 0 && has_bias) ptx::mma_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
-            ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (c > 0 || has_bias) ? 1u : 0u);
-            ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
-            if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
-            ptx::mma_commit(bar_wempty + 8 * stage);
-            if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
-            stage = nstage; ph = nph; ready = nready;
+            if (ptx::elect_one()) {
+              // the layer's first MMA initialises the accumulator with the bias: D = selector(1.0 in this
+              // layer's K columns) x resident bias operand
+              if (c == 0 && has_bias) ptx::mma_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
+              ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (c > 0 || has_bias) ? 1u : 0u);
+              ptx::mma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              if (c == nch - 1) ptx::mma_commit(bar_dfull + 8 * X);
+              ptx::mma_commit(bar_wempty + 8 * stage);
+              if (is_enc && c == 1 && l == last_enc_layer) ptx::mma_commit(bar_encfree);
+            }
+            __syncwarp();
+            // probe the NEXT chunk's weights (usually already there: the ring runs two chunks ahead)
+            ready = !(last_layer && c == nch - 1) && ptx::mbar_try_wait(bar_wfull + 8 * nstage, nph);
+            ready = __all_sync(0xffffffffu, ready);
+            stage = nstage; ph = nph;
             if (tr) trp[3] = clock64();
           }
         }
@@ -865,6 +876,81 @@ __global__ void __launch_bounds__(384, 1) epi_rate_kernel(int reps, int mode, in
     const long long t1 = clock64();
     if (e == 0 && lane == 0) { out[0] = t1 - t0; out[1] = ldw; *s_stop = 1; }
     if (sink == 123.456f) out[1] = 1;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+// Issue-overhead probe: one thread runs `reps` iterations of {optional mbarrier try_wait on a completed
+// barrier; `nmma` x tcgen05.mma (N=256, K=16); optional tcgen05.commit to a scratch barrier} and reports the
+// cycles per iteration (out[0] = to completion of everything, out[1] = issue loop only).
+//   flags bit0: try_wait per iteration   bit1: one commit per iteration   bit2: two commits   bit3: tcgen05.fence::after
+__global__ void __launch_bounds__(128, 1) issue_probe_kernel(int reps, int nmma, int flags, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t BAR = 65536 + 32768, TPTR = BAR + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TPTR);
+  for (int i = threadIdx.x; i < (65536 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { ptx::mbar_init(sb + BAR, 1); ptx::mbar_init(sb + BAR + 8, 1); ptx::mbar_init(sb + BAR + 16, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  if (warp == 0 && (flags & 128)) {
+    // warp-uniform control flow, only the tcgen05 instructions are issued by one elected lane
+    const uint32_t idesc = ptx::umma_idesc_f16(128, 256);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    if (threadIdx.x == 0) ptx::mbar_arrive(sb + BAR + 16);
+    __syncwarp();
+    const uint64_t ad = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128), bd = ptx::umma_desc(sb + 65536, 512, ptx::UMMA_SW64);
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      if (flags & 1) ptx::mbar_wait(sb + BAR + 16, 0);
+      if (flags & 8) ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        for (int j = 0; j < nmma; ++j) {
+          const uint32_t dsel = (flags & 16) ? 0u : ((flags & 32) ? (uint32_t)(j & 1) : (uint32_t)(i & 1));
+          const uint32_t ks = (flags & 64) ? (uint32_t)((i + j) & 3) : (uint32_t)(j & 1);
+          ptx::mma_f16_ss(tm + dsel * 256, ad + 2 * ks, bd + 2 * (ks & 1), idesc, 1u);
+        }
+        if (flags & 2) ptx::mma_commit(sb + BAR + 8);
+        if (flags & 4) ptx::mma_commit(sb + BAR + 8);
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (ptx::elect_one()) ptx::mma_commit(sb + BAR);
+    __syncwarp();
+    ptx::mbar_wait(sb + BAR, 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+  } else if (threadIdx.x == 0 && !(flags & 128)) {
+    const uint32_t idesc = ptx::umma_idesc_f16(128, 256);
+    ptx::mbar_arrive(sb + BAR + 16);                    // complete phase 0 of the "always ready" barrier
+    const uint64_t ad = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128), bd = ptx::umma_desc(sb + 65536, 512, ptx::UMMA_SW64);
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      if (flags & 1) ptx::mbar_wait(sb + BAR + 16, 0);
+      if (flags & 8) ptx::tc_fence_after();
+      // flags bit4: keep ONE accumulator (no alternation)   bit5: alternate the accumulator every MMA   bit6: vary operand k-step per iteration
+      for (int j = 0; j < nmma; ++j) {
+        const uint32_t dsel = (flags & 16) ? 0u : ((flags & 32) ? (uint32_t)(j & 1) : (uint32_t)(i & 1));
+        const uint32_t ks = (flags & 64) ? (uint32_t)((i + j) & 3) : (uint32_t)(j & 1);
+        ptx::mma_f16_ss(tmem + dsel * 256, ad + 2 * ks, bd + 2 * (ks & 1), idesc, 1u);
+      }
+      if (flags & 2) ptx::mma_commit(sb + BAR + 8);
+      if (flags & 4) ptx::mma_commit(sb + BAR + 8);
+    }
+    const long long t1 = clock64();
+    ptx::mma_commit(sb + BAR);
+    ptx::mbar_wait(sb + BAR, 0);
+    const long long t2 = clock64();
+    out[0] = t2 - t0; out[1] = t1 - t0;
   }
   ptx::tc_fence_before();
   __syncthreads();

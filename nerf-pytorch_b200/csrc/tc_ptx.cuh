@@ -96,6 +96,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// one elected lane of a fully converged warp (the surrounding control flow stays warp-uniform, so the
+// compiler keeps descriptors / addresses in uniform registers instead of a per-lane waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- packing helpers ----------------------------------------------------------------------------
 // {lo = a, hi = b} as fp16 pair with ReLU fused into the conversion
 __device__ __forceinline__ uint32_t cvt_relu_f16x2(float a, float b) {
