@@ -113,6 +113,20 @@ int nerf_b200_sample_pdf(const float* bins, const float* weights, const float* u
 int nerf_b200_coarse_z(const float* rays, int ray_stride, const float* t_vals, const float* t_rand,
                        int64_t N, int S, int lindisp, float* z_vals, void* stream);
 
+/* ---- ray batch construction of render() (run_nerf.py:95-123): optional pinhole ray generation (get_rays,
+ *      run_nerf_helpers.py:153-162) for pixels [pixel0, pixel0+N) of an H x W image, view-direction
+ *      normalisation (:108), optional NDC warp (ndc_rays, run_nerf_helpers.py:175-192, near plane 1) and packing
+ *      to out [N, 11 | 8] = o(3) d(3) near far [viewdir(3)].  rays_o/rays_d [N,3] or both NULL (generate from
+ *      `cam`); view_src [N,3] = directions to normalise into viewdirs (NULL -> rays_d, as in :104). ----------- */
+typedef struct NerfCamera {
+  int32_t H, W;
+  float fx, fy, cx, cy;      /* K[0][0], K[1][1], K[0][2], K[1][2] (run_nerf.py:615-620) */
+  float c2w[12];             /* camera-to-world [3,4], row-major */
+} NerfCamera;
+int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam,
+                        int64_t N, int64_t pixel0, int ndc, float near, float far, int use_viewdirs,
+                        float* out, void* stream);
+
 /* ---- hierarchical resampling of render_rays (run_nerf.py:392-396, :412): z_mid, sample_pdf on
  *      weights[...,1:-1], sort(cat) and z_std in one kernel.
  *      z_vals [N,S], weights [N,S], u as above -> z_fine [N,S+n_imp] sorted, z_std [N] ------------ */

@@ -31,6 +31,11 @@ class NerfNetGrads(C.Structure):
                 ("output_w", c_fp), ("output_b", c_fp)]
 
 
+class NerfCamera(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("c2w", C.c_float * 12)]
+
+
 class NerfRenderCfg(C.Structure):
     _fields_ = [("N_samples", C.c_int32), ("N_importance", C.c_int32), ("multires", C.c_int32),
                 ("multires_views", C.c_int32), ("lindisp", C.c_int32), ("perturb", C.c_int32),
@@ -56,6 +61,8 @@ SIGNATURES = {
     "nerf_b200_raw2outputs": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, c_fp, C.c_int64, C.c_int, C.c_int,
                                         C.POINTER(NerfPassOut), c_fp]),
     "nerf_b200_raw2outputs_bwd": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, c_fp, C.c_int64, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
+    "nerf_b200_pack_rays": (C.c_int, [c_fp, c_fp, c_fp, C.POINTER(NerfCamera), C.c_int64, C.c_int64, C.c_int, C.c_float,
+                                      C.c_float, C.c_int, c_fp, c_fp]),
     "nerf_b200_sample_pdf": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int64, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_coarse_z": (C.c_int, [c_fp, C.c_int, c_fp, c_fp, C.c_int64, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_fine_z": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int64, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp]),

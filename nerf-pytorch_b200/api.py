@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import NerfNetGrads, NerfNetParams, NerfPassOut, NerfRenderCfg, PREC_FP32, PREC_TC_FP16, check
+from ._lib import NerfCamera, NerfNetGrads, NerfNetParams, NerfPassOut, NerfRenderCfg, PREC_FP32, PREC_TC_FP16, check
 
 __all__ = ["NeRF", "Embedder", "get_embedder", "sample_pdf", "raw2outputs", "run_network", "batchify",
            "batchify_rays", "render_rays", "render", "create_nerf", "get_rays", "get_rays_np", "ndc_rays",
@@ -406,6 +406,18 @@ def _grad_buffers(net: NeRF):
     return {k: torch.zeros_like(p, dtype=torch.float32) for k, p in net.named_parameters()}
 
 
+_LINSPACE = {}
+
+
+def _linspace01(n, dev):
+    """torch.linspace(0, 1, n) on `dev`, cached (the reference rebuilds it on every call)."""
+    key = (n, str(dev))
+    t = _LINSPACE.get(key)
+    if t is None:
+        t = _LINSPACE[key] = torch.linspace(0., 1., steps=n, device=dev)
+    return t
+
+
 class _RenderRays(torch.autograd.Function):
     """Forward: nerf_b200_render_rays_fwd (coarse z -> fused pass -> resample -> fused pass).
     Backward: nerf_b200_march_bwd per pass (fp32 recompute + GEMM backprop), gradients w.r.t. rgb_map and rgb0 only --
@@ -429,8 +441,8 @@ class _RenderRays(torch.autograd.Function):
         pk_c = net_c.packed() if tc else None
         pk_f = net_f.packed() if (tc and net_f is not None) else None
         f32 = dict(device=dev, dtype=torch.float32)
-        t_vals = torch.linspace(0., 1., steps=Sc, device=dev)                     # run_nerf.py:357
-        u_det = torch.linspace(0., 1., steps=Ni, device=dev) if Ni > 0 else None  # run_nerf_helpers.py:205
+        t_vals = _linspace01(Sc, dev)                                             # run_nerf.py:357
+        u_det = _linspace01(Ni, dev) if Ni > 0 else None                          # run_nerf_helpers.py:205
         z_c = torch.empty((N, Sc), **f32)
         o = {k: torch.empty(s, **f32) for k, s in (("rgb0", (N, 3)), ("disp0", (N,)), ("acc0", (N,)), ("w0", (N, Sc)))}
         retraw, fine = cfgd["retraw"], Ni > 0
@@ -574,28 +586,69 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
     return {k: (torch.cat(v, 0) if len(v) > 1 else v[0]) for k, v in all_ret.items()}
 
 
+def _camera(H, W, K, c2w=None) -> NerfCamera:
+    cam = NerfCamera()
+    cam.H, cam.W = int(H), int(W)
+    cam.fx, cam.fy, cam.cx, cam.cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+    if c2w is not None:
+        m = c2w.detach().float().cpu().numpy() if torch.is_tensor(c2w) else np.asarray(c2w, np.float32)
+        for i, v in enumerate(np.ascontiguousarray(m[:3, :4], np.float32).reshape(-1)):
+            cam.c2w[i] = float(v)
+    return cam
+
+
+def _render_device(kwargs):
+    net = kwargs.get("network_fn")
+    return net._check_device() if isinstance(net, NeRF) else torch.device("cuda")
+
+
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
-    """run_nerf.py:69-134: build the [N, 8|11] ray batch, render in `chunk`-ray slices, reshape."""
-    if c2w is not None:
-        rays_o, rays_d = get_rays(H, W, K, c2w)
+    """run_nerf.py:69-134: build the [N, 8|11] ray batch, render in `chunk`-ray slices, reshape.
+
+    The batch construction (get_rays for `c2w`, view-direction normalisation, NDC warp, packing) is one
+    kernel (nerf_b200_pack_rays); the torch-op path below is kept only for the two cases the kernel
+    does not cover: per-ray near/far arrays and the `c2w_staticcam` visualisation mode."""
+    scalar_bounds = isinstance(near, (int, float)) and isinstance(far, (int, float))
+    if scalar_bounds and c2w_staticcam is None:
+        lib = _lib.load()
+        if c2w is not None:
+            dev = _render_device(kwargs)
+            N, sh = int(H) * int(W), [int(H), int(W), 3]
+            cam = _camera(H, W, K, c2w)
+            o_ptr = d_ptr = None
+            keep = None
+        else:
+            rays_o, rays_d = rays
+            sh = list(rays_d.shape)
+            keep = (_f32c(rays_o, "rays_o").reshape(-1, 3), _f32c(rays_d, "rays_d").reshape(-1, 3))
+            dev, N = keep[0].device, keep[0].shape[0]
+            cam = _camera(H, W, K)
+            o_ptr, d_ptr = keep
+        packed = torch.empty((N, 11 if use_viewdirs else 8), device=dev, dtype=torch.float32)
+        check(lib.nerf_b200_pack_rays(_ptr(o_ptr), _ptr(d_ptr), None, C.byref(cam), N, 0, int(bool(ndc)), float(near), float(far),
+                                      int(bool(use_viewdirs)), _ptr(packed), _stream(packed)), "pack_rays")
+        rays = packed
     else:
-        rays_o, rays_d = rays
-    if use_viewdirs:
-        viewdirs = rays_d
-        if c2w_staticcam is not None:
-            rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
-        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
-        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
-    sh = rays_d.shape
-    if ndc:
-        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
-    rays_o = torch.reshape(rays_o, [-1, 3]).float()
-    rays_d = torch.reshape(rays_d, [-1, 3]).float()
-    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
-    rays = torch.cat([rays_o, rays_d, near, far], -1)
-    if use_viewdirs:
-        rays = torch.cat([rays, viewdirs], -1)
+        if c2w is not None:
+            rays_o, rays_d = get_rays(H, W, K, c2w)
+        else:
+            rays_o, rays_d = rays
+        if use_viewdirs:
+            viewdirs = rays_d
+            if c2w_staticcam is not None:
+                rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
+            viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+            viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        sh = list(rays_d.shape)
+        if ndc:
+            rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+        rays_o = torch.reshape(rays_o, [-1, 3]).float()
+        rays_d = torch.reshape(rays_d, [-1, 3]).float()
+        near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+        rays = torch.cat([rays_o, rays_d, near, far], -1)
+        if use_viewdirs:
+            rays = torch.cat([rays, viewdirs], -1)
     all_ret = batchify_rays(rays, chunk, **kwargs)
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))

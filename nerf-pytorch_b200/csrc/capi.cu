@@ -243,6 +243,27 @@ int nerf_b200_raw2outputs_bwd(const float* raw, const float* z_vals, const float
   return 0;
 }
 
+int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam, int64_t N,
+                        int64_t pixel0, int ndc, float near, float far, int use_viewdirs, float* out, void* stream) {
+  NB_CHECK_ARG(out != nullptr, "NULL output");
+  NB_CHECK_ARG((rays_o && rays_d) || (cam && !rays_o && !rays_d), "give rays_o and rays_d, or a camera to generate them");
+  NB_CHECK_ARG(!ndc || cam, "ndc needs the camera (H, W, focal)");
+  if (N == 0) return 0;
+  PackRaysArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rays_o = rays_o; a.rays_d = rays_d; a.view_src = view_src; a.N = N; a.pixel0 = pixel0;
+  a.ndc = ndc; a.use_viewdirs = use_viewdirs; a.stride = use_viewdirs ? 11 : 8; a.near = near; a.far = far;
+  if (cam) {
+    a.H = cam->H; a.W = cam->W; a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy;
+    memcpy(a.c2w, cam->c2w, sizeof(a.c2w));
+    a.ndc_cw = (float)(-1.0 / ((double)cam->W / (2.0 * (double)cam->fx)));      // run_nerf_helpers.py:181 (focal = K[0][0])
+    a.ndc_ch = (float)(-1.0 / ((double)cam->H / (2.0 * (double)cam->fx)));
+  }
+  pack_rays_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(a, out);
+  NB_LAUNCH_OK("pack_rays_kernel");
+  return 0;
+}
+
 int nerf_b200_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_row_stride, int64_t N, int B,
                          int n_samples, float* samples, void* stream) {
   NB_CHECK_ARG(bins && weights && u && samples, "NULL pointer");

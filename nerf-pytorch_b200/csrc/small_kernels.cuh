@@ -57,6 +57,60 @@ __global__ void coarse_z_kernel(const float* __restrict__ rays, int ray_stride,
   z_out[i] = z;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ray batch construction of render()  (run_nerf.py:95-123): optional pinhole ray generation
+// (get_rays, run_nerf_helpers.py:153-162), view-direction normalisation (:108), optional NDC warp
+// (ndc_rays, run_nerf_helpers.py:175-192) and packing to [N, 8|11] = o d near far [viewdir].
+// Every product/sum is rounded separately, in the reference's order.
+// ---------------------------------------------------------------------------------------------
+struct PackRaysArgs {
+  const float* rays_o; const float* rays_d;     // [N,3] each, or NULL -> generate from the camera
+  const float* view_src;                        // [N,3] directions for viewdirs, or NULL -> rays_d
+  int H, W; float fx, fy, cx, cy; float c2w[12];
+  long long N, pixel0;
+  int ndc, use_viewdirs, stride;
+  float near, far, ndc_cw, ndc_ch;              // ndc_cw = -1/(W/(2 focal)), ndc_ch = -1/(H/(2 focal)) (host double -> float)
+};
+
+__global__ void pack_rays_kernel(PackRaysArgs a, float* __restrict__ out) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  float o[3], d[3];
+  if (a.rays_d != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = a.rays_o[n * 3 + k]; d[k] = a.rays_d[n * 3 + k]; }
+  } else {
+    const long long pix = a.pixel0 + n;
+    const float i = (float)(pix % a.W), j = (float)(pix / a.W);                       // :154-156 (i along W, j along H)
+    const float dir[3] = {__fdiv_rn(__fsub_rn(i, a.cx), a.fx), -__fdiv_rn(__fsub_rn(j, a.cy), a.fy), -1.0f};   // :157
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                                                     // :159 sum(dirs[..., None, :] * c2w[:3,:3], -1)
+      d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dir[0], a.c2w[4 * k]), __fmul_rn(dir[1], a.c2w[4 * k + 1])), __fmul_rn(dir[2], a.c2w[4 * k + 2]));
+      o[k] = a.c2w[4 * k + 3];                                                        // :161
+    }
+  }
+  float* r = out + n * a.stride;
+  if (a.use_viewdirs) {
+    float v[3];
+    if (a.view_src != nullptr) { v[0] = a.view_src[n * 3]; v[1] = a.view_src[n * 3 + 1]; v[2] = a.view_src[n * 3 + 2]; }
+    else { v[0] = d[0]; v[1] = d[1]; v[2] = d[2]; }
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+    r[8] = __fdiv_rn(v[0], nrm); r[9] = __fdiv_rn(v[1], nrm); r[10] = __fdiv_rn(v[2], nrm);   // run_nerf.py:108
+  }
+  if (a.ndc) {                                                                        // ndc_rays(H, W, focal, near=1.)
+    const float t = __fdiv_rn(-__fadd_rn(1.0f, o[2]), d[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = __fadd_rn(o[k], __fmul_rn(t, d[k]));
+    const float o0 = __fdiv_rn(__fmul_rn(a.ndc_cw, o[0]), o[2]), o1 = __fdiv_rn(__fmul_rn(a.ndc_ch, o[1]), o[2]);
+    const float o2 = __fadd_rn(1.0f, __fdiv_rn(2.0f, o[2]));
+    const float d0 = __fmul_rn(a.ndc_cw, __fsub_rn(__fdiv_rn(d[0], d[2]), __fdiv_rn(o[0], o[2])));
+    const float d1 = __fmul_rn(a.ndc_ch, __fsub_rn(__fdiv_rn(d[1], d[2]), __fdiv_rn(o[1], o[2])));
+    const float d2 = __fdiv_rn(-2.0f, o[2]);
+    o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
+  }
+  r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = d[0]; r[4] = d[1]; r[5] = d[2]; r[6] = a.near; r[7] = a.far;
+}
+
 // pts = rays_o + rays_d * z  (run_nerf.py:381), exact-mode helper
 __global__ void pts_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z_vals,
                            long long M, int S, float* __restrict__ pts) {

@@ -158,3 +158,53 @@ def test_run_network_no_viewdirs(G):
             G.nb.set_precision("tc_fp16")
         ref = G.O.run_network(pts, None, st)[..., :4]
         assert rel_l2(got, ref) < tol, (prec, rel_l2(got, ref))
+
+
+def test_pack_rays_matches_reference_ray_construction(G):
+    """get_rays + viewdir normalisation + ndc_rays + packing (run_nerf.py:95-123) vs golden reference rays and the oracle."""
+    import ctypes as C
+    fx = load_golden("units")
+    lib = G._lib.load()
+    # 1. generated lego rays (no NDC) == reference get_rays
+    from nerf_pytorch_b200.api import _camera
+    cam = _camera(40, 40, fx["rays_K"], fx["rays_c2w"])
+    out = torch.empty((1600, 11), device=G.DEV)
+    G._lib.check(lib.nerf_b200_pack_rays(None, None, None, C.byref(cam), 1600, 0, 0, 2.0, 6.0, 1, G.ptr(out), G.stream()), "pack_rays")
+    got = out.cpu().numpy()
+    np.testing.assert_allclose(got[:, 0:3], fx["rays_o"].reshape(-1, 3), atol=1e-6)
+    np.testing.assert_allclose(got[:, 3:6], fx["rays_d"].reshape(-1, 3), atol=1e-6)
+    assert np.all(got[:, 6] == 2.0) and np.all(got[:, 7] == 6.0)
+    d = fx["rays_d"].reshape(-1, 3)
+    np.testing.assert_allclose(got[:, 8:11], d / np.linalg.norm(d, axis=-1, keepdims=True), atol=1e-6)
+    # 2. fern-shaped rays with NDC == reference ndc_rays
+    c2wf = G.synth.fern_camera()[3]
+    cam = _camera(38, 50, fx["ndc_K"], c2wf)
+    out = torch.empty((38 * 50, 11), device=G.DEV)
+    G._lib.check(lib.nerf_b200_pack_rays(None, None, None, C.byref(cam), 38 * 50, 0, 1, 0.0, 1.0, 1, G.ptr(out), G.stream()), "pack_rays")
+    got = out.cpu().numpy()
+    np.testing.assert_allclose(got[:, 0:3], fx["ndc_o"].reshape(-1, 3), atol=2e-6)
+    np.testing.assert_allclose(got[:, 3:6], fx["ndc_d"].reshape(-1, 3), atol=2e-6)
+    # 3. explicit rays in == oracle pack_rays (both NDC settings), 8-wide rows without viewdirs
+    sb = G.synth.ray_batch("fern", 333, seed=2)
+    for ndc in (False, True):
+        for uv in (True, False):
+            ref = G.O.pack_rays(sb["H"], sb["W"], sb["K"], sb["rays"][0], sb["rays"][1], ndc, 0.25, 1.5, uv)
+            o, dd = G.dev(sb["rays"][0]), G.dev(sb["rays"][1])
+            cam = _camera(sb["H"], sb["W"], sb["K"])
+            out = torch.empty((333, 11 if uv else 8), device=G.DEV)
+            G._lib.check(lib.nerf_b200_pack_rays(G.ptr(o), G.ptr(dd), None, C.byref(cam), 333, 0, int(ndc), 0.25, 1.5, int(uv), G.ptr(out), G.stream()), "pack_rays")
+            np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-6, atol=2e-6)
+
+
+def test_render_c2w_full_image_path(G):
+    """render(c2w=...) (render_path's call, run_nerf.py:154): in-kernel ray generation == explicit rays."""
+    H, W, K, c2w = G.synth.lego_camera(24)
+    nets = [G.make_net(G.synth.nerf_state(0)), G.make_net(G.synth.nerf_state(1))]
+    kw = dict(ndc=False, near=2., far=6., use_viewdirs=True, network_fn=nets[0], network_fine=nets[1], network_query_fn=G.query_fn(),
+              N_samples=64, N_importance=128, perturb=0., white_bkgd=True, raw_noise_std=0.)
+    o, d = G.synth.camera_rays(H, W, K, c2w)
+    with torch.no_grad():
+        a = G.nb.render(H, W, K, chunk=300, c2w=torch.from_numpy(c2w).to(G.DEV), **kw)
+        b = G.nb.render(H, W, K, chunk=32768, rays=(G.dev(o), G.dev(d)), **kw)
+    assert a[0].shape == (H, W, 3) and a[1].shape == (H, W)
+    torch.testing.assert_close(a[0], b[0], rtol=2e-4, atol=2e-5)
