@@ -5,6 +5,8 @@
 #include "bwd_simt.cuh"
 #include "mlp_simt.cuh"
 #include "fused_tc.cuh"
+#include "fused_tc2.cuh"
+#include <stdlib.h>
 
 namespace nb {
 thread_local char g_err[512] = {0};
@@ -97,8 +99,15 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   p.rays_per_cta = (int)((N + grid - 1) / grid);
   grid = (int)((N + p.rays_per_cta - 1) / p.rays_per_cta);
   NB_CHECK_ARG((long long)p.rays_per_cta * S < (1ll << 30), "rays_per_cta * S overflows");
+  static int pair_mode = -1;                 // NERF_B200_PAIR=1 -> CTA-pair kernel (fused_tc2.cuh)
+  if (pair_mode < 0) { const char* e = getenv("NERF_B200_PAIR"); pair_mode = (e && e[0] == '1') ? 1 : 0; }
   static bool optin = false;
-  if (!optin) { if (int rc = smem_optin((const void*)march_tc_kernel, SM_ALLOC)) return rc; optin = true; }
+  if (!optin) {
+    if (int rc = smem_optin((const void*)march_tc_kernel, SM_ALLOC)) return rc;
+    if (int rc = smem_optin((const void*)march_tc2_kernel, SM_ALLOC)) return rc;
+    optin = true;
+  }
+  if (pair_mode) grid = (grid + 1) & ~1;                 // whole pairs; a padding CTA owns no rays
   p.trace = g_trace;
   TimedLaunch* tl = nullptr;
   if (g_timing && g_ntimed < 4096) {
@@ -107,7 +116,8 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
     tl->flops = 2.0 * net_macs_per_row(*net) * (double)rows;
     cudaEventRecord(tl->a, st);
   }
-  march_tc_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
+  if (pair_mode) march_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
+  else march_tc_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
   if (tl) cudaEventRecord(tl->b, st);
   NB_LAUNCH_OK("march_tc_kernel");
   return 0;

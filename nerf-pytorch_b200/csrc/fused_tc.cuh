@@ -40,7 +40,8 @@ constexpr uint32_t SM_ENC = 131072;                             // 2 x 16 KB  en
 constexpr uint32_t SM_WRING = 163840;                           // 3 x 16 KB  weight ring
 constexpr uint32_t SM_ONES = 212992;                            // 256 B: ONE 8-row atom of the bias-selector A slab (K=16, SWIZZLE_32B,
                                                                 //        SBO = 0: all 128 rows read the same atom)
-constexpr uint32_t SM_BIASB = SM_ONES + 256;                    // 213248: 8 KB resident B operand [256 x K=16]: all layers' biases
+constexpr uint32_t SM_BIASB = SM_ONES + 512;                    // 213504: 8 KB resident B operand [256 x K=16]: all layers' biases
+                                                                //        (one 256-byte selector atom per tile slot before it)
 constexpr uint32_t SM_HEADS = SM_BIASB + 8192;                  // 221440: head weights, 4128 B
 constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 225568: 2 x 128 x float4 partials
 constexpr uint32_t SM_BARS = SM_PART + 4096;                    // 229664: mbarriers
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
 
   // ---- one-time setup ----
   const int n_bias = D + (p.use_viewdirs ? 1 : 0);      // layers whose bias rides in the GEMM (all but the view layer)
-  if (threadIdx.x < 8) write_bias_selector(sb + SM_ONES, threadIdx.x, 0, n_bias);
+  if (threadIdx.x < 16) write_bias_selector(sb + SM_ONES + (threadIdx.x >> 3) * 256, threadIdx.x & 7, 0, n_bias);
   for (int i = threadIdx.x; i < (int)(TC_BIAS_CHUNK_BYTES / 16); i += TC_THREADS)
     reinterpret_cast<uint4*>(smem + SM_BIASB)[i] = reinterpret_cast<const uint4*>(p.biasb)[i];
   ptx::fence_proxy_async_smem();
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       bool ready = false;                                // w_full of the current chunk already observed
       const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
       const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
-      const uint64_t sel_desc = ptx::umma_desc(sb + SM_ONES, 0, ptx::UMMA_SW32);      // SBO = 0: one atom for all rows
+      const uint64_t sel_desc = ptx::umma_desc(sb + SM_ONES + X * 256, 0, ptx::UMMA_SW32);   // SBO = 0: one atom for all rows
       const uint64_t bias_desc = ptx::umma_desc(sb + SM_BIASB, 256, ptx::UMMA_SW32);
       const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem, 0) + X * 256;
       for (int st = 0; st < nst; ++st) {
@@ -531,10 +532,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
               }
             }
           }
-          // bias selector for the NEXT layer (both slots write identical bytes)
+          // this slot's bias selector for the NEXT layer
           {
             const int nxt = (l + 1 < n_bias) ? l + 1 : ((l == NL - 1) ? 0 : -1);
-            if (q == 0 && ch == 0 && lane < 8 && nxt >= 0) write_bias_selector(sb + SM_ONES, lane, nxt, n_bias);
+            if (q == 0 && ch == 0 && lane < 8 && nxt >= 0) write_bias_selector(sb + SM_ONES + X * 256, lane, nxt, n_bias);
           }
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
           ptx::tmem_ld_x32(t_lane + ch * 64, va);
           ptx::tmem_ld_x32(t_lane + ch * 64 + 32, vb);
           ptx::tmem_ld_wait();
-          if (q == 0 && ch == 0 && lane < 8) write_bias_selector(sb + SM_ONES, lane, 0, n_bias);   // next super-tile, layer 0
+          if (q == 0 && ch == 0 && lane < 8) write_bias_selector(sb + SM_ONES + X * 256, lane, 0, n_bias);   // next super-tile, layer 0
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(bar_act + 8 * X);                      // accumulator drained: next super-tile may start

@@ -1,0 +1,431 @@
+// fused_tc2.cuh -- CTA-pair (cta_group::2) version of the fused network pass.
+//
+// Two CTAs of a cluster (a TPC's SM pair) work as one: every tcgen05.mma covers M = 256 rows -- 128 rows of
+// each CTA's own A tile, accumulated in each CTA's own TMEM -- while the B operand (the weight chunk) is split
+// across the pair, so a K=32 chunk costs 8 KB of shared memory and 8 KB of L2->SM traffic per SM instead of 16.
+// The freed ring space (6 stages x 8 KB) pays for a tile-major schedule: per layer the leader CTA issues ALL
+// chunks of slot A's pair-tile (17 MMAs back to back), then all chunks of slot B's; slot A's epilogue (TMEM
+// drain, ReLU, fp16, next layer's A tile) runs on both CTAs while the tensor pipes work on slot B, and vice
+// versa -- the lock-step kernel (fused_tc.cuh) leaves the tensor pipe idle during both epilogues.
+// Everything else (sampler, epilogue math, heads, compositing) is the code of fused_tc.cuh, per CTA.
+//
+// Cross-CTA protocol (barriers live at the same shared-memory offset in both CTAs):
+//   w_full[6]  local   : this CTA's half chunk landed (cp.async.bulk complete_tx)
+//   p_full[6]  leader  : the peer's relay warp forwards its w_full phase (remote mbarrier arrive)
+//   w_empty[6] both    : tcgen05.commit.cta_group::2 multicast -> both producers may refill the stage
+//   d_full[2]  both    : multicast commit -> both CTAs' epilogue warps of that slot
+//   act[2]     leader  : 512 arrivals = 256 local epilogue threads + 256 remote (accumulator drained, A tile written)
+//   enc_full   leader  : 64 arrivals (both samplers);  enc_free both: multicast commit after the last encoding chunk
+#pragma once
+#include "fused_tc.cuh"
+
+namespace nb {
+
+constexpr int TC2_NST = 6;                       // ring stages
+constexpr uint32_t TC2_STAGE_BYTES = 8192;       // half of a [256 x 32] fp16 chunk
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p) {
+  uint8_t* smem = tc_smem;
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sb & 1023u) != 0) __trap();
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  float* s_heads = reinterpret_cast<float*>(smem + SM_HEADS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SM_MISC);
+  const uint32_t a_heads = sb + SM_HEADS, a_part = sb + SM_PART, a_carry = sb + SM_MISC + 16;
+
+  // mbarriers (same offsets in both CTAs)
+  const uint32_t bar_wfull = sb + SM_BARS;            // [6]
+  const uint32_t bar_wempty = sb + SM_BARS + 48;      // [6]
+  const uint32_t bar_pfull = sb + SM_BARS + 96;       // [6] (leader)
+  const uint32_t bar_dfull = sb + SM_BARS + 144;      // [2]
+  const uint32_t bar_act = sb + SM_BARS + 160;        // [2] (leader)
+  const uint32_t bar_encfull = sb + SM_BARS + 176;    //     (leader)
+  const uint32_t bar_encfree = sb + SM_BARS + 184;
+  // arrive on a barrier that lives in the leader CTA
+  auto arrive_leader = [&](uint32_t bar) { if (leader) ptx::mbar_arrive(bar); else ptx::mbar_arrive_cluster(ptx::mapa(bar, 0)); };
+
+  // this CTA's rays / rows; both CTAs of a pair run the same number of super-tiles
+  const long long ray0 = (long long)blockIdx.x * p.rays_per_cta;
+  const long long ray1 = (ray0 + p.rays_per_cta < p.N) ? ray0 + p.rays_per_cta : p.N;
+  const int nrows = (ray1 > ray0) ? (int)(ray1 - ray0) * p.S : 0;
+  const long long pray0 = (long long)(blockIdx.x ^ 1) * p.rays_per_cta;
+  const long long pray1 = (pray0 + p.rays_per_cta < p.N) ? pray0 + p.rays_per_cta : p.N;
+  const int prows = (pray1 > pray0) ? (int)(pray1 - pray0) * p.S : 0;
+  const int nst = ((nrows > prows ? nrows : prows) + TC_ST - 1) / TC_ST;
+  const long long row_begin = ray0 * p.S;
+  const int D = p.D, NL = p.D + (p.use_viewdirs ? 2 : 0);
+  const int last_enc_layer = (p.skip >= 0 && p.skip + 1 < D) ? p.skip + 1 : 0;
+
+  // ---- one-time setup ----
+  const int n_bias = D + (p.use_viewdirs ? 1 : 0);
+  if (threadIdx.x < 16) write_bias_selector(sb + SM_ONES + (threadIdx.x >> 3) * 256, threadIdx.x & 7, 0, n_bias);
+  // this CTA's half (rows 128*rank ..) of the resident bias operand
+  for (int i = threadIdx.x; i < (int)(TC_BIAS_CHUNK_BYTES / 32); i += TC_THREADS)
+    reinterpret_cast<uint4*>(smem + SM_BIASB)[i] = reinterpret_cast<const uint4*>(p.biasb + rank * (TC_BIAS_CHUNK_BYTES / 2))[i];
+  ptx::fence_proxy_async_smem();
+  for (int i = threadIdx.x; i < HEADS_FLOATS; i += TC_THREADS) s_heads[i] = p.heads[i];
+  if (threadIdx.x == 0) {
+    sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
+    sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f); st_release_shared(a_carry + CARRY_TURN, 0u);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC2_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); ptx::mbar_init(bar_pfull + 8 * i, 1); }
+    for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 512); }
+    ptx::mbar_init(bar_encfull, 2 * TC_SAMPLER_THREADS);
+    ptx::mbar_init(bar_encfree, 2);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish2(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();                                  // peer barriers initialised before any remote arrive
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    // =========================== weight producer (both CTAs): this CTA's half of every chunk ===========
+    uint32_t stage = 0, ph = 0;
+    for (int st = 0; st < nst; ++st) {
+      const uint8_t* lsrc = p.chunks;
+      for (int l = 0; l < NL; ++l) {
+        const int nch = tc_layer_chunks(l, D, p.skip);
+        const uint32_t cb = tc_layer_chunk_bytes(l, D), hb = cb / 2;
+        for (int X = 0; X < 2; ++X) {                     // pass of slot A, then the same chunks again for slot B
+          const uint8_t* src = lsrc + rank * hb;
+          for (int c = 0; c < nch; ++c) {
+            ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, hb);
+              ptx::bulk_g2s(sb + SM_WRING + stage * TC2_STAGE_BYTES, src, hb, bar_wfull + 8 * stage);
+            }
+            __syncwarp();
+            src += cb;
+            if (++stage == TC2_NST) { stage = 0; ph ^= 1; }
+          }
+        }
+        lsrc += (size_t)nch * cb;
+      }
+    }
+  } else if ((warp == 1 || warp == 2) && leader) {
+    // =========================== MMA issuers (leader CTA): warp 1 -> slot A passes, warp 2 -> slot B passes =====
+    const int X = warp - 1;
+    uint32_t gi = 0, actph = 0;                           // gi = index of the next chunk in the pair's stream
+    const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
+    const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
+    const uint64_t sel_desc = ptx::umma_desc(sb + SM_ONES + X * 256, 0, ptx::UMMA_SW32);
+    const uint64_t bias_desc = ptx::umma_desc(sb + SM_BIASB, 256, ptx::UMMA_SW32);
+    const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem, 0) + X * 256;
+    for (int st = 0; st < nst; ++st) {
+      const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0 && lane == 0;
+      ptx::mbar_wait_cluster(bar_encfull, st & 1);
+      for (int l = 0; l < NL; ++l) {
+        const int nch = tc_layer_chunks(l, D, p.skip);
+        const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
+        const bool has_bias = tc_layer_has_bias(l, D);
+        const uint32_t idesc = ptx::umma_idesc_f16(256, (l == D + 1) ? 128 : 256);
+        if (X == 1) gi += nch;                            // skip slot A's pass of this layer
+        for (int c0 = 0; c0 < nch; c0 += 2) {
+          long long* trp = p.trace + 4 * (l * 10 + c0);
+          if (tr) trp[0] = clock64();
+          const bool two = (c0 + 1 < nch);
+          const uint32_t g0 = gi + c0, s0 = g0 % TC2_NST, p0 = (g0 / TC2_NST) & 1;
+          const uint32_t g1 = g0 + 1, s1 = g1 % TC2_NST, p1 = (g1 / TC2_NST) & 1;
+          ptx::mbar_wait(bar_wfull + 8 * s0, p0);
+          ptx::mbar_wait_cluster(bar_pfull + 8 * s0, p0);
+          if (two) { ptx::mbar_wait(bar_wfull + 8 * s1, p1); ptx::mbar_wait_cluster(bar_pfull + 8 * s1, p1); }
+          if (tr) trp[1] = clock64();
+          if (c0 == 0) { ptx::mbar_wait_cluster(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            if (c0 == 0 && has_bias) ptx::mma2_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two) break;
+              const int c = c0 + h;
+              const uint32_t sg = h ? s1 : s0;
+              const bool is_enc = (l == 0) || (skip_layer && c < 2);
+              const int kc = skip_layer ? c - 2 : c;
+              const uint64_t bd = bdesc0 + ((SM_WRING + sg * TC2_STAGE_BYTES) >> 4);
+              const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
+              const uint64_t ad = adesc0 + (a_off >> 4);
+              ptx::mma2_f16_ss(d_tmem, ad, bd, idesc, (c > 0 || has_bias) ? 1u : 0u);
+              ptx::mma2_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              ptx::mma2_commit_mc(bar_wempty + 8 * sg, 3);
+              if (is_enc && c == 1 && l == last_enc_layer) ptx::mma2_commit_mc(bar_encfree, 3);
+            }
+            if (c0 + 2 >= nch) ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
+          }
+          __syncwarp();
+          if (tr) trp[3] = clock64();
+        }
+        gi += nch;                                        // own pass consumed
+        if (X == 0) gi += nch;                            // skip slot B's pass of this layer
+      }
+    }
+  } else if (warp == 1 && !leader) {
+    // =========================== relay (peer CTA): forward "my half landed" to the leader ====================
+    uint32_t stage = 0, ph = 0;
+    const uint32_t remote_pfull = ptx::mapa(bar_pfull, 0);
+    for (int st = 0; st < nst; ++st)
+      for (int l = 0; l < NL; ++l) {
+        const int n2 = 2 * tc_layer_chunks(l, D, p.skip);
+        for (int c = 0; c < n2; ++c) {
+          ptx::mbar_wait(bar_wfull + 8 * stage, ph);
+          if (ptx::elect_one()) ptx::mbar_arrive_cluster(remote_pfull + 8 * stage);
+          __syncwarp();
+          if (++stage == TC2_NST) { stage = 0; ph ^= 1; }
+        }
+      }
+  } else if (warp == 2 && !leader) {
+    // idle
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    // TMEM lane quadrant is fixed by (warp id % 4)
+    const int X = (warp - 4) >> 3, e = (warp - 4) & 7, q = warp & 3, ch = e >> 2;
+    const int r = 32 * q + lane;                                  // tile row == TMEM lane
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + X * 256;
+    const uint32_t act_base = sb + SM_ACT + X * 65536;
+    arrive_leader(bar_act + 8 * X);                            // accumulator initially free
+    uint32_t dph = 0;
+    // swizzled 16-byte-chunk addresses of this thread's row in the two K-blocks of its column half
+    uint32_t swk[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) swk[c] = act_base + (uint32_t)(ch * 2) * 16384u + act_row_off(r) + (uint32_t)((c ^ (r & 7)) << 4);
+    for (int st = 0; st < nst; ++st) {
+      float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f, hp3 = 0.f;           // head partial sums of this thread's columns
+      const int lr = st * TC_ST + X * TC_TILE + r;                // row index inside this CTA's range
+      const bool valid = lr < nrows;
+      const int rl = (valid ? lr : nrows - 1) / p.S;              // local ray
+      long long n_ray = ray0 + rl;
+      if (n_ray > p.N - 1) n_ray = p.N - 1;                       // (padding CTA of an odd pair / empty range)
+      if (n_ray < 0) n_ray = 0;
+      for (int l = 0; l < NL; ++l) {
+        const bool tr = p.trace && blockIdx.x == 0 && st == 1 && e == 0 && lane == 0;
+        long long* trp = p.trace + 2048 + 4 * (X * 16 + l);
+        if (tr) trp[0] = clock64();
+        ptx::mbar_wait(bar_dfull + 8 * X, dph);
+        dph ^= 1;
+        ptx::tc_fence_after();
+        if (tr) trp[1] = clock64();
+        if (l <= D) {
+          // pts layer (ReLU) or feature layer (no activation): 128 columns per warp in 4 batches,
+          // the TMEM load of batch b+1 in flight while batch b is converted and stored
+          const bool last_pts = (l == D - 1);
+          const bool write_act = !(last_pts && !p.use_viewdirs);
+          const int colw = ch * 128;
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld_x32(t_lane + colw, va);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int col0 = colw + b * 32;
+            uint32_t (&v)[32] = (b & 1) ? vb : va;
+            uint32_t (&vn)[32] = (b & 1) ? va : vb;
+            ptx::tmem_ld_wait();
+            if (b < 3) ptx::tmem_ld_x32(t_lane + col0 + 32, vn);
+            float x[32];
+            as_float32(v, x);
+            if (last_pts) {
+              if (p.use_viewdirs) {                               // alpha_linear (run_nerf_helpers.py:106)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w = lds128(a_heads + (uint32_t)(col0 + 4 * j) * 4u);
+                  hp3 = fmaf(fmaxf(x[4 * j + 0], 0.f), w.x, hp3); hp3 = fmaf(fmaxf(x[4 * j + 1], 0.f), w.y, hp3);
+                  hp3 = fmaf(fmaxf(x[4 * j + 2], 0.f), w.z, hp3); hp3 = fmaf(fmaxf(x[4 * j + 3], 0.f), w.w, hp3);
+                }
+              } else {                                            // output_linear (:117)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w0 = lds128(a_heads + (uint32_t)(col0 + 4 * j) * 4u), w1 = lds128(a_heads + (uint32_t)(256 + col0 + 4 * j) * 4u);
+                  const float4 w2 = lds128(a_heads + (uint32_t)(512 + col0 + 4 * j) * 4u), w3 = lds128(a_heads + (uint32_t)(768 + col0 + 4 * j) * 4u);
+                  const float h0 = fmaxf(x[4 * j + 0], 0.f), h1 = fmaxf(x[4 * j + 1], 0.f), h2 = fmaxf(x[4 * j + 2], 0.f), h3 = fmaxf(x[4 * j + 3], 0.f);
+                  hp0 = fmaf(h0, w0.x, hp0); hp0 = fmaf(h1, w0.y, hp0); hp0 = fmaf(h2, w0.z, hp0); hp0 = fmaf(h3, w0.w, hp0);
+                  hp1 = fmaf(h0, w1.x, hp1); hp1 = fmaf(h1, w1.y, hp1); hp1 = fmaf(h2, w1.z, hp1); hp1 = fmaf(h3, w1.w, hp1);
+                  hp2 = fmaf(h0, w2.x, hp2); hp2 = fmaf(h1, w2.y, hp2); hp2 = fmaf(h2, w2.z, hp2); hp2 = fmaf(h3, w2.w, hp2);
+                  hp3 = fmaf(h0, w3.x, hp3); hp3 = fmaf(h1, w3.y, hp3); hp3 = fmaf(h2, w3.z, hp3); hp3 = fmaf(h3, w3.w, hp3);
+                }
+              }
+            }
+            if (write_act) {
+              // (b & 1) selects the K-block inside the column half; ch selects the half: the
+              // immediate part of the address is compile-time, the row/swizzle part is in sw[]
+              if (l < D) {
+                if (b == 0) store_act32_pre<true, 0>(x, swk); else if (b == 1) store_act32_pre<true, 32>(x, swk);
+                else if (b == 2) store_act32_pre<true, 64>(x, swk); else store_act32_pre<true, 96>(x, swk);
+              } else {
+                if (b == 0) store_act32_pre<false, 0>(x, swk); else if (b == 1) store_act32_pre<false, 32>(x, swk);
+                else if (b == 2) store_act32_pre<false, 64>(x, swk); else store_act32_pre<false, 96>(x, swk);
+              }
+            }
+          }
+          // this slot's bias selector for the NEXT layer
+          {
+            const int nxt = (l + 1 < n_bias) ? l + 1 : ((l == NL - 1) ? 0 : -1);
+            if (q == 0 && ch == 0 && lane < 8 && nxt >= 0) write_bias_selector(sb + SM_ONES + X * 256, lane, nxt, n_bias);
+          }
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          arrive_leader(bar_act + 8 * X);
+          if (tr) trp[2] = clock64();
+        } else {
+          // views_linears[0] (N=128): 64 columns per warp; + per-ray view bias, ReLU, rgb_linear
+          const float* vbrow = p.vb + n_ray * 128;
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld_x32(t_lane + ch * 64, va);
+          ptx::tmem_ld_x32(t_lane + ch * 64 + 32, vb);
+          ptx::tmem_ld_wait();
+          if (q == 0 && ch == 0 && lane < 8) write_bias_selector(sb + SM_ONES + X * 256, lane, 0, n_bias);   // next super-tile, layer 0
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          arrive_leader(bar_act + 8 * X);                      // accumulator drained: next super-tile may start
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int col0 = ch * 64 + b * 32;
+            const uint32_t (&v)[32] = b ? vb : va;
+            const float4* vb4 = reinterpret_cast<const float4*>(vbrow + col0);
+            const uint32_t w0 = a_heads + (uint32_t)(256 + col0) * 4u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = vb4[j];
+              const float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
+              const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
+              const float4 wr = lds128(w0 + 16 * j), wg = lds128(w0 + 512 + 16 * j), wb = lds128(w0 + 1024 + 16 * j);
+              hp0 = fmaf(h0, wr.x, hp0); hp0 = fmaf(h1, wr.y, hp0); hp0 = fmaf(h2, wr.z, hp0); hp0 = fmaf(h3, wr.w, hp0);
+              hp1 = fmaf(h0, wg.x, hp1); hp1 = fmaf(h1, wg.y, hp1); hp1 = fmaf(h2, wg.z, hp1); hp1 = fmaf(h3, wg.w, hp1);
+              hp2 = fmaf(h0, wb.x, hp2); hp2 = fmaf(h1, wb.y, hp2); hp2 = fmaf(h2, wb.z, hp2); hp2 = fmaf(h3, wb.w, hp2);
+            }
+          }
+        }
+      }
+      // ---- heads: combine the two column halves, then raw -> compositing (ch == 0 warps) ----
+      const uint32_t part = a_part + (uint32_t)(X * 128 + r) * 16u;
+      if (ch == 1) sts128(part, make_float4(hp0, hp1, hp2, hp3));
+      ptx::named_bar_sync(1 + X, 256);
+      if (ch == 0) {
+        const float4 o = lds128(part);
+        float4 raw4;
+        if (p.use_viewdirs) raw4 = make_float4(hp0 + o.x + lds32(a_heads + 641 * 4), hp1 + o.y + lds32(a_heads + 642 * 4),
+                                               hp2 + o.z + lds32(a_heads + 643 * 4), hp3 + o.w + lds32(a_heads + 640 * 4));
+        else raw4 = make_float4(hp0 + o.x + lds32(a_heads + 1024 * 4), hp1 + o.y + lds32(a_heads + 1025 * 4),
+                                hp2 + o.z + lds32(a_heads + 1026 * 4), hp3 + o.w + lds32(a_heads + 1027 * 4));
+        const long long m = row_begin + lr;
+        if (valid && p.out.raw) reinterpret_cast<float4*>(p.out.raw)[m] = raw4;
+        if (p.do_composite) {
+          const int k = lr - rl * p.S;
+          float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, z = 0.f;
+          if (valid) {
+            const float* rd = p.rays + n_ray * p.ray_stride + 3;
+            const float norm = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);         // run_nerf.py:280
+            z = p.z_vals[m];
+            float dist = (k == p.S - 1) ? 1e10f : __fsub_rn(p.z_vals[m + 1], z);             // :277-278
+            dist = __fmul_rn(dist, norm);
+            const float sg = raw4.w + (p.noise ? p.noise[m] : 0.0f);
+            alpha = __fsub_rn(1.0f, expf(-fmaxf(sg, 0.0f) * dist));                           // :275
+            cr = sigmoidf_acc(raw4.x); cg = sigmoidf_acc(raw4.y); cb = sigmoidf_acc(raw4.z); // :282
+          }
+          // warp-local part (independent of the carry): transmittance / weights relative to
+          // max(ray start, warp start) and their segmented sums
+          const bool seg_start = valid && (k == 0), seg_end = valid && (k == p.S - 1);
+          const unsigned smask = __ballot_sync(0xffffffffu, seg_start);
+          const unsigned below = smask & ((lane == 31) ? 0xffffffffu : ((2u << lane) - 1u));
+          const int s = below ? (31 - __clz(below)) : -1;
+          const float qv = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;         // :295
+          const float pv = seg_scan_mul(qv, lane, s);
+          float ev = __shfl_up_sync(0xffffffffu, pv, 1);
+          if (lane == 0 || s == lane) ev = 1.0f;
+          const float wl = valid ? alpha * ev : 0.0f;
+          float t_r = seg_scan_add(wl * cr, lane, s), t_g = seg_scan_add(wl * cg, lane, s), t_b = seg_scan_add(wl * cb, lane, s);
+          float t_d = seg_scan_add(wl * z, lane, s), t_a = seg_scan_add(wl, lane, s);
+          // take the compositing turn: rows are consumed in order across warps / slots / super-tiles;
+          // only the few flops that thread the carry through this warp sit on the serial chain
+          const uint32_t ticket = (uint32_t)((st * 2 + X) * 4 + q);
+          if (lane == 0) { while (ld_acquire_shared(a_carry + CARRY_TURN) != ticket) { } }
+          __syncwarp();
+          const float Tin = lds32(a_carry + CARRY_T);
+          const float c_r = lds32(a_carry + CARRY_R), c_g = lds32(a_carry + CARRY_G), c_b = lds32(a_carry + CARRY_B);
+          const float c_d = lds32(a_carry + CARRY_D), c_a = lds32(a_carry + CARRY_A);
+          __syncwarp();
+          if (s < 0) { t_r = fmaf(Tin, t_r, c_r); t_g = fmaf(Tin, t_g, c_g); t_b = fmaf(Tin, t_b, c_b); t_d = fmaf(Tin, t_d, c_d); t_a = fmaf(Tin, t_a, c_a); }
+          if (lane == 31) {
+            if (seg_end) {
+              sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
+              sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f);
+            } else {
+              sts32(a_carry + CARRY_T, (s >= 0) ? pv : Tin * pv);
+              sts32(a_carry + CARRY_R, t_r); sts32(a_carry + CARRY_G, t_g); sts32(a_carry + CARRY_B, t_b);
+              sts32(a_carry + CARRY_D, t_d); sts32(a_carry + CARRY_A, t_a);
+            }
+            st_release_shared(a_carry + CARRY_TURN, ticket + 1u);
+          }
+          // off the chain: weights and per-ray outputs
+          if (valid && p.out.weights) p.out.weights[m] = (s < 0) ? Tin * wl : wl;
+          if (seg_end) {
+            float rr = t_r, gg = t_g, bb = t_b;
+            if (p.white_bkgd) { const float bg = 1.0f - t_a; rr += bg; gg += bg; bb += bg; }  // :302-303
+            if (p.out.rgb_map) { p.out.rgb_map[n_ray * 3] = rr; p.out.rgb_map[n_ray * 3 + 1] = gg; p.out.rgb_map[n_ray * 3 + 2] = bb; }
+            if (p.out.disp_map) {
+              const float ratio = t_d / t_a;
+              const float mm = (ratio != ratio) ? ratio : fmaxf(1e-10f, ratio);              // :299
+              p.out.disp_map[n_ray] = 1.0f / mm;
+            }
+            if (p.out.acc_map) p.out.acc_map[n_ray] = t_a;
+            if (p.out.depth_map) p.out.depth_map[n_ray] = t_d;
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== sampler (warp 3) ===========================
+    const int t = threadIdx.x - 96;                               // 0..31
+    for (int st = 0; st < nst; ++st) {
+      ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const int X = i >> 2, tr_ = t + 32 * (i & 3);             // tile slot, tile row
+        const int lr = st * TC_ST + X * TC_TILE + tr_;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (lr < nrows) {
+          const long long m = row_begin + lr;
+          if (p.pts) { px = p.pts[m * 3]; py = p.pts[m * 3 + 1]; pz = p.pts[m * 3 + 2]; }
+          else {
+            const float* ry = p.rays + (ray0 + lr / p.S) * p.ray_stride;
+            const float z = p.z_vals[m];
+            px = __fadd_rn(ry[0], __fmul_rn(ry[3], z));                                       // run_nerf.py:381
+            py = __fadd_rn(ry[1], __fmul_rn(ry[4], z));
+            pz = __fadd_rn(ry[2], __fmul_rn(ry[5], z));
+          }
+        }
+        // 64 encoded channels (63 + zero pad), one fp16 store each into the 128B-swizzled K-block
+        const uint32_t row = sb + SM_ENC + X * 16384 + act_row_off(tr_);
+        auto put = [&](int c, float v) {
+          const uint32_t a = row + (uint32_t)((((c >> 3) ^ (tr_ & 7)) << 4) + ((c & 7) << 1));
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
+        };
+        put(0, px); put(1, py); put(2, pz);
+#pragma unroll 1
+        for (int f = 0; f < 10; ++f) {
+          float s0 = 0.f, c0 = 0.f, s1 = 0.f, c1 = 0.f, s2 = 0.f, c2 = 0.f;
+          if (f < p.L) {
+            const float sc = (float)(1 << f);
+            sincosf(px * sc, &s0, &c0); sincosf(py * sc, &s1, &c1); sincosf(pz * sc, &s2, &c2);
+          }
+          const int c = 3 + 6 * f;
+          put(c + 0, s0); put(c + 1, s1); put(c + 2, s2); put(c + 3, c0); put(c + 4, c1); put(c + 5, c2);
+        }
+        put(63, 0.f);
+      }
+      ptx::fence_proxy_async_smem();
+      arrive_leader(bar_encfull);
+    }
+  }
+
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();                                  // the pair's MMAs / multicast commits are all done
+  if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
+}
+
+}  // namespace nb
