@@ -44,7 +44,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   const uint32_t bar_act = sb + SM_BARS + 160;        // [2] (leader)
   const uint32_t bar_encfull = sb + SM_BARS + 176;    //     (leader)
   const uint32_t bar_encfree = sb + SM_BARS + 184;
+  const uint32_t bar_turn = sb + SM_BARS + 192;       // [2] (leader, local): the two issuer warps take turns in stream order
   // arrive on a barrier that lives in the leader CTA
+  // debug heartbeat: trace[blockIdx.x * 32 + role] = last wait this role entered (trace may be mapped host memory)
+  auto hb_ = [&](int role, long long code) { if (p.trace && lane == 0) { volatile long long* t = p.trace; t[blockIdx.x * 32 + role] = code; } };
   auto arrive_leader = [&](uint32_t bar) { if (leader) ptx::mbar_arrive(bar); else ptx::mbar_arrive_cluster(ptx::mapa(bar, 0)); };
 
   // this CTA's rays / rows; both CTAs of a pair run the same number of super-tiles
@@ -76,6 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 512); }
     ptx::mbar_init(bar_encfull, 2 * TC_SAMPLER_THREADS);
     ptx::mbar_init(bar_encfree, 2);
+    ptx::mbar_init(bar_turn, 1); ptx::mbar_init(bar_turn + 8, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish2(); }
@@ -96,6 +100,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         for (int X = 0; X < 2; ++X) {                     // pass of slot A, then the same chunks again for slot B
           const uint8_t* src = lsrc + rank * hb;
           for (int c = 0; c < nch; ++c) {
+            hb_(0, 1000000 + st * 10000 + l * 100 + X * 50 + c);
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
             if (ptx::elect_one()) {
               ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, hb);
@@ -112,7 +117,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   } else if ((warp == 1 || warp == 2) && leader) {
     // =========================== MMA issuers (leader CTA): warp 1 -> slot A passes, warp 2 -> slot B passes =====
     const int X = warp - 1;
-    uint32_t gi = 0, actph = 0;                           // gi = index of the next chunk in the pair's stream
+    uint32_t gi = 0, actph = 0, turnph = 0;               // gi = index of the next chunk in the pair's stream
+    bool first_pass = (X == 0);                           // slot A's very first pass needs no hand-over
     const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
     const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
     const uint64_t sel_desc = ptx::umma_desc(sb + SM_ONES + X * 256, 0, ptx::UMMA_SW32);
@@ -120,6 +126,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem, 0) + X * 256;
     for (int st = 0; st < nst; ++st) {
       const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0 && lane == 0;
+      hb_(1 + X, 9000000 + st * 10000);
       ptx::mbar_wait_cluster(bar_encfull, st & 1);
       for (int l = 0; l < NL; ++l) {
         const int nch = tc_layer_chunks(l, D, p.skip);
@@ -127,17 +134,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         const bool has_bias = tc_layer_has_bias(l, D);
         const uint32_t idesc = ptx::umma_idesc_f16(256, (l == D + 1) ? 128 : 256);
         if (X == 1) gi += nch;                            // skip slot A's pass of this layer
+        // passes are consumed strictly in stream order (A(l), B(l), A(l+1), ...): a parity wait on a ring stage
+        // is only meaningful once every earlier chunk of the stream has been consumed
+        if (!first_pass) { ptx::mbar_wait(bar_turn + 8 * X, turnph); turnph ^= 1; }
+        first_pass = false;
         for (int c0 = 0; c0 < nch; c0 += 2) {
           long long* trp = p.trace + 4 * (l * 10 + c0);
           if (tr) trp[0] = clock64();
           const bool two = (c0 + 1 < nch);
           const uint32_t g0 = gi + c0, s0 = g0 % TC2_NST, p0 = (g0 / TC2_NST) & 1;
           const uint32_t g1 = g0 + 1, s1 = g1 % TC2_NST, p1 = (g1 / TC2_NST) & 1;
+          hb_(1 + X, 1000000 + st * 10000 + l * 100 + c0);
           ptx::mbar_wait(bar_wfull + 8 * s0, p0);
+          hb_(1 + X, 2000000 + st * 10000 + l * 100 + c0);
           ptx::mbar_wait_cluster(bar_pfull + 8 * s0, p0);
+          hb_(1 + X, 3000000 + st * 10000 + l * 100 + c0);
           if (two) { ptx::mbar_wait(bar_wfull + 8 * s1, p1); ptx::mbar_wait_cluster(bar_pfull + 8 * s1, p1); }
           if (tr) trp[1] = clock64();
-          if (c0 == 0) { ptx::mbar_wait_cluster(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
+          if (c0 == 0) { hb_(1 + X, 4000000 + st * 10000 + l * 100 + c0); ptx::mbar_wait_cluster(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
+          hb_(1 + X, 5000000 + st * 10000 + l * 100 + c0);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (c0 == 0 && has_bias) ptx::mma2_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
@@ -161,6 +176,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           __syncwarp();
           if (tr) trp[3] = clock64();
         }
+        if (ptx::elect_one()) ptx::mbar_arrive(bar_turn + 8 * (X ^ 1));   // hand the stream over to the other slot's issuer
+        __syncwarp();
         gi += nch;                                        // own pass consumed
         if (X == 0) gi += nch;                            // skip slot B's pass of this layer
       }
@@ -173,6 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       for (int l = 0; l < NL; ++l) {
         const int n2 = 2 * tc_layer_chunks(l, D, p.skip);
         for (int c = 0; c < n2; ++c) {
+          hb_(1, 1000000 + st * 10000 + l * 100 + c);
           ptx::mbar_wait(bar_wfull + 8 * stage, ph);
           if (ptx::elect_one()) ptx::mbar_arrive_cluster(remote_pfull + 8 * stage);
           __syncwarp();
@@ -206,7 +224,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         const bool tr = p.trace && blockIdx.x == 0 && st == 1 && e == 0 && lane == 0;
         long long* trp = p.trace + 2048 + 4 * (X * 16 + l);
         if (tr) trp[0] = clock64();
+        hb_(warp, 1000000 + st * 10000 + l * 100);
         ptx::mbar_wait(bar_dfull + 8 * X, dph);
+        hb_(warp, 2000000 + st * 10000 + l * 100);
         dph ^= 1;
         ptx::tc_fence_after();
         if (tr) trp[1] = clock64();
@@ -380,7 +400,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     // =========================== sampler (warp 3) ===========================
     const int t = threadIdx.x - 96;                               // 0..31
     for (int st = 0; st < nst; ++st) {
+      hb_(3, 1000000 + st * 10000);
       ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
+      hb_(3, 2000000 + st * 10000);
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
         const int X = i >> 2, tr_ = t + 32 * (i & 3);             // tile slot, tile row
@@ -422,6 +444,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   }
 
 
+  hb_(warp, 7000000);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();                                  // the pair's MMAs / multicast commits are all done
