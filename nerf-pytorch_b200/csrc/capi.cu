@@ -116,7 +116,33 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
     tl->flops = 2.0 * net_macs_per_row(*net) * (double)rows;
     cudaEventRecord(tl->a, st);
   }
-  if (pair_mode) march_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
+  if (pair_mode) {
+    // tensor map over the packed chunk stream, viewed as [rows][256] uint16 (512-byte rows), box = 8 rows (4 KB)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      NB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      NB_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    CUtensorMap wmap8k, wmap4k;
+    const cuuint64_t gdim[2] = {256, (cuuint64_t)(PL.chunk_bytes / 512)};
+    const cuuint64_t gstr[1] = {512};
+    const cuuint32_t box16[2] = {256, 16}, box8[2] = {256, 8}, estr[2] = {1, 1};
+    CUresult cr = encode(&wmap8k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint8_t*>(p.chunks), gdim, gstr, box16, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    cr = encode(&wmap4k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint8_t*>(p.chunks), gdim, gstr, box8, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    march_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p, wmap8k, wmap4k);
+  }
   else march_tc_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
   if (tl) cudaEventRecord(tl->b, st);
   NB_LAUNCH_OK("march_tc_kernel");

@@ -17,6 +17,7 @@
 //   act[2]     leader  : 512 arrivals = 256 local epilogue threads + 256 remote (accumulator drained, A tile written)
 //   enc_full   leader  : 64 arrivals (both samplers);  enc_free both: multicast commit after the last encoding chunk
 #pragma once
+#include <cuda.h>
 #include "fused_tc.cuh"
 
 namespace nb {
@@ -24,7 +25,7 @@ namespace nb {
 constexpr int TC2_NST = 6;                       // ring stages
 constexpr uint32_t TC2_STAGE_BYTES = 8192;       // half of a [256 x 32] fp16 chunk
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p, const __grid_constant__ CUtensorMap wmap8k, const __grid_constant__ CUtensorMap wmap4k) {
   uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -47,7 +48,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   const uint32_t bar_turn = sb + SM_BARS + 192;       // [2] (leader, local): the two issuer warps take turns in stream order
   // arrive on a barrier that lives in the leader CTA
   // debug heartbeat: trace[blockIdx.x * 32 + role] = last wait this role entered (trace may be mapped host memory)
-  auto hb_ = [&](int role, long long code) { if (p.trace && lane == 0) { volatile long long* t = p.trace; t[blockIdx.x * 32 + role] = code; } };
+  auto hb_ = [&](int role, long long code) { if (p.trace && lane == 0 && blockIdx.x < 32) { volatile long long* t = p.trace; t[3000 + blockIdx.x * 32 + role] = code; } };
   auto arrive_leader = [&](uint32_t bar) { if (leader) ptx::mbar_arrive(bar); else ptx::mbar_arrive_cluster(ptx::mapa(bar, 0)); };
 
   // this CTA's rays / rows; both CTAs of a pair run the same number of super-tiles
@@ -75,7 +76,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f); st_release_shared(a_carry + CARRY_TURN, 0u);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < TC2_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); ptx::mbar_init(bar_pfull + 8 * i, 1); }
+    for (int i = 0; i < TC2_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); }
     for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 512); }
     ptx::mbar_init(bar_encfull, 2 * TC_SAMPLER_THREADS);
     ptx::mbar_init(bar_encfree, 2);
@@ -101,12 +102,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           const uint8_t* src = lsrc + rank * hb;
           for (int c = 0; c < nch; ++c) {
             hb_(0, 1000000 + st * 10000 + l * 100 + X * 50 + c);
+            const bool ptr_ = p.trace && blockIdx.x == 0 && st == 1 && l == 2 && lane == 0;
+            if (ptr_) p.trace[1024 + 4 * (X * 8 + c)] = clock64();
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
+            if (ptr_) p.trace[1024 + 4 * (X * 8 + c) + 1] = clock64();
             if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, hb);
-              ptx::bulk_g2s(sb + SM_WRING + stage * TC2_STAGE_BYTES, src, hb, bar_wfull + 8 * stage);
+              // both halves complete on the LEADER's w_full: the leader expects the bytes of both CTAs' copies and
+              // every TMA load (cta_group::2) counts its bytes on the leader's mbarrier.  The stream is viewed as
+              // a [rows][256] uint16 tensor; box = 16 rows (8 KB half chunk) or 8 rows (4 KB, view layer).
+              if (leader) ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, 2 * hb);
+              const int row = (int)((src - p.chunks) >> 9);
+              ptx::tma2_load_2d(sb + SM_WRING + stage * TC2_STAGE_BYTES, (hb > 4096) ? (const void*)&wmap8k : (const void*)&wmap4k, 0, row,
+                                bar_wfull + 8 * stage);
             }
             __syncwarp();
+            if (ptr_) p.trace[1024 + 4 * (X * 8 + c) + 2] = clock64();
             src += cb;
             if (++stage == TC2_NST) { stage = 0; ph ^= 1; }
           }
@@ -138,29 +148,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         // is only meaningful once every earlier chunk of the stream has been consumed
         if (!first_pass) { ptx::mbar_wait(bar_turn + 8 * X, turnph); turnph ^= 1; }
         first_pass = false;
-        for (int c0 = 0; c0 < nch; c0 += 2) {
+        for (int c0 = 0; c0 < nch; c0 += 3) {
+          // up to three stream chunks per hand-off (6-7 MMAs back to back); the ring keeps three more in flight
           long long* trp = p.trace + 4 * (l * 10 + c0);
           if (tr) trp[0] = clock64();
-          const bool two = (c0 + 1 < nch);
-          const uint32_t g0 = gi + c0, s0 = g0 % TC2_NST, p0 = (g0 / TC2_NST) & 1;
-          const uint32_t g1 = g0 + 1, s1 = g1 % TC2_NST, p1 = (g1 / TC2_NST) & 1;
+          const int ng = (nch - c0 < 3) ? nch - c0 : 3;
           hb_(1 + X, 1000000 + st * 10000 + l * 100 + c0);
-          ptx::mbar_wait(bar_wfull + 8 * s0, p0);
-          hb_(1 + X, 2000000 + st * 10000 + l * 100 + c0);
-          ptx::mbar_wait_cluster(bar_pfull + 8 * s0, p0);
-          hb_(1 + X, 3000000 + st * 10000 + l * 100 + c0);
-          if (two) { ptx::mbar_wait(bar_wfull + 8 * s1, p1); ptx::mbar_wait_cluster(bar_pfull + 8 * s1, p1); }
+          for (int h = 0; h < ng; ++h) { const uint32_t g = gi + c0 + h; ptx::mbar_wait(bar_wfull + 8 * (g % TC2_NST), (g / TC2_NST) & 1); }
           if (tr) trp[1] = clock64();
           if (c0 == 0) { hb_(1 + X, 4000000 + st * 10000 + l * 100 + c0); ptx::mbar_wait_cluster(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
           hb_(1 + X, 5000000 + st * 10000 + l * 100 + c0);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (c0 == 0 && has_bias) ptx::mma2_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1 && !two) break;
+            for (int h = 0; h < ng; ++h) {
               const int c = c0 + h;
-              const uint32_t sg = h ? s1 : s0;
+              const uint32_t sg = (gi + c) % TC2_NST;
               const bool is_enc = (l == 0) || (skip_layer && c < 2);
               const int kc = skip_layer ? c - 2 : c;
               const uint64_t bd = bdesc0 + ((SM_WRING + sg * TC2_STAGE_BYTES) >> 4);
@@ -171,7 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
               ptx::mma2_commit_mc(bar_wempty + 8 * sg, 3);
               if (is_enc && c == 1 && l == last_enc_layer) ptx::mma2_commit_mc(bar_encfree, 3);
             }
-            if (c0 + 2 >= nch) ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
+            if (c0 + 3 >= nch) ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
           }
           __syncwarp();
           if (tr) trp[3] = clock64();
@@ -182,23 +185,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         if (X == 0) gi += nch;                            // skip slot B's pass of this layer
       }
     }
-  } else if (warp == 1 && !leader) {
-    // =========================== relay (peer CTA): forward "my half landed" to the leader ====================
-    uint32_t stage = 0, ph = 0;
-    const uint32_t remote_pfull = ptx::mapa(bar_pfull, 0);
-    for (int st = 0; st < nst; ++st)
-      for (int l = 0; l < NL; ++l) {
-        const int n2 = 2 * tc_layer_chunks(l, D, p.skip);
-        for (int c = 0; c < n2; ++c) {
-          hb_(1, 1000000 + st * 10000 + l * 100 + c);
-          ptx::mbar_wait(bar_wfull + 8 * stage, ph);
-          if (ptx::elect_one()) ptx::mbar_arrive_cluster(remote_pfull + 8 * stage);
-          __syncwarp();
-          if (++stage == TC2_NST) { stage = 0; ph ^= 1; }
-        }
-      }
-  } else if (warp == 2 && !leader) {
-    // idle
+  } else if ((warp == 1 || warp == 2) && !leader) {
+    // idle: the peer's bulk copies signal the leader's w_full barriers directly
   } else if (warp >= 4) {
     // =========================== epilogue ===========================
     // TMEM lane quadrant is fixed by (warp id % 4)

@@ -116,6 +116,17 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// 2D tensor-map TMA load into this CTA's shared memory whose completion bytes are counted on the LEADER CTA's
+// mbarrier (cta_group::2: the peer bit of the mbarrier address is cleared, as in CUTLASS' SM100_TMA_2SM_LOAD)
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
+}
+// relaxed remote arrive: pure signal (the waiter's data dependency is carried by the control dependency on the
+// local wait that precedes it; no data written by this thread is published)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"

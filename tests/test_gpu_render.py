@@ -103,3 +103,33 @@ def test_empty_and_single_ray(G):
         r1 = G.nb.render_rays(G.dev(packed), net, q, 64, N_importance=128, network_fine=None, white_bkgd=True)   # fine None -> coarse net (:399)
     ref = G.O.render_rays(packed, pc, 64, p_fine=None, N_importance=128, white_bkgd=True)
     assert rel_l2(r1["rgb_map"].cpu().numpy(), ref["rgb_map"]) < 2e-4
+
+
+def test_cta_pair_kernel_matches_default_kernel():
+    """NERF_B200_PAIR=1 selects the cta_group::2 pair kernel (fused_tc2.cuh, experimental): same results as the
+    default kernel to fp32 accumulation-order noise.  Run in a subprocess because the mode is latched at first launch."""
+    import os, subprocess, sys
+    code = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import gpu_common as G
+sb = G.synth.ray_batch("lego", 777, seed=5)
+nets = [G.make_net(G.synth.nerf_state(0)), G.make_net(G.synth.nerf_state(1))]
+with torch.no_grad():
+    r = G.nb.render(400, 400, sb["K"], rays=G.dev(sb["rays"]), ndc=False, near=2., far=6., use_viewdirs=True, network_fn=nets[0],
+                    network_fine=nets[1], network_query_fn=G.query_fn(), N_samples=64, N_importance=128, perturb=0.,
+                    white_bkgd=True, raw_noise_std=0.)
+np.save(sys.argv[1], torch.cat([r[0], r[1][:, None], r[2][:, None], r[3]["rgb0"]], -1).cpu().numpy())
+'''
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ("0", "1"):
+            path = os.path.join(tmp, f"o{mode}.npy")
+            env = dict(os.environ, NERF_B200_PAIR=mode)
+            subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=env, timeout=300)
+            outs.append(np.load(path))
+    assert rel_l2(outs[1][:, :3], outs[0][:, :3]) < 2e-5
+    assert rel_l2(outs[1][:, 4], outs[0][:, 4]) < 2e-5
+    assert rel_l2(outs[1][:, 5:8], outs[0][:, 5:8]) < 2e-5

@@ -41,6 +41,8 @@ for l in range(10):
         print(f"  L{l} c{c}: start {a[0]-t00:7d}  wfull_wait {a[1]-a[0]:5d}  act_wait {(a[2]-a[1]) if a[2] else 0:5d}  total {a[3]-a[0]:5d}  gap_prev {(a[0]-prev) if prev else 0:5d}")
         prev = a[3]
 print("super-tile issuer span:", iss[iss > 0].max() - t00)
+pp = t[1024:1024 + 64].reshape(16, 4)
+print("pair producer L2: (pass,chunk) start, wempty_wait, issue", [(i // 8, i % 8, int(r[0] - t00), int(r[1] - r[0]), int(r[2] - r[1])) for i, r in enumerate(pp) if r[0]])
 print("producer: chunk | wempty_wait")
 pw = [(i, p[1] - p[0], p[0] - t00) for i, p in enumerate(prod) if p[0]]
 print("  ", [(i, int(w)) for i, w, _ in pw][:160])
