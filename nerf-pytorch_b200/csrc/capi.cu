@@ -84,7 +84,7 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
     NB_CHECK_ARG(workspace != nullptr && workspace_bytes >= (size_t)N * 128 * 4, "workspace too small: need %zu bytes", (size_t)N * 128 * 4);
     NB_CHECK_ARG(3 + 6 * Lv == net->input_ch_views || (Lv == 0 && net->input_ch_views == 3), "multires_views mismatch");
     float* vb = static_cast<float*>(workspace);
-    view_bias_kernel<<<(unsigned)N, 128, 0, st>>>(dirs, dir_stride, N, Lv, net->input_ch_views,
+    view_bias_kernel<<<cdiv(N, VB_RAYS), 128, 0, st>>>(dirs, dir_stride, N, Lv, net->input_ch_views,
                                                   reinterpret_cast<const float*>(pk + PL.off_vdir), vb);
     NB_LAUNCH_OK("view_bias_kernel");
     p.vb = vb;

@@ -182,22 +182,33 @@ __global__ void pack_tables_kernel(PackTables t, uint8_t* __restrict__ dst) {
 
 // view-direction contribution of views_linears[0], once per ray (the reference recomputes it per
 // sample through the expand at run_nerf.py:44-46):  vb[n][j] = b[j] + sum_c W[j][256+c] * enc(v_n)[c]
-__global__ void view_bias_kernel(const float* __restrict__ dirs, int dir_stride, long long N, int Lv, int ICV,
-                                 const float* __restrict__ vdir, float* __restrict__ vb) {
-  __shared__ float s_enc[64];
-  const long long n = blockIdx.x;
+constexpr int VB_RAYS = 32;       // rays per block
+__global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict__ dirs, int dir_stride, long long N, int Lv, int ICV,
+                                                     const float* __restrict__ vdir, float* __restrict__ vb) {
+  __shared__ float s_enc[VB_RAYS][64];
+  const long long n0 = (long long)blockIdx.x * VB_RAYS;
   const int j = threadIdx.x;
-  if (j < ICV) {
-    float v;
-    const float* d = dirs + n * dir_stride;
-    if (j < 3) v = d[j];
-    else { int f = (j - 3) / 6, q = (j - 3) % 6; float a = __fmul_rn(d[q % 3], exp2f((float)f)); v = (q < 3) ? sinf(a) : cosf(a); }
-    s_enc[j] = v;
+  for (int i = threadIdx.x; i < VB_RAYS * ICV; i += 128) {
+    const int r = i / ICV, c = i - r * ICV;
+    float v = 0.0f;
+    if (n0 + r < N) {
+      const float* d = dirs + (n0 + r) * dir_stride;
+      if (c < 3) v = d[c];
+      else { int f = (c - 3) / 6, q = (c - 3) % 6; float a = __fmul_rn(d[q % 3], exp2f((float)f)); v = (q < 3) ? sinf(a) : cosf(a); }
+    }
+    s_enc[r][c] = v;
   }
+  float w[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) w[c] = (c < ICV) ? vdir[j * ICV + c] : 0.0f;
+  const float b = vdir[128 * ICV + j];
   __syncthreads();
-  float acc = vdir[128 * ICV + j];
-  for (int c = 0; c < ICV; ++c) acc = fmaf(vdir[j * ICV + c], s_enc[c], acc);
-  vb[n * 128 + j] = acc;
+  for (int r = 0; r < VB_RAYS && n0 + r < N; ++r) {
+    float acc = b;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) if (c < ICV) acc = fmaf(w[c], s_enc[r][c], acc);
+    vb[(n0 + r) * 128 + j] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -265,10 +265,12 @@ __device__ __forceinline__ void sample_pdf_row(const float* s_bins, const float*
   float part = 0.0f;
   for (int i = lane; i < B - 1; i += 32) part += __fadd_rn(s_w[i], 1e-5f);                    // :198
   const float total = warp_sum(part);                                                         // :199
+  for (int i = lane; i < B - 1; i += 32) s_cdf[i + 1] = __fdiv_rn(__fadd_rn(s_w[i], 1e-5f), total);   // pdf (:199)
+  __syncwarp();
   if (lane == 0) {                                  // sequential cumsum, like torch/numpy (:200-201)
     float c = 0.0f;
     s_cdf[0] = 0.0f;
-    for (int i = 0; i < B - 1; ++i) { c = __fadd_rn(c, __fdiv_rn(__fadd_rn(s_w[i], 1e-5f), total)); s_cdf[i + 1] = c; }
+    for (int i = 1; i < B; ++i) { c = __fadd_rn(c, s_cdf[i]); s_cdf[i] = c; }
   }
   __syncwarp();
   for (int j = lane; j < n_samples; j += 32) {
@@ -338,22 +340,26 @@ __global__ void fine_z_kernel(const float* __restrict__ z_vals, const float* __r
   if (lane == 0 && z_std) z_std[n] = sqrtf(var);
   if (z_samples_out) for (int j = lane; j < n_imp; j += 32) z_samples_out[n * n_imp + j] = o[j];
   __syncwarp();
-  // bitonic sort of s_all[0..P) ascending (:396)
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < P; i += 32) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          float a = s_all[i], b = s_all[ixj];
-          bool asc = ((i & k) == 0);
-          if ((a > b) == asc) { s_all[i] = b; s_all[ixj] = a; }
-        }
-      }
-      __syncwarp();
-    }
-  }
+  // sort(cat[z_vals, z_samples]) (:396) by ranking: z_vals is already ascending, so
+  //   rank(z_i) = i + #{samples < z_i}            rank(s_j) = #{z <= s_j} + #{s_k < s_j, or == with k < j}
+  // (ties resolved z-before-sample and by index: a permutation, like any sort)
   const int SF = S + n_imp;
-  for (int i = lane; i < SF; i += 32) z_fine[n * SF + i] = s_all[i];
+  float* zout = z_fine + n * SF;
+  for (int i = lane; i < S; i += 32) {
+    const float zi = s_all[i];
+    int cnt = 0;
+    for (int k = 0; k < n_imp; ++k) cnt += (o[k] < zi) ? 1 : 0;
+    zout[i + cnt] = zi;
+  }
+  for (int j = lane; j < n_imp; j += 32) {
+    const float sj = o[j];
+    int lo = 0, hi = S;                               // #{z <= s_j}: first index with z > s_j
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (s_all[mid] > sj) hi = mid; else lo = mid + 1; }
+    int cnt = lo;
+    for (int k = 0; k < n_imp; ++k) { const float sk = o[k]; cnt += (sk < sj || (sk == sj && k < j)) ? 1 : 0; }
+    zout[cnt] = sj;
+  }
 }
+
 
 }  // namespace nb
