@@ -183,6 +183,7 @@ int nerf_b200_debug_set_trace(void* dev_buf_4096_i64);
 int nerf_b200_debug_mma_rate(int reps, int N, int b_sw64, void* out_2_i64, void* stream);
 int nerf_b200_debug_ldtm_rate(int reps, int shape, int nwarps, int mma, void* out_2_i64, void* stream);
 int nerf_b200_debug_issue_probe(int reps, int nmma, int flags, void* out_2_i64, void* stream);
+int nerf_b200_debug_l2_stream(const void* buf, int buf_bytes, int chunk, int stages, int passes, int nblocks, void* out_i64, void* stream);
 int nerf_b200_debug_epi_rate(int reps, int mode, int mma, void* out_2_i64, void* stream);
 
 /* ---- device-time accounting of the dominant kernel (march_tc_kernel) for bench.py's roofline:

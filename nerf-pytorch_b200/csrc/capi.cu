@@ -129,15 +129,18 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
       NB_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
       encode = reinterpret_cast<EncodeFn>(fn);
     }
-    CUtensorMap wmap8k, wmap4k;
+    CUtensorMap wmap8k, wmap4k;                 // boxes of two chunk halves: 2 x 8 KB (32 rows) and 2 x 4 KB (16 rows, view layer)
     const cuuint64_t gdim[2] = {256, (cuuint64_t)(PL.chunk_bytes / 512)};
     const cuuint64_t gstr[1] = {512};
-    const cuuint32_t box16[2] = {256, 16}, box8[2] = {256, 8}, estr[2] = {1, 1};
-    CUresult cr = encode(&wmap8k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint8_t*>(p.chunks), gdim, gstr, box16, estr,
+    const cuuint32_t box16[2] = {256, 32}, box8[2] = {256, 16}, estr[2] = {1, 1};
+    uint8_t* pair_stream = const_cast<uint8_t*>(pk + PL.off_pair);
+    p.chunks = pair_stream;                     // the pair kernel walks the rank-split stream
+    p.pair_half_bytes = PL.chunk_bytes / 2;
+    CUresult cr = encode(&wmap8k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pair_stream, gdim, gstr, box16, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    cr = encode(&wmap4k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint8_t*>(p.chunks), gdim, gstr, box8, estr,
+    cr = encode(&wmap4k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pair_stream, gdim, gstr, box8, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
@@ -225,6 +228,19 @@ int nerf_b200_pack_weights(const NerfNetParams* net, void* packed, size_t packed
   dim3 grid(4, job.n);
   pack_chunks_kernel<<<grid, 256, 0, st>>>(job, static_cast<uint8_t*>(packed));
   NB_LAUNCH_OK("pack_chunks_kernel");
+  {
+    // rank-split copy for the CTA-pair kernel: [rank 0: every chunk's rows 0..N/2-1][rank 1: rows N/2..N-1], so that
+    // two consecutive chunk halves of one CTA are contiguous (one 16 KB TMA box)
+    uint8_t* base = static_cast<uint8_t*>(packed);
+    const size_t views_bytes = net->use_viewdirs ? (size_t)8 * (TC_STAGE_BYTES / 2) : 0;
+    const size_t reg_bytes = PL.chunk_bytes - views_bytes;
+    for (int r = 0; r < 2; ++r) {
+      uint8_t* dst = base + PL.off_pair + (size_t)r * (PL.chunk_bytes / 2);
+      NB_CUDA(cudaMemcpy2DAsync(dst, 8192, base + PL.off_chunks + (size_t)r * 8192, 16384, 8192, reg_bytes / 16384, cudaMemcpyDeviceToDevice, st));
+      if (views_bytes)
+        NB_CUDA(cudaMemcpy2DAsync(dst + reg_bytes / 2, 4096, base + PL.off_chunks + reg_bytes + (size_t)r * 4096, 8192, 4096, 8, cudaMemcpyDeviceToDevice, st));
+    }
+  }
   PackTables t;
   t.net = *net; t.off_bias = PL.off_bias; t.off_heads = PL.off_heads; t.off_vdir = PL.off_vdir;
   pack_tables_kernel<<<8, 256, 0, st>>>(t, static_cast<uint8_t*>(packed));
@@ -538,6 +554,14 @@ int nerf_b200_debug_issue_probe(int reps, int nmma, int flags, void* out_2_i64, 
   if (int rc = smem_optin((const void*)issue_probe_kernel, sm)) return rc;
   issue_probe_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(reps, nmma, flags, static_cast<long long*>(out_2_i64));
   NB_LAUNCH_OK("issue_probe_kernel");
+  return 0;
+}
+
+int nerf_b200_debug_l2_stream(const void* buf, int buf_bytes, int chunk, int stages, int passes, int nblocks, void* out_i64, void* stream) {
+  const size_t sm = (size_t)stages * chunk + 512 + 1024;
+  if (int rc = smem_optin((const void*)l2_stream_probe_kernel, sm)) return rc;
+  l2_stream_probe_kernel<<<nblocks, 64, sm, (cudaStream_t)stream>>>(static_cast<const uint8_t*>(buf), buf_bytes, chunk, stages, passes, static_cast<long long*>(out_i64));
+  NB_LAUNCH_OK("l2_stream_probe_kernel");
   return 0;
 }
 

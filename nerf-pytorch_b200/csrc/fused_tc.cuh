@@ -44,7 +44,7 @@ constexpr uint32_t SM_BIASB = SM_ONES + 512;                    // 213504: 8 KB 
                                                                 //        (one 256-byte selector atom per tile slot before it)
 constexpr uint32_t SM_HEADS = SM_BIASB + 8192;                  // 221440: head weights, 4128 B
 constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 225568: 2 x 128 x float4 partials
-constexpr uint32_t SM_BARS = SM_PART + 4096;                    // 229664: mbarriers
+constexpr uint32_t SM_BARS = SM_PART + 6144;                    // (the pair kernel exchanges 3 x 128 float4 partials)                    // 229664: mbarriers
 constexpr uint32_t SM_MISC = SM_BARS + 256;                     // 229920: tmem ptr, compositing carry
 constexpr uint32_t SM_TOTAL = SM_MISC + 128;                    // 230048
 constexpr uint32_t SM_ALLOC = SM_TOTAL;                         // dynamic smem base is 1024-aligned (checked at run time)
@@ -68,7 +68,7 @@ constexpr int HEADS_FLOATS = 1032;
 struct PackLayout {
   int D, skip, use_viewdirs, IC, ICV, NL;
   int n_chunks;
-  size_t off_chunks, chunk_bytes, off_bias, off_heads, off_vdir, off_biasb, total;
+  size_t off_chunks, chunk_bytes, off_bias, off_heads, off_vdir, off_biasb, off_pair, total;
 };
 
 __host__ __device__ inline int tc_layer_chunks(int l, int D, int skip) {
@@ -97,7 +97,8 @@ static inline PackLayout make_pack_layout(const NerfNetParams& n) {
   L.off_vdir = L.off_heads + HEADS_FLOATS * 4;
   L.off_biasb = L.off_vdir + (size_t)(128 * (n.input_ch_views > 0 ? n.input_ch_views : 1) + 128) * 4;
   L.off_biasb = (L.off_biasb + 255) & ~(size_t)255;
-  L.total = L.off_biasb + TC_BIAS_CHUNK_BYTES;
+  L.off_pair = L.off_biasb + TC_BIAS_CHUNK_BYTES;          // rank-split copy of the chunk stream for the CTA-pair kernel
+  L.total = L.off_pair + L.chunk_bytes;
   return L;
 }
 
@@ -225,6 +226,7 @@ struct MarchParams {
   int D, skip, use_viewdirs, L, IC;
   int white_bkgd, do_composite;
   NerfPassOut out;
+  unsigned long long pair_half_bytes;     // pair kernel: bytes of one rank's half of the chunk stream
   long long* trace;                       // debug: clock64 timestamps of CTA 0, super-tile 1 (or NULL)
 };
 
@@ -328,6 +330,118 @@ __device__ __forceinline__ void write_bias_selector(uint32_t slab, int r, int li
   ptx::st_shared_v4(a + ((1 ^ sw) << 4), w[4], w[5], w[6], w[7]);
 }
 
+// Positional encoding of one point into its 128-byte K-block row of the A operand (64 fp16 channels:
+// x y z, then per frequency sin(2^f xyz), cos(2^f xyz); channel 63 is zero padding), written as eight
+// 16-byte swizzled chunks.  run_nerf_helpers.py:36-45 evaluates sin/cos of 2^f x for every f; here only
+// f = 0 and f = 5 are evaluated with sincosf, the other octaves come from the double-angle identities
+// sin 2a = 2 sin a cos a, cos 2a = (cos a - sin a)(cos a + sin a).  Four doublings amplify the fp32
+// rounding of the anchor to <= 1.6e-6 absolute (numpy model over [-6, 6]: 0.07 % of the fp16 operand
+// values move by one fp16 ulp), far below the fp16 quantisation of the operand itself, and cut the
+// sampler warp's work ~4x: with 30 sincosf per row it took longer than the MMAs of half a super-tile and
+// the issuers idled on enc_full (profiles/r01_summary.md, "sampler").
+__device__ __forceinline__ void encode_row_store(uint32_t row, int tr_, float px, float py, float pz, int L) {
+  uint32_t h[32];
+  float s[3], c[3];
+  const float q[3] = {px, py, pz};
+  float carry = 0.f;                                   // pending even-indexed channel of the current pair
+  int n = 0;                                           // channels emitted so far (compile-time after unrolling)
+  auto emit = [&](float v) {
+    if (n & 1) { __half2 hh = __floats2half2_rn(carry, v); h[n >> 1] = *reinterpret_cast<uint32_t*>(&hh); }
+    else carry = v;
+    ++n;
+  };
+  emit(px); emit(py); emit(pz);
+#pragma unroll
+  for (int f = 0; f < 10; ++f) {
+    if (f == 0 || f == 5) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) sincosf(q[j] * (float)(1 << f), &s[j], &c[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float s2 = (s[j] + s[j]) * c[j], c2 = (c[j] - s[j]) * (c[j] + s[j]);
+        s[j] = s2; c[j] = c2;
+      }
+    }
+    const bool on = f < L;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) emit(on ? s[j] : 0.f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) emit(on ? c[j] : 0.f);
+  }
+  emit(0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t a = row + (uint32_t)((k ^ (tr_ & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[4 * k]), "r"(h[4 * k + 1]), "r"(h[4 * k + 2]), "r"(h[4 * k + 3]) : "memory");
+  }
+}
+
+// raw (rgb, sigma) of one row per lane -> alpha compositing of whole rays (run_nerf.py:275-303) with the carry of the
+// ray that is open at the warp boundary threaded warp -> warp through shared memory (ticket order: st, slot, q).
+__device__ __forceinline__ void composite_rows(const MarchParams& p, const float4 raw4, const bool valid, const int lr, const int rl,
+                                               const long long n_ray, const long long row_begin, const int st, const int X,
+                                               const int q, const int lane, const uint32_t a_carry) {
+  const long long m = row_begin + lr;
+  if (valid && p.out.raw) reinterpret_cast<float4*>(p.out.raw)[m] = raw4;
+  if (!p.do_composite) return;
+  const int k = lr - rl * p.S;
+  float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, z = 0.f;
+  if (valid) {
+    const float* rd = p.rays + n_ray * p.ray_stride + 3;
+    const float norm = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);         // run_nerf.py:280
+    z = p.z_vals[m];
+    float dist = (k == p.S - 1) ? 1e10f : __fsub_rn(p.z_vals[m + 1], z);             // :277-278
+    dist = __fmul_rn(dist, norm);
+    const float sg = raw4.w + (p.noise ? p.noise[m] : 0.0f);
+    alpha = __fsub_rn(1.0f, expf(-fmaxf(sg, 0.0f) * dist));                           // :275
+    cr = sigmoidf_acc(raw4.x); cg = sigmoidf_acc(raw4.y); cb = sigmoidf_acc(raw4.z); // :282
+  }
+  const bool seg_start = valid && (k == 0), seg_end = valid && (k == p.S - 1);
+  const unsigned smask = __ballot_sync(0xffffffffu, seg_start);
+  const unsigned below = smask & ((lane == 31) ? 0xffffffffu : ((2u << lane) - 1u));
+  const int s = below ? (31 - __clz(below)) : -1;
+  const float qv = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;         // :295
+  const float pv = seg_scan_mul(qv, lane, s);
+  float ev = __shfl_up_sync(0xffffffffu, pv, 1);
+  if (lane == 0 || s == lane) ev = 1.0f;
+  const float wl = valid ? alpha * ev : 0.0f;
+  float t_r = seg_scan_add(wl * cr, lane, s), t_g = seg_scan_add(wl * cg, lane, s), t_b = seg_scan_add(wl * cb, lane, s);
+  float t_d = seg_scan_add(wl * z, lane, s), t_a = seg_scan_add(wl, lane, s);
+  const uint32_t ticket = (uint32_t)((st * 2 + X) * 4 + q);
+  if (lane == 0) { while (ld_acquire_shared(a_carry + CARRY_TURN) != ticket) { } }
+  __syncwarp();
+  const float Tin = lds32(a_carry + CARRY_T);
+  const float c_r = lds32(a_carry + CARRY_R), c_g = lds32(a_carry + CARRY_G), c_b = lds32(a_carry + CARRY_B);
+  const float c_d = lds32(a_carry + CARRY_D), c_a = lds32(a_carry + CARRY_A);
+  __syncwarp();
+  if (s < 0) { t_r = fmaf(Tin, t_r, c_r); t_g = fmaf(Tin, t_g, c_g); t_b = fmaf(Tin, t_b, c_b); t_d = fmaf(Tin, t_d, c_d); t_a = fmaf(Tin, t_a, c_a); }
+  if (lane == 31) {
+    if (seg_end) {
+      sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
+      sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f);
+    } else {
+      sts32(a_carry + CARRY_T, (s >= 0) ? pv : Tin * pv);
+      sts32(a_carry + CARRY_R, t_r); sts32(a_carry + CARRY_G, t_g); sts32(a_carry + CARRY_B, t_b);
+      sts32(a_carry + CARRY_D, t_d); sts32(a_carry + CARRY_A, t_a);
+    }
+    st_release_shared(a_carry + CARRY_TURN, ticket + 1u);
+  }
+  if (valid && p.out.weights) p.out.weights[m] = (s < 0) ? Tin * wl : wl;
+  if (seg_end) {
+    float rr = t_r, gg = t_g, bb = t_b;
+    if (p.white_bkgd) { const float bg = 1.0f - t_a; rr += bg; gg += bg; bb += bg; }  // :302-303
+    if (p.out.rgb_map) { p.out.rgb_map[n_ray * 3] = rr; p.out.rgb_map[n_ray * 3 + 1] = gg; p.out.rgb_map[n_ray * 3 + 2] = bb; }
+    if (p.out.disp_map) {
+      const float ratio = t_d / t_a;
+      const float mm = (ratio != ratio) ? ratio : fmaxf(1e-10f, ratio);              // :299
+      p.out.disp_map[n_ray] = 1.0f / mm;
+    }
+    if (p.out.acc_map) p.out.acc_map[n_ray] = t_a;
+    if (p.out.depth_map) p.out.depth_map[n_ray] = t_d;
+  }
+}
+
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
 __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchParams p) {
@@ -425,7 +539,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
       const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem, 0) + X * 256;
       for (int st = 0; st < nst; ++st) {
         const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0 && lane == 0;
+        const bool trs = p.trace && blockIdx.x == 0 && X == 0 && lane == 0 && st < 48;
+        if (trs) p.trace[2200 + 2 * st] = clock64();
         ptx::mbar_wait(bar_encfull, st & 1);
+        if (trs) p.trace[2201 + 2 * st] = clock64();
         for (int l = 0; l < NL; ++l) {
           const int nch = tc_layer_chunks(l, D, p.skip);
           const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
@@ -663,7 +780,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
     // =========================== sampler (warp 3) ===========================
     const int t = threadIdx.x - 96;                               // 0..31
     for (int st = 0; st < nst; ++st) {
+      const bool trs = p.trace && blockIdx.x == 0 && t == 0 && st < 48;
+      if (trs) p.trace[2300 + 2 * st] = clock64();
       ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
+      if (trs) p.trace[2301 + 2 * st] = clock64();
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
         const int X = i >> 2, tr_ = t + 32 * (i & 3);             // tile slot, tile row
@@ -680,27 +800,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) march_tc_kernel(const MarchPara
             pz = __fadd_rn(ry[2], __fmul_rn(ry[5], z));
           }
         }
-        // 64 encoded channels (63 + zero pad), one fp16 store each into the 128B-swizzled K-block
-        const uint32_t row = sb + SM_ENC + X * 16384 + act_row_off(tr_);
-        auto put = [&](int c, float v) {
-          const uint32_t a = row + (uint32_t)((((c >> 3) ^ (tr_ & 7)) << 4) + ((c & 7) << 1));
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
-        };
-        put(0, px); put(1, py); put(2, pz);
-#pragma unroll 1
-        for (int f = 0; f < 10; ++f) {
-          float s0 = 0.f, c0 = 0.f, s1 = 0.f, c1 = 0.f, s2 = 0.f, c2 = 0.f;
-          if (f < p.L) {
-            const float sc = (float)(1 << f);
-            sincosf(px * sc, &s0, &c0); sincosf(py * sc, &s1, &c1); sincosf(pz * sc, &s2, &c2);
-          }
-          const int c = 3 + 6 * f;
-          put(c + 0, s0); put(c + 1, s1); put(c + 2, s2); put(c + 3, c0); put(c + 4, c1); put(c + 5, c2);
-        }
-        put(63, 0.f);
+        encode_row_store(sb + SM_ENC + X * 16384 + act_row_off(tr_), tr_, px, py, pz, p.L);
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bar_encfull);
+      if (trs) p.trace[2400 + st] = clock64();
     }
   }
 
@@ -892,6 +996,45 @@ __global__ void __launch_bounds__(384, 1) epi_rate_kernel(int reps, int mode, in
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+// L2 -> shared-memory streaming probe: every CTA streams the same `buf_bytes` buffer `passes` times through a ring of
+// `stages` x `chunk` bytes with cp.async.bulk (a consumer warp frees a stage as soon as it lands).
+// out[blockIdx.x*2] = cycles, out[blockIdx.x*2+1] = summed issue->landed latency of warp 0's copies.
+__global__ void __launch_bounds__(64, 1) l2_stream_probe_kernel(const uint8_t* __restrict__ buf, int buf_bytes, int chunk, int stages,
+                                                              int passes, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const uint32_t BAR = (uint32_t)stages * (uint32_t)chunk;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { for (int i = 0; i < stages; ++i) { ptx::mbar_init(sb + BAR + 8 * i, 1); ptx::mbar_init(sb + BAR + 128 + 8 * i, 1); } ptx::fence_mbar_init(); }
+  __syncthreads();
+  const int n = (buf_bytes / chunk) * passes;
+  const long long t0 = clock64();
+  if (warp == 0) {
+    uint32_t stage = 0, ph = 0;
+    int off = 0;
+    for (int i = 0; i < n; ++i) {
+      ptx::mbar_wait(sb + BAR + 128 + 8 * stage, ph ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(sb + BAR + 8 * stage, chunk);
+        ptx::bulk_g2s(sb + stage * chunk, buf + off, chunk, sb + BAR + 8 * stage);
+      }
+      __syncwarp();
+      off += chunk; if (off + chunk > buf_bytes) off = 0;
+      if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+    }
+  } else {
+    uint32_t stage = 0, ph = 0;
+    for (int i = 0; i < n; ++i) {
+      ptx::mbar_wait(sb + BAR + 8 * stage, ph);
+      if (ptx::elect_one()) ptx::mbar_arrive(sb + BAR + 128 + 8 * stage);
+      __syncwarp();
+      if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+    }
+    if (threadIdx.x == 32) out[blockIdx.x] = clock64() - t0;
+  }
 }
 
 // Issue-overhead probe: one thread runs `reps` iterations of {optional mbarrier try_wait on a completed

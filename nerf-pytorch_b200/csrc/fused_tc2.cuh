@@ -22,8 +22,8 @@
 
 namespace nb {
 
-constexpr int TC2_NST = 6;                       // ring stages
-constexpr uint32_t TC2_STAGE_BYTES = 8192;       // half of a [256 x 32] fp16 chunk
+constexpr int TC2_NST = 3;                       // ring stages; one stage = TWO consecutive chunk halves (one TMA, one barrier)
+constexpr uint32_t TC2_STAGE_BYTES = 16384;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p, const __grid_constant__ CUtensorMap wmap8k, const __grid_constant__ CUtensorMap wmap4k) {
   uint8_t* smem = tc_smem;
@@ -93,35 +93,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   if (warp == 0) {
     // =========================== weight producer (both CTAs): this CTA's half of every chunk ===========
     uint32_t stage = 0, ph = 0;
+    const int half_rows = (int)(p.pair_half_bytes >> 9);     // rows (512 B) of one rank's stream
     for (int st = 0; st < nst; ++st) {
-      const uint8_t* lsrc = p.chunks;
+      int row = (int)rank * half_rows;
       for (int l = 0; l < NL; ++l) {
         const int nch = tc_layer_chunks(l, D, p.skip);
-        const uint32_t cb = tc_layer_chunk_bytes(l, D), hb = cb / 2;
-        for (int X = 0; X < 2; ++X) {                     // pass of slot A, then the same chunks again for slot B
-          const uint8_t* src = lsrc + rank * hb;
-          for (int c = 0; c < nch; ++c) {
+        const uint32_t hb = tc_layer_chunk_bytes(l, D) / 2;          // this CTA's bytes of one chunk
+        for (int X = 0; X < 2; ++X) {                               // pass of slot A, then the same chunks again for slot B
+          int prow = row;
+          for (int c = 0; c < nch; c += 2) {
             hb_(0, 1000000 + st * 10000 + l * 100 + X * 50 + c);
-            const bool ptr_ = p.trace && blockIdx.x == 0 && st == 1 && l == 2 && lane == 0;
-            if (ptr_) p.trace[1024 + 4 * (X * 8 + c)] = clock64();
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
-            if (ptr_) p.trace[1024 + 4 * (X * 8 + c) + 1] = clock64();
             if (ptx::elect_one()) {
-              // both halves complete on the LEADER's w_full: the leader expects the bytes of both CTAs' copies and
-              // every TMA load (cta_group::2) counts its bytes on the leader's mbarrier.  The stream is viewed as
-              // a [rows][256] uint16 tensor; box = 16 rows (8 KB half chunk) or 8 rows (4 KB, view layer).
-              if (leader) ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, 2 * hb);
-              const int row = (int)((src - p.chunks) >> 9);
-              ptx::tma2_load_2d(sb + SM_WRING + stage * TC2_STAGE_BYTES, (hb > 4096) ? (const void*)&wmap8k : (const void*)&wmap4k, 0, row,
+              // two chunk halves per TMA box; every load (cta_group::2) counts its bytes on the LEADER's w_full, which
+              // expects both CTAs' boxes
+              if (leader) ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, 4 * hb);
+              ptx::tma2_load_2d(sb + SM_WRING + stage * TC2_STAGE_BYTES, (hb > 4096) ? (const void*)&wmap8k : (const void*)&wmap4k, 0, prow,
                                 bar_wfull + 8 * stage);
             }
             __syncwarp();
-            if (ptr_) p.trace[1024 + 4 * (X * 8 + c) + 2] = clock64();
-            src += cb;
+            prow += (int)(2 * hb >> 9);
             if (++stage == TC2_NST) { stage = 0; ph ^= 1; }
           }
         }
-        lsrc += (size_t)nch * cb;
+        row += (int)((size_t)nch * hb >> 9);
       }
     }
   } else if ((warp == 1 || warp == 2) && leader) {
@@ -136,53 +131,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem, 0) + X * 256;
     for (int st = 0; st < nst; ++st) {
       const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0 && lane == 0;
-      hb_(1 + X, 9000000 + st * 10000);
+      const bool trs = p.trace && blockIdx.x == 0 && X == 0 && lane == 0 && st < 48;
+      if (trs) p.trace[2200 + 2 * st] = clock64();
       ptx::mbar_wait_cluster(bar_encfull, st & 1);
+      if (trs) p.trace[2201 + 2 * st] = clock64();
       for (int l = 0; l < NL; ++l) {
         const int nch = tc_layer_chunks(l, D, p.skip);
         const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
         const bool has_bias = tc_layer_has_bias(l, D);
         const uint32_t idesc = ptx::umma_idesc_f16(256, (l == D + 1) ? 128 : 256);
-        if (X == 1) gi += nch;                            // skip slot A's pass of this layer
+        const uint32_t hbytes = tc_layer_chunk_bytes(l, D) / 2;
+        const uint32_t nds = (uint32_t)nch >> 1;            // ring stages per pass
+        if (X == 1) gi += nds;                            // skip slot A's pass of this layer
         // passes are consumed strictly in stream order (A(l), B(l), A(l+1), ...): a parity wait on a ring stage
         // is only meaningful once every earlier chunk of the stream has been consumed
         if (!first_pass) { ptx::mbar_wait(bar_turn + 8 * X, turnph); turnph ^= 1; }
         first_pass = false;
-        for (int c0 = 0; c0 < nch; c0 += 3) {
-          // up to three stream chunks per hand-off (6-7 MMAs back to back); the ring keeps three more in flight
+        for (int c0 = 0; c0 < nch; c0 += 2) {
+          // one ring stage = two chunks = four MMAs back to back (+ the bias MMA at the start of a pass)
           long long* trp = p.trace + 4 * (l * 10 + c0);
           if (tr) trp[0] = clock64();
-          const int ng = (nch - c0 < 3) ? nch - c0 : 3;
+          const uint32_t g = gi + (uint32_t)(c0 >> 1), sg = g % TC2_NST;
           hb_(1 + X, 1000000 + st * 10000 + l * 100 + c0);
-          for (int h = 0; h < ng; ++h) { const uint32_t g = gi + c0 + h; ptx::mbar_wait(bar_wfull + 8 * (g % TC2_NST), (g / TC2_NST) & 1); }
+          ptx::mbar_wait(bar_wfull + 8 * sg, (g / TC2_NST) & 1);
           if (tr) trp[1] = clock64();
           if (c0 == 0) { hb_(1 + X, 4000000 + st * 10000 + l * 100 + c0); ptx::mbar_wait_cluster(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
           hb_(1 + X, 5000000 + st * 10000 + l * 100 + c0);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (c0 == 0 && has_bias) ptx::mma2_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
-            for (int h = 0; h < ng; ++h) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
               const int c = c0 + h;
-              const uint32_t sg = (gi + c) % TC2_NST;
               const bool is_enc = (l == 0) || (skip_layer && c < 2);
               const int kc = skip_layer ? c - 2 : c;
-              const uint64_t bd = bdesc0 + ((SM_WRING + sg * TC2_STAGE_BYTES) >> 4);
+              const uint64_t bd = bdesc0 + ((SM_WRING + sg * TC2_STAGE_BYTES + h * hbytes) >> 4);
               const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
               const uint64_t ad = adesc0 + (a_off >> 4);
               ptx::mma2_f16_ss(d_tmem, ad, bd, idesc, (c > 0 || has_bias) ? 1u : 0u);
               ptx::mma2_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
-              ptx::mma2_commit_mc(bar_wempty + 8 * sg, 3);
               if (is_enc && c == 1 && l == last_enc_layer) ptx::mma2_commit_mc(bar_encfree, 3);
             }
-            if (c0 + 3 >= nch) ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
+            ptx::mma2_commit_mc(bar_wempty + 8 * sg, 3);
+            if (c0 + 2 >= nch) ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
           }
           __syncwarp();
           if (tr) trp[3] = clock64();
         }
         if (ptx::elect_one()) ptx::mbar_arrive(bar_turn + 8 * (X ^ 1));   // hand the stream over to the other slot's issuer
         __syncwarp();
-        gi += nch;                                        // own pass consumed
-        if (X == 0) gi += nch;                            // skip slot B's pass of this layer
+        gi += nds;                                        // own pass consumed
+        if (X == 0) gi += nds;                            // skip slot B's pass of this layer
       }
     }
   } else if ((warp == 1 || warp == 2) && !leader) {
@@ -212,9 +211,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         const bool tr = p.trace && blockIdx.x == 0 && st == 1 && e == 0 && lane == 0;
         long long* trp = p.trace + 2048 + 4 * (X * 16 + l);
         if (tr) trp[0] = clock64();
-        hb_(warp, 1000000 + st * 10000 + l * 100);
         ptx::mbar_wait(bar_dfull + 8 * X, dph);
-        hb_(warp, 2000000 + st * 10000 + l * 100);
         dph ^= 1;
         ptx::tc_fence_after();
         if (tr) trp[1] = clock64();
@@ -388,9 +385,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     // =========================== sampler (warp 3) ===========================
     const int t = threadIdx.x - 96;                               // 0..31
     for (int st = 0; st < nst; ++st) {
-      hb_(3, 1000000 + st * 10000);
+      const bool trs = p.trace && blockIdx.x == 0 && t == 0 && st < 48;
+      if (trs) p.trace[2300 + 2 * st] = clock64();
       ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
-      hb_(3, 2000000 + st * 10000);
+      if (trs) p.trace[2301 + 2 * st] = clock64();
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
         const int X = i >> 2, tr_ = t + 32 * (i & 3);             // tile slot, tile row
@@ -407,27 +405,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
             pz = __fadd_rn(ry[2], __fmul_rn(ry[5], z));
           }
         }
-        // 64 encoded channels (63 + zero pad), one fp16 store each into the 128B-swizzled K-block
-        const uint32_t row = sb + SM_ENC + X * 16384 + act_row_off(tr_);
-        auto put = [&](int c, float v) {
-          const uint32_t a = row + (uint32_t)((((c >> 3) ^ (tr_ & 7)) << 4) + ((c & 7) << 1));
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
-        };
-        put(0, px); put(1, py); put(2, pz);
-#pragma unroll 1
-        for (int f = 0; f < 10; ++f) {
-          float s0 = 0.f, c0 = 0.f, s1 = 0.f, c1 = 0.f, s2 = 0.f, c2 = 0.f;
-          if (f < p.L) {
-            const float sc = (float)(1 << f);
-            sincosf(px * sc, &s0, &c0); sincosf(py * sc, &s1, &c1); sincosf(pz * sc, &s2, &c2);
-          }
-          const int c = 3 + 6 * f;
-          put(c + 0, s0); put(c + 1, s1); put(c + 2, s2); put(c + 3, c0); put(c + 4, c1); put(c + 5, c2);
-        }
-        put(63, 0.f);
+        encode_row_store(sb + SM_ENC + X * 16384 + act_row_off(tr_), tr_, px, py, pz, p.L);
       }
       ptx::fence_proxy_async_smem();
       arrive_leader(bar_encfull);
+      if (trs) p.trace[2400 + st] = clock64();
     }
   }
 

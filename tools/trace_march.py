@@ -50,3 +50,11 @@ for X in range(2):
     for l in range(10):
         a = epi[X, l]
         if a[0]: print(f"epi X{X} L{l}: wait_start {a[0]-t00:7d} dfull_wait {a[1]-a[0]:6d} epilogue {a[2]-a[1] if a[2] else -1:6d}")
+
+# per-super-tile timeline of CTA 0 (fine launch): issuer enc_full wait, sampler enc_free wait + encode time
+ist = t[2200:2296].reshape(48, 2); smp = t[2300:2396].reshape(48, 2); send = t[2400:2448]
+n = int((ist[:, 0] > 0).sum())
+print("super-tile | issuer start (rel), encfull_wait | period | sampler encfree_wait, encode")
+for s in range(n):
+    print(f"  st{s:2d}: start {ist[s,0]-ist[0,0]:8d} encfull_wait {ist[s,1]-ist[s,0]:6d} period {(ist[s,0]-ist[s-1,0]) if s else 0:6d} | "
+          f"encfree_wait {smp[s,1]-smp[s,0]:6d} encode {send[s]-smp[s,1]:6d}")
