@@ -253,7 +253,7 @@ def main():
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e,
                 "api": "nerf_pytorch_b200.render(rays=<pinned host tensor copied in>) -> rgb/disp/acc copied out"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "march_tc_kernel (coarse + fine launches)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "tensor", "kernel": ("march_tc_kernel" if os.environ.get("NERF_B200_PAIR", "1")[:1] == "0" else "march_tc2_kernel (cta_group::2 pair)") + " (coarse + fine launches)", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_src, "kernel_ms_per_step": kms.value / max(1, kn.value) * 2,
                      "launches_timed": int(kn.value)},

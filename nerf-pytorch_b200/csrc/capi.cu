@@ -99,8 +99,10 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   p.rays_per_cta = (int)((N + grid - 1) / grid);
   grid = (int)((N + p.rays_per_cta - 1) / p.rays_per_cta);
   NB_CHECK_ARG((long long)p.rays_per_cta * S < (1ll << 30), "rays_per_cta * S overflows");
-  static int pair_mode = -1;                 // NERF_B200_PAIR=1 -> CTA-pair kernel (fused_tc2.cuh)
-  if (pair_mode < 0) { const char* e = getenv("NERF_B200_PAIR"); pair_mode = (e && e[0] == '1') ? 1 : 0; }
+  // default: the CTA-pair kernel (fused_tc2.cuh, cta_group::2); NERF_B200_PAIR=0 selects the single-CTA kernel
+  // (fused_tc.cuh) that it superseded -- kept for A/B measurements, latched at the first launch.
+  static int pair_mode = -1;
+  if (pair_mode < 0) { const char* e = getenv("NERF_B200_PAIR"); pair_mode = (e && e[0] == '0') ? 0 : 1; }
   static bool optin = false;
   if (!optin) {
     if (int rc = smem_optin((const void*)march_tc_kernel, SM_ALLOC)) return rc;
@@ -109,6 +111,7 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   }
   if (pair_mode) grid = (grid + 1) & ~1;                 // whole pairs; a padding CTA owns no rays
   p.trace = g_trace;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("NERF_B200_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   TimedLaunch* tl = nullptr;
   if (g_timing && g_ntimed < 4096) {
     tl = &g_timed[g_ntimed++];
@@ -117,7 +120,7 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
     cudaEventRecord(tl->a, st);
   }
   if (pair_mode) {
-    // tensor map over the packed chunk stream, viewed as [rows][256] uint16 (512-byte rows), box = 8 rows (4 KB)
+    // tensor map over the rank-split chunk stream, viewed as [rows][256] uint16 (512-byte rows)
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -129,22 +132,18 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
       NB_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
       encode = reinterpret_cast<EncodeFn>(fn);
     }
-    CUtensorMap wmap8k, wmap4k;                 // boxes of two chunk halves: 2 x 8 KB (32 rows) and 2 x 4 KB (16 rows, view layer)
+    CUtensorMap wmap;                           // box = 16 stream rows = 8 KB = one ring stage
     const cuuint64_t gdim[2] = {256, (cuuint64_t)(PL.chunk_bytes / 512)};
     const cuuint64_t gstr[1] = {512};
-    const cuuint32_t box16[2] = {256, 32}, box8[2] = {256, 16}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {256, 16}, estr[2] = {1, 1};
     uint8_t* pair_stream = const_cast<uint8_t*>(pk + PL.off_pair);
     p.chunks = pair_stream;                     // the pair kernel walks the rank-split stream
     p.pair_half_bytes = PL.chunk_bytes / 2;
-    CUresult cr = encode(&wmap8k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pair_stream, gdim, gstr, box16, estr,
+    CUresult cr = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pair_stream, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    cr = encode(&wmap4k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pair_stream, gdim, gstr, box8, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    march_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p, wmap8k, wmap4k);
+    march_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p, wmap);
   }
   else march_tc_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
   if (tl) cudaEventRecord(tl->b, st);

@@ -44,10 +44,11 @@ constexpr uint32_t SM_BIASB = SM_ONES + 512;                    // 213504: 8 KB 
                                                                 //        (one 256-byte selector atom per tile slot before it)
 constexpr uint32_t SM_HEADS = SM_BIASB + 8192;                  // 221440: head weights, 4128 B
 constexpr uint32_t SM_PART = SM_HEADS + 4128;                   // 225568: 2 x 128 x float4 partials
-constexpr uint32_t SM_BARS = SM_PART + 6144;                    // (the pair kernel exchanges 3 x 128 float4 partials)                    // 229664: mbarriers
+constexpr uint32_t SM_BARS = SM_PART + 4096;                    // mbarriers
 constexpr uint32_t SM_MISC = SM_BARS + 256;                     // 229920: tmem ptr, compositing carry
 constexpr uint32_t SM_TOTAL = SM_MISC + 128;                    // 230048
-constexpr uint32_t SM_ALLOC = SM_TOTAL;                         // dynamic smem base is 1024-aligned (checked at run time)
+constexpr uint32_t SM_ALLOC = 230400 > SM_TOTAL ? 230400 : SM_TOTAL;                           // >= SM_TOTAL and the pair kernel's P2_TOTAL; dynamic smem base is 1024-aligned (checked at run time)
+static_assert(SM_TOTAL <= SM_ALLOC, "shared-memory map exceeds the allocation");
 constexpr uint32_t TC_BIAS_CHUNK_BYTES = 256 * 32;              // [256 rows x K=16] fp16: column pair (2l, 2l+1) = (hi, lo) of layer l's bias
 
 // K columns of the resident bias operand used by bias layer `li` of `nb`: (hi, lo) pairs while 16 columns
@@ -228,6 +229,7 @@ struct MarchParams {
   NerfPassOut out;
   unsigned long long pair_half_bytes;     // pair kernel: bytes of one rank's half of the chunk stream
   long long* trace;                       // debug: clock64 timestamps of CTA 0, super-tile 1 (or NULL)
+  int dbg;                                // debug: NERF_B200_DBG bit flags for A/B experiments (0 in production)
 };
 
 // compositing carry of the ray that is still open at a warp boundary (shared memory, 32 B)

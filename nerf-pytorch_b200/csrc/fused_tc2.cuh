@@ -14,18 +14,35 @@
 //   p_full[6]  leader  : the peer's relay warp forwards its w_full phase (remote mbarrier arrive)
 //   w_empty[6] both    : tcgen05.commit.cta_group::2 multicast -> both producers may refill the stage
 //   d_full[2]  both    : multicast commit -> both CTAs' epilogue warps of that slot
-//   act[2]     leader  : 512 arrivals = 256 local epilogue threads + 256 remote (accumulator drained, A tile written)
-//   enc_full   leader  : 64 arrivals (both samplers);  enc_free both: multicast commit after the last encoding chunk
+//   act[2]     leader  : 16 arrivals = one per epilogue warp of the slot, 8 local + 8 remote (accumulator drained, A tile written)
+//   enc_full   leader  : 2 arrivals (both sampler warps);  enc_free both: multicast commit after the last encoding chunk
 #pragma once
 #include <cuda.h>
 #include "fused_tc.cuh"
 
 namespace nb {
 
-constexpr int TC2_NST = 3;                       // ring stages; one stage = TWO consecutive chunk halves (one TMA, one barrier)
-constexpr uint32_t TC2_STAGE_BYTES = 16384;
+constexpr int TC2_NST = 7;                       // ring stages; one stage (unit) = 8 KB = one TMA box, one barrier pair
+constexpr uint32_t TC2_STAGE_BYTES = 8192;
+// shared-memory map behind the ring (ACT / ENC / WRING start as in fused_tc.cuh): the pair kernel needs only its
+// N-half of the resident bias operand and parks the head partials in the (dead) A tile, which pays for the
+// 7th stage.  With 7 x 8 KB in flight and a release -> refill -> ready round trip of ~1.4 k cycles the stream
+// sustains one unit per ~240 cycles (consumption: 257); 3 x 16 KB sustained one per ~325.
+constexpr uint32_t P2_ONES = SM_WRING + TC2_NST * TC2_STAGE_BYTES;   // 221184: 2 x 256 B bias-selector atoms
+constexpr uint32_t P2_BIASB = P2_ONES + 512;                          // 221696: 4 KB, this CTA's rows of the bias operand
+constexpr uint32_t P2_HEADS = P2_BIASB + TC_BIAS_CHUNK_BYTES / 2;     // 225792: head weights
+constexpr uint32_t P2_BARS = P2_HEADS + 4128;                         // 229920: mbarriers
+constexpr uint32_t P2_MISC = P2_BARS + 256;                           // 230176: tmem ptr, compositing carry, pass counter
+constexpr uint32_t P2_TOTAL = P2_MISC + 128;                          // 230304
+static_assert(P2_TOTAL <= SM_ALLOC, "pair kernel shared-memory map exceeds the allocation");
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p, const __grid_constant__ CUtensorMap wmap8k, const __grid_constant__ CUtensorMap wmap4k) {
+// ring units per pass of layer l (all even)
+__host__ __device__ __forceinline__ int tc2_layer_units(int l, int D, int skip) {
+  const int nch = tc_layer_chunks(l, D, skip);
+  return (l == D + 1) ? nch / 2 : nch;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p, const __grid_constant__ CUtensorMap wmap) {
   uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,23 +50,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = (rank == 0);
 
-  float* s_heads = reinterpret_cast<float*>(smem + SM_HEADS);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SM_MISC);
-  const uint32_t a_heads = sb + SM_HEADS, a_part = sb + SM_PART, a_carry = sb + SM_MISC + 16;
+  float* s_heads = reinterpret_cast<float*>(smem + P2_HEADS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + P2_MISC);
+  const uint32_t a_heads = sb + P2_HEADS, a_carry = sb + P2_MISC + 16, a_pass = sb + P2_MISC + 64;
 
   // mbarriers (same offsets in both CTAs)
-  const uint32_t bar_wfull = sb + SM_BARS;            // [6]
-  const uint32_t bar_wempty = sb + SM_BARS + 48;      // [6]
-  const uint32_t bar_pfull = sb + SM_BARS + 96;       // [6] (leader)
-  const uint32_t bar_dfull = sb + SM_BARS + 144;      // [2]
-  const uint32_t bar_act = sb + SM_BARS + 160;        // [2] (leader)
-  const uint32_t bar_encfull = sb + SM_BARS + 176;    //     (leader)
-  const uint32_t bar_encfree = sb + SM_BARS + 184;
-  const uint32_t bar_turn = sb + SM_BARS + 192;       // [2] (leader, local): the two issuer warps take turns in stream order
+  const uint32_t bar_wfull = sb + P2_BARS;            // [7] (leader)
+  const uint32_t bar_wempty = sb + P2_BARS + 56;      // [7]
+  const uint32_t bar_dfull = sb + P2_BARS + 112;      // [2]
+  const uint32_t bar_act = sb + P2_BARS + 128;        // [2] (leader)
+  const uint32_t bar_encfull = sb + P2_BARS + 144;    //     (leader)
+  const uint32_t bar_encfree = sb + P2_BARS + 152;
   // arrive on a barrier that lives in the leader CTA
   // debug heartbeat: trace[blockIdx.x * 32 + role] = last wait this role entered (trace may be mapped host memory)
   auto hb_ = [&](int role, long long code) { if (p.trace && lane == 0 && blockIdx.x < 32) { volatile long long* t = p.trace; t[3000 + blockIdx.x * 32 + role] = code; } };
-  auto arrive_leader = [&](uint32_t bar) { if (leader) ptx::mbar_arrive(bar); else ptx::mbar_arrive_cluster(ptx::mapa(bar, 0)); };
+  // One arrival per warp; every lane has fenced its own writes (fence.proxy.async) before the __syncwarp.  The peer's
+  // data is consumed by the peer SM's own tensor core, so the remote arrive needs no cluster-scope release.
+  auto arrive_leader = [&](uint32_t bar) {
+    __syncwarp();
+    if (lane == 0) {
+      if (leader) ptx::mbar_arrive(bar);
+      else if (p.dbg & 2) ptx::mbar_arrive_cluster(ptx::mapa(bar, 0));      // A/B: .release.cluster (slow)
+      else ptx::mbar_arrive_remote(ptx::mapa(bar, 0));
+    }
+  };
 
   // this CTA's rays / rows; both CTAs of a pair run the same number of super-tiles
   const long long ray0 = (long long)blockIdx.x * p.rays_per_cta;
@@ -65,22 +89,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
 
   // ---- one-time setup ----
   const int n_bias = D + (p.use_viewdirs ? 1 : 0);
-  if (threadIdx.x < 16) write_bias_selector(sb + SM_ONES + (threadIdx.x >> 3) * 256, threadIdx.x & 7, 0, n_bias);
+  if (threadIdx.x < 16) write_bias_selector(sb + P2_ONES + (threadIdx.x >> 3) * 256, threadIdx.x & 7, 0, n_bias);
   // this CTA's half (rows 128*rank ..) of the resident bias operand
   for (int i = threadIdx.x; i < (int)(TC_BIAS_CHUNK_BYTES / 32); i += TC_THREADS)
-    reinterpret_cast<uint4*>(smem + SM_BIASB)[i] = reinterpret_cast<const uint4*>(p.biasb + rank * (TC_BIAS_CHUNK_BYTES / 2))[i];
+    reinterpret_cast<uint4*>(smem + P2_BIASB)[i] = reinterpret_cast<const uint4*>(p.biasb + rank * (TC_BIAS_CHUNK_BYTES / 2))[i];
   ptx::fence_proxy_async_smem();
   for (int i = threadIdx.x; i < HEADS_FLOATS; i += TC_THREADS) s_heads[i] = p.heads[i];
   if (threadIdx.x == 0) {
     sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
-    sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f); st_release_shared(a_carry + CARRY_TURN, 0u);
+    sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f); st_release_shared(a_carry + CARRY_TURN, 0u); st_release_shared(a_pass, 0u);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC2_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); }
-    for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 512); }
-    ptx::mbar_init(bar_encfull, 2 * TC_SAMPLER_THREADS);
+    for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 16); }
+    ptx::mbar_init(bar_encfull, 2);
     ptx::mbar_init(bar_encfree, 2);
-    ptx::mbar_init(bar_turn, 1); ptx::mbar_init(bar_turn + 8, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish2(); }
@@ -91,99 +114,142 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   const uint32_t tmem = *s_tmem;
 
   if (warp == 0) {
-    // =========================== weight producer (both CTAs): this CTA's half of every chunk ===========
+    // =========================== weight producer (both CTAs): this CTA's half of every unit ===========
+    // unit = one 8 KB ring stage = one TMA box of 16 stream rows: one chunk half of an N=256 layer, or two
+    // consecutive chunk halves (2 x 4 KB) of the N=128 view layer
     uint32_t stage = 0, ph = 0;
     const int half_rows = (int)(p.pair_half_bytes >> 9);     // rows (512 B) of one rank's stream
     for (int st = 0; st < nst; ++st) {
       int row = (int)rank * half_rows;
       for (int l = 0; l < NL; ++l) {
-        const int nch = tc_layer_chunks(l, D, p.skip);
-        const uint32_t hb = tc_layer_chunk_bytes(l, D) / 2;          // this CTA's bytes of one chunk
-        for (int X = 0; X < 2; ++X) {                               // pass of slot A, then the same chunks again for slot B
+        const int nu = tc2_layer_units(l, D, p.skip);
+        for (int X = 0; X < 2; ++X) {                               // pass of slot A, then the same units again for slot B
           int prow = row;
-          for (int c = 0; c < nch; c += 2) {
-            hb_(0, 1000000 + st * 10000 + l * 100 + X * 50 + c);
+          for (int u = 0; u < nu; ++u) {
+            hb_(0, 1000000 + st * 10000 + l * 100 + X * 50 + u);
             ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
             if (ptx::elect_one()) {
-              // two chunk halves per TMA box; every load (cta_group::2) counts its bytes on the LEADER's w_full, which
-              // expects both CTAs' boxes
-              if (leader) ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, 4 * hb);
-              ptx::tma2_load_2d(sb + SM_WRING + stage * TC2_STAGE_BYTES, (hb > 4096) ? (const void*)&wmap8k : (const void*)&wmap4k, 0, prow,
-                                bar_wfull + 8 * stage);
+              // every load (cta_group::2) counts its bytes on the LEADER's w_full, which expects both CTAs' boxes
+              if (leader) ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, 2 * TC2_STAGE_BYTES);
+              ptx::tma2_load_2d(sb + SM_WRING + stage * TC2_STAGE_BYTES, (const void*)&wmap, 0, prow, bar_wfull + 8 * stage);
             }
             __syncwarp();
-            prow += (int)(2 * hb >> 9);
+            prow += (int)(TC2_STAGE_BYTES >> 9);
             if (++stage == TC2_NST) { stage = 0; ph ^= 1; }
           }
         }
-        row += (int)((size_t)nch * hb >> 9);
+        row += nu * (int)(TC2_STAGE_BYTES >> 9);
       }
     }
-  } else if ((warp == 1 || warp == 2) && leader) {
-    // =========================== MMA issuers (leader CTA): warp 1 -> slot A passes, warp 2 -> slot B passes =====
-    const int X = warp - 1;
-    uint32_t gi = 0, actph = 0, turnph = 0;               // gi = index of the next chunk in the pair's stream
-    bool first_pass = (X == 0);                           // slot A's very first pass needs no hand-over
+  } else if (warp == 1 && leader) {
+    // =========================== MMA issuer (leader CTA, one warp) ===========================
+    // A whole pass (all units of one slot's layer: 17-21 MMAs) is issued by ONE elected lane inside ONE elected
+    // region; the w_full waits and the w_empty / d_full commits of the pass happen inside it.  Measured
+    // (tools/issue_probe2.py): every entry into an elect_one() region costs the tensor pipe ~85 idle cycles,
+    // whatever else the iteration does -- bursts of 2 / 4 / 8 MMAs per region run at 76 % / 86 % / 97 % of the
+    // back-to-back rate, commits are free and a (ready) mbarrier wait costs ~33 cycles.  Earlier versions of
+    // this kernel entered a region per ring stage (4 MMAs) and were issue-bound at ~645 cycles per 515 of MMA.
+    uint32_t stage = 0, ph = 0, actph0 = 0, actph1 = 0;
     const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
     const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
-    const uint64_t sel_desc = ptx::umma_desc(sb + SM_ONES + X * 256, 0, ptx::UMMA_SW32);
-    const uint64_t bias_desc = ptx::umma_desc(sb + SM_BIASB, 256, ptx::UMMA_SW32);
-    const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem, 0) + X * 256;
+    const uint64_t bias_desc = ptx::umma_desc(sb + P2_BIASB, 256, ptx::UMMA_SW32);
+    const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem, 0);
     for (int st = 0; st < nst; ++st) {
-      const bool tr = p.trace && blockIdx.x == 0 && st == 1 && X == 0 && lane == 0;
-      const bool trs = p.trace && blockIdx.x == 0 && X == 0 && lane == 0 && st < 48;
+      const bool tr = p.trace && blockIdx.x == 0 && st == 1;
+      const bool trs = p.trace && blockIdx.x == 0 && lane == 0 && st < 48;
       if (trs) p.trace[2200 + 2 * st] = clock64();
       ptx::mbar_wait_cluster(bar_encfull, st & 1);
       if (trs) p.trace[2201 + 2 * st] = clock64();
       for (int l = 0; l < NL; ++l) {
-        const int nch = tc_layer_chunks(l, D, p.skip);
+        const int nu = tc2_layer_units(l, D, p.skip);
+        const bool view_layer = (l == D + 1);
         const bool skip_layer = (l < D && p.skip >= 0 && l == p.skip + 1);
         const bool has_bias = tc_layer_has_bias(l, D);
-        const uint32_t idesc = ptx::umma_idesc_f16(256, (l == D + 1) ? 128 : 256);
-        const uint32_t hbytes = tc_layer_chunk_bytes(l, D) / 2;
-        const uint32_t nds = (uint32_t)nch >> 1;            // ring stages per pass
-        if (X == 1) gi += nds;                            // skip slot A's pass of this layer
-        // passes are consumed strictly in stream order (A(l), B(l), A(l+1), ...): a parity wait on a ring stage
-        // is only meaningful once every earlier chunk of the stream has been consumed
-        if (!first_pass) { ptx::mbar_wait(bar_turn + 8 * X, turnph); turnph ^= 1; }
-        first_pass = false;
-        for (int c0 = 0; c0 < nch; c0 += 2) {
-          // one ring stage = two chunks = four MMAs back to back (+ the bias MMA at the start of a pass)
-          long long* trp = p.trace + 4 * (l * 10 + c0);
-          if (tr) trp[0] = clock64();
-          const uint32_t g = gi + (uint32_t)(c0 >> 1), sg = g % TC2_NST;
-          hb_(1 + X, 1000000 + st * 10000 + l * 100 + c0);
-          ptx::mbar_wait(bar_wfull + 8 * sg, (g / TC2_NST) & 1);
-          if (tr) trp[1] = clock64();
-          if (c0 == 0) { hb_(1 + X, 4000000 + st * 10000 + l * 100 + c0); ptx::mbar_wait_cluster(bar_act + 8 * X, actph); actph ^= 1; if (tr) trp[2] = clock64(); }
-          hb_(1 + X, 5000000 + st * 10000 + l * 100 + c0);
+        const uint32_t idesc = ptx::umma_idesc_f16(256, view_layer ? 128 : 256);
+        for (int X = 0; X < 2; ++X) {
+          const uint32_t d_tmem = tmem0 + X * 256;
+          const uint64_t sel_desc = ptx::umma_desc(sb + P2_ONES + X * 256, 0, ptx::UMMA_SW32);
+          long long* trp = p.trace + 4 * (l * 2 + X);          // pass trace: start, act seen, first MMA issued, pass issued
+          long long t_a = 0, t_b = 0, t_c = 0;
+          if (tr) t_a = clock64();
+          hb_(1, 4000000 + st * 10000 + l * 100 + X * 50);
+          // slot X's accumulator drained and its A tile written by both CTAs' epilogue warps
+          if (p.dbg & 1) {
+            if (X == 0) { ptx::mbar_wait(bar_act, actph0); actph0 ^= 1; }
+            else { ptx::mbar_wait(bar_act + 8, actph1); actph1 ^= 1; }
+          } else {
+            if (X == 0) { ptx::mbar_wait_cluster(bar_act, actph0); actph0 ^= 1; }
+            else { ptx::mbar_wait_cluster(bar_act + 8, actph1); actph1 ^= 1; }
+          }
+          if (tr) t_b = clock64();
+          hb_(1, 5000000 + st * 10000 + l * 100 + X * 50);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            if (c0 == 0 && has_bias) ptx::mma2_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
+            // Everything between two MMAs of the issuing thread is exposed tensor-pipe idle time (the queue is
+            // shallow), so the per-unit work is kept to: one try_wait, one multiply-add for the stage's B
+            // descriptor, the MMAs, one commit.  A-descriptor offsets are compile-time (unrolled loops).
+            uint32_t s_ = stage, ph_ = ph;
+            const uint64_t bring = bdesc0 + (SM_WRING >> 4);
+            uint32_t acc = has_bias ? 1u : 0u;
+            if (has_bias) ptx::mma2_f16_ss(d_tmem, sel_desc, bias_desc, idesc, 0u);
+            if (l == 0 || skip_layer) {
+              const uint64_t aenc = adesc0 + ((SM_ENC + X * 16384) >> 4);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c = c0 + h;
-              const bool is_enc = (l == 0) || (skip_layer && c < 2);
-              const int kc = skip_layer ? c - 2 : c;
-              const uint64_t bd = bdesc0 + ((SM_WRING + sg * TC2_STAGE_BYTES + h * hbytes) >> 4);
-              const uint32_t a_off = is_enc ? (SM_ENC + X * 16384 + c * 64) : (SM_ACT + X * 65536 + (kc >> 1) * 16384 + (kc & 1) * 64);
-              const uint64_t ad = adesc0 + (a_off >> 4);
-              ptx::mma2_f16_ss(d_tmem, ad, bd, idesc, (c > 0 || has_bias) ? 1u : 0u);
-              ptx::mma2_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
-              if (is_enc && c == 1 && l == last_enc_layer) ptx::mma2_commit_mc(bar_encfree, 3);
+              for (int c = 0; c < 2; ++c) {
+                while (!ptx::mbar_try_wait(bar_wfull + 8 * s_, ph_)) { }
+                const uint64_t bd = bring + s_ * (TC2_STAGE_BYTES >> 4);
+                ptx::mma2_f16_ss(d_tmem, aenc + c * 4, bd, idesc, acc);
+                ptx::mma2_f16_ss(d_tmem, aenc + c * 4 + 2, bd + 2, idesc, 1u);
+                acc = 1u;
+                if (c == 1 && l == last_enc_layer) ptx::mma2_commit_mc(bar_encfree, 3);
+                ptx::mma2_commit_mc(bar_wempty + 8 * s_, 3);
+                if (c == 0 && tr) t_c = clock64();
+                if (++s_ == TC2_NST) { s_ = 0; ph_ ^= 1; }
+              }
             }
-            ptx::mma2_commit_mc(bar_wempty + 8 * sg, 3);
-            if (c0 + 2 >= nch) ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
+            const uint64_t aact = adesc0 + ((SM_ACT + X * 65536) >> 4);
+            if (l != 0 && !view_layer) {
+#pragma unroll
+              for (int kc = 0; kc < 8; ++kc) {
+                while (!ptx::mbar_try_wait(bar_wfull + 8 * s_, ph_)) { }
+                const uint64_t bd = bring + s_ * (TC2_STAGE_BYTES >> 4);
+                const uint64_t ad = aact + (uint64_t)((kc >> 1) * 1024 + (kc & 1) * 4);
+                ptx::mma2_f16_ss(d_tmem, ad, bd, idesc, acc);
+                ptx::mma2_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                acc = 1u;
+                ptx::mma2_commit_mc(bar_wempty + 8 * s_, 3);
+                if (kc == 0 && tr && !skip_layer) t_c = clock64();
+                if (++s_ == TC2_NST) { s_ = 0; ph_ ^= 1; }
+              }
+            } else if (view_layer) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                while (!ptx::mbar_try_wait(bar_wfull + 8 * s_, ph_)) { }
+                const uint64_t bd = bring + s_ * (TC2_STAGE_BYTES >> 4);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int kc = 2 * u + h;
+                  const uint64_t ad = aact + (uint64_t)((kc >> 1) * 1024 + (kc & 1) * 4);
+                  ptx::mma2_f16_ss(d_tmem, ad, bd + h * 256, idesc, acc);
+                  ptx::mma2_f16_ss(d_tmem, ad + 2, bd + h * 256 + 2, idesc, 1u);
+                  acc = 1u;
+                }
+                ptx::mma2_commit_mc(bar_wempty + 8 * s_, 3);
+                if (u == 0 && tr) t_c = clock64();
+                if (++s_ == TC2_NST) { s_ = 0; ph_ ^= 1; }
+              }
+            }
+            ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
+            if (tr) { trp[0] = t_a; trp[1] = t_b; trp[2] = t_c; trp[3] = clock64(); }
           }
           __syncwarp();
-          if (tr) trp[3] = clock64();
+          stage += (uint32_t)nu;
+          while (stage >= TC2_NST) { stage -= TC2_NST; ph ^= 1; }
         }
-        if (ptx::elect_one()) ptx::mbar_arrive(bar_turn + 8 * (X ^ 1));   // hand the stream over to the other slot's issuer
-        __syncwarp();
-        gi += nds;                                        // own pass consumed
-        if (X == 0) gi += nds;                            // skip slot B's pass of this layer
       }
     }
+  } else if (warp == 2 && leader) {
+    // idle (the second issuer warp of the single-CTA kernel)
   } else if ((warp == 1 || warp == 2) && !leader) {
     // idle: the peer's bulk copies signal the leader's w_full barriers directly
   } else if (warp >= 4) {
@@ -268,12 +334,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           // this slot's bias selector for the NEXT layer
           {
             const int nxt = (l + 1 < n_bias) ? l + 1 : ((l == NL - 1) ? 0 : -1);
-            if (q == 0 && ch == 0 && lane < 8 && nxt >= 0) write_bias_selector(sb + SM_ONES + X * 256, lane, nxt, n_bias);
+            if (q == 0 && ch == 0 && lane < 8 && nxt >= 0) write_bias_selector(sb + P2_ONES + X * 256, lane, nxt, n_bias);
           }
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
+          const long long t_f = (p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) ? clock64() : 0;
           arrive_leader(bar_act + 8 * X);
           if (tr) trp[2] = clock64();
+          if (p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) { p.trace[2500 + blockIdx.x * 32 + (warp - 4) * 2] = t_f; p.trace[2501 + blockIdx.x * 32 + (warp - 4) * 2] = clock64(); }
         } else {
           // views_linears[0] (N=128): 64 columns per warp; + per-ray view bias, ReLU, rgb_linear
           const float* vbrow = p.vb + n_ray * 128;
@@ -281,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           ptx::tmem_ld_x32(t_lane + ch * 64, va);
           ptx::tmem_ld_x32(t_lane + ch * 64 + 32, vb);
           ptx::tmem_ld_wait();
-          if (q == 0 && ch == 0 && lane < 8) write_bias_selector(sb + SM_ONES + X * 256, lane, 0, n_bias);   // next super-tile, layer 0
+          if (q == 0 && ch == 0 && lane < 8) write_bias_selector(sb + P2_ONES + X * 256, lane, 0, n_bias);   // next super-tile, layer 0
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           arrive_leader(bar_act + 8 * X);                      // accumulator drained: next super-tile may start
@@ -305,11 +373,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         }
       }
       // ---- heads: combine the two column halves, then raw -> compositing (ch == 0 warps) ----
-      const uint32_t part = a_part + (uint32_t)(X * 128 + r) * 16u;
+      // the partials are parked in the first 2 KB of this slot's A tile, which is dead between the last layer's
+      // d_full and the next super-tile's layer-0 epilogue (second barrier: nobody overwrites them before they are read)
+      const uint32_t part = act_base + (uint32_t)r * 16u;
       if (ch == 1) sts128(part, make_float4(hp0, hp1, hp2, hp3));
       ptx::named_bar_sync(1 + X, 256);
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ch == 0) o = lds128(part);
+      ptx::named_bar_sync(1 + X, 256);
       if (ch == 0) {
-        const float4 o = lds128(part);
         float4 raw4;
         if (p.use_viewdirs) raw4 = make_float4(hp0 + o.x + lds32(a_heads + 641 * 4), hp1 + o.y + lds32(a_heads + 642 * 4),
                                                hp2 + o.z + lds32(a_heads + 643 * 4), hp3 + o.w + lds32(a_heads + 640 * 4));

@@ -105,9 +105,9 @@ def test_empty_and_single_ray(G):
     assert rel_l2(r1["rgb_map"].cpu().numpy(), ref["rgb_map"]) < 2e-4
 
 
-def test_cta_pair_kernel_matches_default_kernel():
-    """NERF_B200_PAIR=1 selects the cta_group::2 pair kernel (fused_tc2.cuh, experimental): same results as the
-    default kernel to fp32 accumulation-order noise.  Run in a subprocess because the mode is latched at first launch."""
+def test_cta_pair_kernel_matches_single_cta_kernel():
+    """The default cta_group::2 pair kernel (fused_tc2.cuh) and the single-CTA kernel it superseded
+    (fused_tc.cuh, NERF_B200_PAIR=0) give the same results to fp32 accumulation-order noise.  Run in a subprocess because the mode is latched at first launch."""
     import os, subprocess, sys
     code = r'''
 import os, sys, numpy as np, torch

@@ -156,3 +156,19 @@ def test_fp64_oracle_is_consistent():
     r32 = run_oracle_case(fx)
     r64 = run_oracle_case(fx, np.float64)
     assert rel_l2(r32["rgb_map"], r64["rgb_map"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["lego_det", "lego_sharp_det"])
+def test_torch_restatement_matches_reference(name):
+    """oracle/torch_ref.py (the op chain timed as the PyTorch-GPU baseline by tools/torch_gpu_reference.py)
+    reproduces the reference's outputs on the deterministic lego fixtures."""
+    import torch
+    from oracle import torch_ref as T
+    fx = load_golden(name)
+    sd = [{k: torch.from_numpy(v) for k, v in synth.nerf_state(int(fx["seed_w"]) + i, bool(fx["sharpen"])).items()} for i in (0, 1)]
+    rays = torch.from_numpy(fx["rays"])
+    with torch.no_grad():
+        r = T.render(rays[0], rays[1], sd[0], sd[1], float(fx["near"]), float(fx["far"]), S=int(fx["N_samples"]),
+                     n_imp=int(fx["N_importance"]), white_bkgd=bool(fx["white_bkgd"]))
+    for k, t in {"rgb_map": 1e-5, "acc_map": 1e-5, "rgb0": 1e-5, "acc0": 1e-5, "z_std": 2e-5}.items():
+        assert rel_l2(r[k].numpy(), fx[k]) < t, (name, k, rel_l2(r[k].numpy(), fx[k]))

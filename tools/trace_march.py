@@ -30,22 +30,31 @@ with torch.no_grad():
     nb.render(400, 400, sb["K"], rays=rays, **kw); torch.cuda.synchronize()
     lib.nerf_b200_debug_set_trace(None)
 t = tr.cpu().numpy()
-iss = t[:400].reshape(10, 10, 4); prod = t[1024:1024 + 400].reshape(-1, 2); epi = t[2048:2048 + 128].reshape(2, 16, 4)
-t00 = iss[0, 0, 0]
-print("issuer: layer chunk | t_start wfull_wait act_wait(chunk0) chunk_total")
-prev = None
-for l in range(10):
-    for c in range(10):
-        a = iss[l, c]
-        if a[0] == 0: continue
-        print(f"  L{l} c{c}: start {a[0]-t00:7d}  wfull_wait {a[1]-a[0]:5d}  act_wait {(a[2]-a[1]) if a[2] else 0:5d}  total {a[3]-a[0]:5d}  gap_prev {(a[0]-prev) if prev else 0:5d}")
-        prev = a[3]
-print("super-tile issuer span:", iss[iss > 0].max() - t00)
-pp = t[1024:1024 + 64].reshape(16, 4)
-print("pair producer L2: (pass,chunk) start, wempty_wait, issue", [(i // 8, i % 8, int(r[0] - t00), int(r[1] - r[0]), int(r[2] - r[1])) for i, r in enumerate(pp) if r[0]])
-print("producer: chunk | wempty_wait")
-pw = [(i, p[1] - p[0], p[0] - t00) for i, p in enumerate(prod) if p[0]]
-print("  ", [(i, int(w)) for i, w, _ in pw][:160])
+PAIR = os.environ.get("NERF_B200_PAIR", "1")[:1] != "0"
+epi = t[2048:2048 + 128].reshape(2, 16, 4)
+if PAIR:
+    ps = t[:80].reshape(10, 2, 4); t00 = ps[0, 0, 0]
+    print("pair issuer, per pass (layer, slot): start | act_wait | first unit issued after | pass issue time | gap to next pass start")
+    flat = [(l, X, ps[l, X]) for l in range(10) for X in range(2) if ps[l, X, 0]]
+    for i, (l, X, a) in enumerate(flat):
+        nxt = flat[i + 1][2][0] if i + 1 < len(flat) else a[3]
+        print(f"  L{l} {'AB'[X]}: start {a[0]-t00:7d}  act_wait {a[1]-a[0]:5d}  first_unit {a[2]-a[1]:5d}  issue {a[3]-a[1]:5d}  gap_next {nxt-a[3]:5d}")
+    print("super-tile issuer span:", ps[ps > 0].max() - t00)
+else:
+    iss = t[:400].reshape(10, 10, 4); prod = t[1024:1024 + 400].reshape(-1, 2)
+    t00 = iss[0, 0, 0]
+    print("issuer: layer chunk | t_start wfull_wait act_wait(chunk0) chunk_total")
+    prev = None
+    for l in range(10):
+        for c in range(10):
+            a = iss[l, c]
+            if a[0] == 0: continue
+            print(f"  L{l} c{c}: start {a[0]-t00:7d}  wfull_wait {a[1]-a[0]:5d}  act_wait {(a[2]-a[1]) if a[2] else 0:5d}  total {a[3]-a[0]:5d}  gap_prev {(a[0]-prev) if prev else 0:5d}")
+            prev = a[3]
+    print("super-tile issuer span:", iss[iss > 0].max() - t00)
+    pw = [(i, p[1] - p[0], p[0] - t00) for i, p in enumerate(prod) if p[0]]
+    print("producer: chunk | wempty_wait")
+    print("  ", [(i, int(w)) for i, w, _ in pw][:160])
 for X in range(2):
     for l in range(10):
         a = epi[X, l]
@@ -58,3 +67,12 @@ print("super-tile | issuer start (rel), encfull_wait | period | sampler encfree_
 for s in range(n):
     print(f"  st{s:2d}: start {ist[s,0]-ist[0,0]:8d} encfull_wait {ist[s,1]-ist[s,0]:6d} period {(ist[s,0]-ist[s-1,0]) if s else 0:6d} | "
           f"encfree_wait {smp[s,1]-smp[s,0]:6d} encode {send[s]-smp[s,1]:6d}")
+
+if PAIR:
+    w = t[2500:2564].reshape(2, 16, 2)
+    print("pair kernel, layer 3 epilogue, per warp (CTA 0 / CTA 1; warps 4..19): fence done, arrive done  (relative to pass L3 A start)")
+    base = ps[3, 0, 0]
+    for b in range(2):
+        print(f"  CTA {b}:", [(int(w[b, i, 0] - base), int(w[b, i, 1] - base)) for i in range(16)])
+    print("  issuer: L3 A act seen", int(ps[3,0,1]-base), "L3 A issued", int(ps[3,0,3]-base), "| L3 B act seen", int(ps[3,1,1]-base), "issued", int(ps[3,1,3]-base), "| L4 A act seen", int(ps[4,0,1]-base), "| L4 B act seen", int(ps[4,1,1]-base))
+    e = epi; print("  epi warp 4 (CTA 0) L3: d_full seen", int(e[0,3,1]-base), " X1:", int(e[1,3,1]-base))
