@@ -26,7 +26,7 @@ from ._lib import NerfCamera, NerfNetGrads, NerfNetParams, NerfPassOut, NerfRend
 
 __all__ = ["NeRF", "Embedder", "get_embedder", "sample_pdf", "raw2outputs", "run_network", "batchify",
            "batchify_rays", "render_rays", "render", "create_nerf", "get_rays", "get_rays_np", "ndc_rays",
-           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "launch_count", "DEBUG"]
+           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "launch_count", "DEBUG", "GraphedRender"]
 
 DEBUG = False
 _PRECISION = {"mode": PREC_TC_FP16}
@@ -708,3 +708,59 @@ def create_nerf(args, device=None):
     render_kwargs_test['perturb'] = False
     render_kwargs_test['raw_noise_std'] = 0.
     return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer
+
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of render() for a fixed ray count (no reference counterpart)
+# ------------------------------------------------------------------------------------------------
+
+class GraphedRender:
+    """`render(H, W, K, rays=..., **render_kwargs)` under `torch.no_grad()`, captured once into a CUDA graph for a
+    fixed number of rays and replayed per call: host -> device copy of the rays, one graph launch (ray packing,
+    z sampling, both fused passes, resampling), one device -> host copy of `[rgb(3), disp, acc]`.
+
+    After the fusion a 4096-ray render is ~1 ms of GPU time, so the ~10 Python-level launches and allocations of
+    `render()` (the reference's structure, run_nerf.py:69-134 -> :54-66 -> :308-418) cost as much as the kernels
+    when the GPU starts idle; render_only / test-time callers (run_nerf.py:668,:805,:823 iterate `render` over
+    poses under no_grad) can use this instead.  Deterministic settings only (perturb = 0, raw_noise_std = 0:
+    the graph would replay the same random draws).  Weight updates are picked up by `refresh()` (re-packs into
+    the same device buffer the graph reads)."""
+
+    def __init__(self, H, W, K, n_rays, **render_kwargs):
+        if render_kwargs.get("perturb", 0.) or render_kwargs.get("raw_noise_std", 0.):
+            raise ValueError("GraphedRender supports deterministic rendering only (perturb = 0, raw_noise_std = 0)")
+        self._nets = [n for n in (render_kwargs.get("network_fn"), render_kwargs.get("network_fine")) if isinstance(n, NeRF)]
+        dev = _render_device(render_kwargs)
+        self.n_rays = int(n_rays)
+        self.rays = torch.zeros((2, self.n_rays, 3), device=dev, dtype=torch.float32)
+        self.rays[1, :, 2] = -1.0                                       # any non-degenerate direction for the warm-up
+        self.host_out = torch.empty((self.n_rays, 5), dtype=torch.float32).pin_memory()
+        call = lambda: render(H, W, K, rays=self.rays, **render_kwargs)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(2):                                          # one-time work (packing, opt-ins, caches) outside the capture
+                call()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            rgb, disp, acc, extras = call()
+            self.packed_out = torch.cat([rgb, disp[:, None], acc[:, None]], -1)
+        self.device_out = (rgb, disp, acc, extras)
+
+    def refresh(self):
+        """Call after the networks' parameters changed (optimizer step, load_state_dict)."""
+        if _PRECISION["mode"] == PREC_TC_FP16:
+            for n in self._nets:
+                n.packed()
+
+    def __call__(self, rays_host):
+        """rays_host: [2, n_rays, 3] fp32 (pinned memory makes the copy asynchronous).  Returns the pinned host
+        tensor [n_rays, 5] = rgb_map (3), disp_map, acc_map; the device tensors of the last call stay available
+        in `.device_out`.  Synchronises the current stream before returning."""
+        self.rays.copy_(rays_host, non_blocking=True)
+        self.graph.replay()
+        self.host_out.copy_(self.packed_out, non_blocking=True)
+        torch.cuda.current_stream(self.rays.device).synchronize()
+        return self.host_out

@@ -265,6 +265,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     uint32_t swk[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) swk[c] = act_base + (uint32_t)(ch * 2) * 16384u + act_row_off(r) + (uint32_t)((c ^ (r & 7)) << 4);
+    // Compositing of super-tile s is deferred to the idle window after this slot's layer-1 epilogue of super-tile
+    // s + 1 (the epilogue warps wait ~3.5 k cycles for every d_full): done right after the heads it delayed the
+    // next super-tile's layer-0 epilogue and left the tensor pipes idle for ~7 k cycles per super-tile.
+    // The raw values wait in registers (ch == 0 warps), row indices are recomputed.
+    float4 pend = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto composite_st = [&](int s) {
+      const int lr_ = s * TC_ST + X * TC_TILE + r;
+      const bool valid_ = lr_ < nrows;
+      const int rl_ = (valid_ ? lr_ : nrows - 1) / p.S;
+      long long nr_ = ray0 + rl_;
+      if (nr_ > p.N - 1) nr_ = p.N - 1;
+      if (nr_ < 0) nr_ = 0;
+      composite_rows(p, pend, valid_, lr_, rl_, nr_, row_begin, s, X, q, lane, a_carry);
+    };
+    const int defer_l = (NL > 1) ? 1 : 0;
     for (int st = 0; st < nst; ++st) {
       float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f, hp3 = 0.f;           // head partial sums of this thread's columns
       const int lr = st * TC_ST + X * TC_TILE + r;                // row index inside this CTA's range
@@ -371,8 +386,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
             }
           }
         }
+        if (l == defer_l && st > 0 && ch == 0) composite_st(st - 1);
       }
-      // ---- heads: combine the two column halves, then raw -> compositing (ch == 0 warps) ----
+      // ---- heads: combine the two column halves -> raw (ch == 0 warps keep it for the deferred compositing) ----
       // the partials are parked in the first 2 KB of this slot's A tile, which is dead between the last layer's
       // d_full and the next super-tile's layer-0 epilogue (second barrier: nobody overwrites them before they are read)
       const uint32_t part = act_base + (uint32_t)r * 16u;
@@ -382,77 +398,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       if (ch == 0) o = lds128(part);
       ptx::named_bar_sync(1 + X, 256);
       if (ch == 0) {
-        float4 raw4;
-        if (p.use_viewdirs) raw4 = make_float4(hp0 + o.x + lds32(a_heads + 641 * 4), hp1 + o.y + lds32(a_heads + 642 * 4),
+        if (p.use_viewdirs) pend = make_float4(hp0 + o.x + lds32(a_heads + 641 * 4), hp1 + o.y + lds32(a_heads + 642 * 4),
                                                hp2 + o.z + lds32(a_heads + 643 * 4), hp3 + o.w + lds32(a_heads + 640 * 4));
-        else raw4 = make_float4(hp0 + o.x + lds32(a_heads + 1024 * 4), hp1 + o.y + lds32(a_heads + 1025 * 4),
+        else pend = make_float4(hp0 + o.x + lds32(a_heads + 1024 * 4), hp1 + o.y + lds32(a_heads + 1025 * 4),
                                 hp2 + o.z + lds32(a_heads + 1026 * 4), hp3 + o.w + lds32(a_heads + 1027 * 4));
-        const long long m = row_begin + lr;
-        if (valid && p.out.raw) reinterpret_cast<float4*>(p.out.raw)[m] = raw4;
-        if (p.do_composite) {
-          const int k = lr - rl * p.S;
-          float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, z = 0.f;
-          if (valid) {
-            const float* rd = p.rays + n_ray * p.ray_stride + 3;
-            const float norm = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);         // run_nerf.py:280
-            z = p.z_vals[m];
-            float dist = (k == p.S - 1) ? 1e10f : __fsub_rn(p.z_vals[m + 1], z);             // :277-278
-            dist = __fmul_rn(dist, norm);
-            const float sg = raw4.w + (p.noise ? p.noise[m] : 0.0f);
-            alpha = __fsub_rn(1.0f, expf(-fmaxf(sg, 0.0f) * dist));                           // :275
-            cr = sigmoidf_acc(raw4.x); cg = sigmoidf_acc(raw4.y); cb = sigmoidf_acc(raw4.z); // :282
-          }
-          // warp-local part (independent of the carry): transmittance / weights relative to
-          // max(ray start, warp start) and their segmented sums
-          const bool seg_start = valid && (k == 0), seg_end = valid && (k == p.S - 1);
-          const unsigned smask = __ballot_sync(0xffffffffu, seg_start);
-          const unsigned below = smask & ((lane == 31) ? 0xffffffffu : ((2u << lane) - 1u));
-          const int s = below ? (31 - __clz(below)) : -1;
-          const float qv = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;         // :295
-          const float pv = seg_scan_mul(qv, lane, s);
-          float ev = __shfl_up_sync(0xffffffffu, pv, 1);
-          if (lane == 0 || s == lane) ev = 1.0f;
-          const float wl = valid ? alpha * ev : 0.0f;
-          float t_r = seg_scan_add(wl * cr, lane, s), t_g = seg_scan_add(wl * cg, lane, s), t_b = seg_scan_add(wl * cb, lane, s);
-          float t_d = seg_scan_add(wl * z, lane, s), t_a = seg_scan_add(wl, lane, s);
-          // take the compositing turn: rows are consumed in order across warps / slots / super-tiles;
-          // only the few flops that thread the carry through this warp sit on the serial chain
-          const uint32_t ticket = (uint32_t)((st * 2 + X) * 4 + q);
-          if (lane == 0) { while (ld_acquire_shared(a_carry + CARRY_TURN) != ticket) { } }
-          __syncwarp();
-          const float Tin = lds32(a_carry + CARRY_T);
-          const float c_r = lds32(a_carry + CARRY_R), c_g = lds32(a_carry + CARRY_G), c_b = lds32(a_carry + CARRY_B);
-          const float c_d = lds32(a_carry + CARRY_D), c_a = lds32(a_carry + CARRY_A);
-          __syncwarp();
-          if (s < 0) { t_r = fmaf(Tin, t_r, c_r); t_g = fmaf(Tin, t_g, c_g); t_b = fmaf(Tin, t_b, c_b); t_d = fmaf(Tin, t_d, c_d); t_a = fmaf(Tin, t_a, c_a); }
-          if (lane == 31) {
-            if (seg_end) {
-              sts32(a_carry + CARRY_T, 1.0f); sts32(a_carry + CARRY_R, 0.f); sts32(a_carry + CARRY_G, 0.f); sts32(a_carry + CARRY_B, 0.f);
-              sts32(a_carry + CARRY_D, 0.f); sts32(a_carry + CARRY_A, 0.f);
-            } else {
-              sts32(a_carry + CARRY_T, (s >= 0) ? pv : Tin * pv);
-              sts32(a_carry + CARRY_R, t_r); sts32(a_carry + CARRY_G, t_g); sts32(a_carry + CARRY_B, t_b);
-              sts32(a_carry + CARRY_D, t_d); sts32(a_carry + CARRY_A, t_a);
-            }
-            st_release_shared(a_carry + CARRY_TURN, ticket + 1u);
-          }
-          // off the chain: weights and per-ray outputs
-          if (valid && p.out.weights) p.out.weights[m] = (s < 0) ? Tin * wl : wl;
-          if (seg_end) {
-            float rr = t_r, gg = t_g, bb = t_b;
-            if (p.white_bkgd) { const float bg = 1.0f - t_a; rr += bg; gg += bg; bb += bg; }  // :302-303
-            if (p.out.rgb_map) { p.out.rgb_map[n_ray * 3] = rr; p.out.rgb_map[n_ray * 3 + 1] = gg; p.out.rgb_map[n_ray * 3 + 2] = bb; }
-            if (p.out.disp_map) {
-              const float ratio = t_d / t_a;
-              const float mm = (ratio != ratio) ? ratio : fmaxf(1e-10f, ratio);              // :299
-              p.out.disp_map[n_ray] = 1.0f / mm;
-            }
-            if (p.out.acc_map) p.out.acc_map[n_ray] = t_a;
-            if (p.out.depth_map) p.out.depth_map[n_ray] = t_d;
-          }
-        }
       }
     }
+    if (ch == 0 && nst > 0) composite_st(nst - 1);                 // the last super-tile's rows
   } else {
     // =========================== sampler (warp 3) ===========================
     const int t = threadIdx.x - 96;                               // 0..31

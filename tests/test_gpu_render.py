@@ -133,3 +133,24 @@ np.save(sys.argv[1], torch.cat([r[0], r[1][:, None], r[2][:, None], r[3]["rgb0"]
     assert rel_l2(outs[1][:, :3], outs[0][:, :3]) < 2e-5
     assert rel_l2(outs[1][:, 4], outs[0][:, 4]) < 2e-5
     assert rel_l2(outs[1][:, 5:8], outs[0][:, 5:8]) < 2e-5
+
+
+def test_graphed_render_matches_render(G):
+    """GraphedRender replays exactly the kernels render() launches: bit-identical maps, also after a weight update."""
+    sb = G.synth.ray_batch("lego", 513, seed=7)
+    nets = [G.make_net(G.synth.nerf_state(0)), G.make_net(G.synth.nerf_state(1))]
+    kw = dict(ndc=False, near=2., far=6., use_viewdirs=True, network_fn=nets[0], network_fine=nets[1], network_query_fn=G.query_fn(),
+              N_samples=64, N_importance=128, perturb=0., white_bkgd=True, raw_noise_std=0.)
+    g = G.nb.GraphedRender(400, 400, sb["K"], 513, **kw)
+    rays_host = torch.from_numpy(sb["rays"]).pin_memory()
+    for rep in range(2):
+        out = g(rays_host).clone()
+        with torch.no_grad():
+            r = G.nb.render(400, 400, sb["K"], rays=G.dev(sb["rays"]), **kw)
+        ref = torch.cat([r[0], r[1][:, None], r[2][:, None]], -1).cpu()
+        assert torch.equal(out, ref), rep
+        with torch.no_grad():                                   # in-place update, as an optimizer step would do
+            nets[1].rgb_linear.bias.add_(0.25)
+        g.refresh()
+    with pytest.raises(ValueError):
+        G.nb.GraphedRender(400, 400, sb["K"], 16, **dict(kw, perturb=1.))
