@@ -177,6 +177,11 @@ size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S);
 int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch,
                             size_t scratch_bytes, void* stream);
 
+/* ---- tcgen05 "TN" self-test (groundwork for the tensor-core weight-gradient GEMM, no reference counterpart):
+ *      out[256,256] = fp16(X[128,256])^T * fp16(Y[128,256]) with fp32 accumulation; both operands are read as
+ *      MN-major SWIZZLE_128B tiles straight from the forward's activation layout (lbo = 16384, sbo = 1024). -- */
+int nerf_b200_selftest_gemm_tn(const float* X, const float* Y, float* out, int lbo_bytes, int sbo_bytes, void* stream);
+
 /* ---- debug hooks (not part of the drop-in surface): clock64 trace of CTA 0 / super-tile 1 of the next
  *      march launches into a device buffer of 4096 int64 (NULL disables); tcgen05.mma issue-rate probe */
 int nerf_b200_debug_set_trace(void* dev_buf_4096_i64);

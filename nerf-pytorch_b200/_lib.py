@@ -86,6 +86,7 @@ SIGNATURES = {
     "nerf_b200_debug_issue_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_debug_l2_stream": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_selftest_gemm": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, C.c_size_t, c_fp]),
+    "nerf_b200_selftest_gemm_tn": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp]),
 }
 
 _lib = None

@@ -564,6 +564,17 @@ int nerf_b200_debug_l2_stream(const void* buf, int buf_bytes, int chunk, int sta
   return 0;
 }
 
+int nerf_b200_selftest_gemm_tn(const float* X, const float* Y, float* out, int lbo_bytes, int sbo_bytes, void* stream) {
+  NB_CHECK_ARG(X && Y && out, "null pointer");
+  NB_CHECK_ARG(lbo_bytes >= 0 && sbo_bytes >= 0 && lbo_bytes % 16 == 0 && sbo_bytes % 16 == 0, "lbo / sbo must be multiples of 16 bytes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sm = 131072 + 256 + 1024;
+  if (int rc = smem_optin((const void*)selftest_gemm_tn_kernel, sm)) return rc;
+  selftest_gemm_tn_kernel<<<1, 128, sm, st>>>(X, Y, out, (uint32_t)lbo_bytes, (uint32_t)sbo_bytes);
+  NB_LAUNCH_OK("selftest_gemm_tn_kernel");
+  return 0;
+}
+
 int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch, size_t scratch_bytes, void* stream) {
   NB_CHECK_ARG(A && W && out && scratch, "NULL pointer");
   NB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 256 && (N == 128 || N == 256), "bad K/N");

@@ -869,6 +869,60 @@ __global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __re
   if (warp == 0) ptx::tmem_dealloc(tmem, 256);
 }
 
+// ---------------------------------------------------------------------------------------------
+// "TN" self-test for the weight-gradient GEMM of the backward (round 2): out[256,256] = X^T Y with
+// X, Y [128 rows, 256] given as the forward's activation tiles (row = sample, K-blocks of 64 columns,
+// SWIZZLE_128B) and read by the MMA as MN-MAJOR operands: A = X viewed [M = column, K = row],
+// B = Y viewed [N = column, K = row].  The canonical MN-major SWIZZLE_128B atom is 64 contiguous
+// MN elements x 8 K rows = the same physical 1 KB atom as the K-major one, so no re-layout is needed:
+// LBO = stride between 64-column groups (16 KB: the K-block stride), SBO = stride between 8-row groups
+// (1 KB).  lbo / sbo are arguments so that one GPU run can confirm the encoding.  1 CTA, 128 threads.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) selftest_gemm_tn_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                                float* __restrict__ out, uint32_t lbo, uint32_t sbo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, r = threadIdx.x;
+  const uint32_t XT = 0, YT = 65536, BAR = 131072, TPTR = BAR + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TPTR);
+  if (threadIdx.x == 0) { ptx::mbar_init(sb + BAR, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    float x[32], y[32];
+    for (int j = 0; j < 32; ++j) { x[j] = X[(size_t)r * 256 + c0 + j]; y[j] = Y[(size_t)r * 256 + c0 + j]; }
+    store_act32<false>(x, sb + XT, r, c0);
+    store_act32<false>(y, sb + YT, r, c0);
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::umma_idesc_f16_major(128, 256, 1, 1);
+    for (int mh = 0; mh < 2; ++mh)                      // output rows (X columns) 0-127, 128-255
+      for (int k = 0; k < 8; ++k) {                     // 16 sample rows per MMA: two 8-row groups = 2 KB
+        const uint64_t ad = ptx::umma_desc_full(sb + XT + mh * 2 * 16384 + k * 2048, lbo, sbo, ptx::UMMA_SW128);
+        const uint64_t bd = ptx::umma_desc_full(sb + YT + k * 2048, lbo, sbo, ptx::UMMA_SW128);
+        ptx::mma_f16_ss(tmem + mh * 256, ad, bd, idesc, k > 0 ? 1u : 0u);
+      }
+    ptx::mma_commit(sb + BAR);
+  }
+  ptx::mbar_wait(sb + BAR, 0);
+  ptx::tc_fence_after();
+  for (int mh = 0; mh < 2; ++mh)
+    for (int col0 = 0; col0 < 256; col0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_x32(tmem + ((uint32_t)(32 * warp) << 16) + mh * 256 + col0, v);
+      ptx::tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) out[(size_t)(mh * 128 + r) * 256 + col0 + j] = __uint_as_float(v[j]);
+    }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
 // MMA issue-rate microbenchmark: `reps` x (M=128, N, K=16) tcgen05.mma on resident (garbage) operands,
 // alternating between two accumulators; out[0] = cycles from first issue to completion of the last.
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int reps, int N, int b_sw64, long long* out) {

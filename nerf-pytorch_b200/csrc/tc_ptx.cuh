@@ -91,9 +91,23 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_b
   d |= layout_type << 61;                              // layout type    [61,64)
   return d;
 }
+// full form: explicit leading-dimension byte offset (MN-major operands use both strides)
+__device__ __forceinline__ uint64_t umma_desc_full(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout_type << 61;
+  return d;
+}
 // instruction descriptor: D=f32, A=B=f16, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with MN-major A and/or B (bits 15 / 16): the operand's contiguous dimension is M (N), not K
+__host__ __device__ constexpr uint32_t umma_idesc_f16_major(int M, int N, int a_mn, int b_mn) {
+  return umma_idesc_f16(M, N) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16);
 }
 
 // one elected lane of a fully converged warp (the surrounding control flow stays warp-uniform, so the

@@ -34,6 +34,21 @@ def test_tcgen05_selftest_gemm(G, K, N):
     assert err < 2e-3, err          # only fp32 accumulation order differs
 
 
+def test_tcgen05_selftest_gemm_tn(G):
+    """MN-major operands straight from the activation layout (the weight-gradient GEMM's access pattern):
+    out[256,256] = fp16(X)^T fp16(Y) over 128 sample rows, LBO = K-block stride, SBO = 8-row group stride."""
+    lib = G._lib.load()
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((128, 256)).astype(np.float32)
+    Y = rng.standard_normal((128, 256)).astype(np.float32)
+    x, y = G.dev(X), G.dev(Y)
+    out = torch.zeros((256, 256), device=G.DEV)
+    G._lib.check(lib.nerf_b200_selftest_gemm_tn(G.ptr(x), G.ptr(y), G.ptr(out), 16384, 1024, G.stream()), "selftest_tn")
+    torch.cuda.synchronize()
+    ref = X.astype(np.float16).astype(np.float64).T @ Y.astype(np.float16).astype(np.float64)
+    assert rel_l2(out.cpu().numpy(), ref) < 1e-5
+
+
 def test_embed(G):
     fx = load_golden("units")
     for L in (10, 4, 2):
