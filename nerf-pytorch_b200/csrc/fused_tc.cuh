@@ -184,7 +184,7 @@ __global__ void pack_tables_kernel(PackTables t, uint8_t* __restrict__ dst) {
 
 // view-direction contribution of views_linears[0], once per ray (the reference recomputes it per
 // sample through the expand at run_nerf.py:44-46):  vb[n][j] = b[j] + sum_c W[j][256+c] * enc(v_n)[c]
-constexpr int VB_RAYS = 32;       // rays per block
+constexpr int VB_RAYS = 8;        // rays per block (512 blocks for a 4096-ray chunk: the kernel is latency-bound)
 __global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict__ dirs, int dir_stride, long long N, int Lv, int ICV,
                                                      const float* __restrict__ vdir, float* __restrict__ vb) {
   __shared__ float s_enc[VB_RAYS][64];

@@ -345,6 +345,27 @@ __global__ void fine_z_kernel(const float* __restrict__ z_vals, const float* __r
   // (ties resolved z-before-sample and by index: a permutation, like any sort)
   const int SF = S + n_imp;
   float* zout = z_fine + n * SF;
+  // the samples are themselves ascending whenever u is (always for det = True: the inverse CDF is monotone);
+  // then #{s_k < s_j or tied with k < j} = j and #{samples < z_i} is a lower bound: two binary searches
+  // instead of S * n_imp comparisons.  Same permutation as the general path below.
+  bool sorted = true;
+  for (int j = lane; j + 1 < n_imp; j += 32) sorted = sorted && (o[j] <= o[j + 1]);
+  sorted = __all_sync(0xffffffffu, sorted);
+  if (sorted) {
+    for (int i = lane; i < S; i += 32) {
+      const float zi = s_all[i];
+      int lo = 0, hi = n_imp;                           // first index with sample >= z_i
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (o[mid] < zi) lo = mid + 1; else hi = mid; }
+      zout[i + lo] = zi;
+    }
+    for (int j = lane; j < n_imp; j += 32) {
+      const float sj = o[j];
+      int lo = 0, hi = S;                               // #{z <= s_j}: first index with z > s_j
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (s_all[mid] > sj) hi = mid; else lo = mid + 1; }
+      zout[lo + j] = sj;
+    }
+    return;
+  }
   for (int i = lane; i < S; i += 32) {
     const float zi = s_all[i];
     int cnt = 0;
@@ -360,6 +381,5 @@ __global__ void fine_z_kernel(const float* __restrict__ z_vals, const float* __r
     zout[cnt] = sj;
   }
 }
-
 
 }  // namespace nb
