@@ -130,3 +130,56 @@ def test_bench_reference_arm_runs_on_cpu():
                          capture_output=True, text=True, timeout=600)
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def _cuobjdump(*args):
+    import shutil, subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    from nerf_pytorch_b200 import _lib
+    return subprocess.run([exe, *args, _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+
+
+def test_built_kernels_use_blackwell_tensor_and_tma_instructions(nb):
+    """Static evidence in the cross-compiled sm_100a SASS (no GPU needed): the default fused kernel issues
+    cta_group::2 tcgen05.mma, loads weights with tensor-map TMA, reads accumulators with tcgen05.ld and commits through
+    multicast mbarrier arrives; the superseded single-CTA kernel uses the cta_group::1 forms.  Guards against a silent
+    regression to mma.sync / plain loads."""
+    sass = _cuobjdump("-sass")
+    funcs = {}
+    cur = None
+    for ln in sass.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1); funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(ln)
+    def body(sub):
+        names = [k for k in funcs if sub in k]
+        assert len(names) == 1, (sub, names)
+        return "\n".join(funcs[names[0]])
+    pair, single = body("march_tc2_kernel"), body("march_tc_kernel")
+    for mnem in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "LDTM.x32", "UTCBAR.2CTA.MULTICAST", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "ELECT", "F2FP.RELU"):
+        assert mnem in pair, mnem
+    for mnem in ("UTCHMMA", "UBLKCP", "LDTM.x32", "UTCBAR", "ELECT"):
+        assert mnem in single, mnem
+    assert "HMMA.16816" not in pair and "HMMA.16816" not in single          # no mma.sync path
+    assert "UTCHMMA" in body("selftest_gemm_tn_kernel")
+
+
+def test_fused_kernels_fit_their_resource_budget(nb):
+    """640 threads x 96 registers is the whole register file (allocation granularity: 4 warps); the fused kernels must
+    not exceed it, and their spill stack stays small (sincosf slow path + the deferred raw values)."""
+    usage = _cuobjdump("-res-usage")
+    found = {}
+    lines = usage.splitlines()
+    for i, ln in enumerate(lines):
+        m = re.search(r"Function (\S*march_tc2?_kernel\S*):", ln)
+        if m and i + 1 < len(lines):
+            r = re.search(r"REG:(\d+) STACK:(\d+)", lines[i + 1])
+            found[m.group(1)] = (int(r.group(1)), int(r.group(2)))
+    assert len(found) == 2, found
+    for name, (reg, stack) in found.items():
+        assert reg <= 96, (name, reg)
+        assert stack <= 160, (name, stack)
