@@ -182,6 +182,20 @@ int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float*
  *      MN-major SWIZZLE_128B tiles straight from the forward's activation layout (lbo = 16384, sbo = 1024). -- */
 int nerf_b200_selftest_gemm_tn(const float* X, const float* Y, float* out, int lbo_bytes, int sbo_bytes, void* stream);
 
+/* ---- EXPERIMENTAL (round-2 groundwork, no reference counterpart, not used by any entry point above): building
+ *      blocks of the tensor-core backward over "tile images" -- [128 x C] fp16 tiles (C in {64,128,256}) stored in
+ *      global memory byte-for-byte in the shared-memory activation layout (csrc/bwd_tc.cuh).  A [M x C] matrix takes
+ *      ceil(M/128) * C * 256 bytes.
+ *        tile_pack   : fp32 row-major [M,C] * scale -> images          tile_unpack: images * scale -> fp32 [M,C]
+ *        tile_colsum : colsum[c] += scale * sum_rows X[r][c]           (bias gradients)
+ *        wgrad_tiles : dW[Mc,Nc] (ld = ldw, fp32, atomically accumulated) += scale * sum_tiles X_t^T Y_t
+ *        dgrad_tiles : OUT_t[128,256] = relu_mask(H_t)( X_t[128,Kc] * W[Kc,256] ), W and OUT as images, H nullable ---- */
+int nerf_b200_exp_tile_pack(const float* src, int64_t M, int C, float scale, void* img, void* stream);
+int nerf_b200_exp_tile_unpack(const void* img, int64_t M, int C, float scale, float* dst, void* stream);
+int nerf_b200_exp_tile_colsum(const void* img, int64_t n_tiles, int C, float scale, float* colsum, void* stream);
+int nerf_b200_exp_wgrad_tiles(const void* ximg, const void* yimg, int64_t n_tiles, int Mc, int Nc, float scale, float* dW, int ldw, void* stream);
+int nerf_b200_exp_dgrad_tiles(const void* ximg, const void* wimg, const void* himg, int64_t n_tiles, int Kc, void* oimg, void* stream);
+
 /* ---- debug hooks (not part of the drop-in surface): clock64 trace of CTA 0 / super-tile 1 of the next
  *      march launches into a device buffer of 4096 int64 (NULL disables); tcgen05.mma issue-rate probe */
 int nerf_b200_debug_set_trace(void* dev_buf_4096_i64);

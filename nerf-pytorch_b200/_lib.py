@@ -87,6 +87,11 @@ SIGNATURES = {
     "nerf_b200_debug_l2_stream": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_selftest_gemm": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, C.c_size_t, c_fp]),
     "nerf_b200_selftest_gemm_tn": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp]),
+    "nerf_b200_exp_tile_pack": (C.c_int, [c_fp, C.c_int64, C.c_int, C.c_float, c_fp, c_fp]),
+    "nerf_b200_exp_tile_unpack": (C.c_int, [c_fp, C.c_int64, C.c_int, C.c_float, c_fp, c_fp]),
+    "nerf_b200_exp_tile_colsum": (C.c_int, [c_fp, C.c_int64, C.c_int, C.c_float, c_fp, c_fp]),
+    "nerf_b200_exp_wgrad_tiles": (C.c_int, [c_fp, c_fp, C.c_int64, C.c_int, C.c_int, C.c_float, c_fp, C.c_int, c_fp]),
+    "nerf_b200_exp_dgrad_tiles": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, c_fp, c_fp]),
 }
 
 _lib = None

@@ -6,6 +6,7 @@
 #include "mlp_simt.cuh"
 #include "fused_tc.cuh"
 #include "fused_tc2.cuh"
+#include "bwd_tc.cuh"
 #include <stdlib.h>
 
 namespace nb {
@@ -561,6 +562,53 @@ int nerf_b200_debug_l2_stream(const void* buf, int buf_bytes, int chunk, int sta
   if (int rc = smem_optin((const void*)l2_stream_probe_kernel, sm)) return rc;
   l2_stream_probe_kernel<<<nblocks, 64, sm, (cudaStream_t)stream>>>(static_cast<const uint8_t*>(buf), buf_bytes, chunk, stages, passes, static_cast<long long*>(out_i64));
   NB_LAUNCH_OK("l2_stream_probe_kernel");
+  return 0;
+}
+
+// ---- experimental building blocks of the tensor-core backward (bwd_tc.cuh); not used by any default path ----
+int nerf_b200_exp_tile_pack(const float* src, int64_t M, int C, float scale, void* img, void* stream) {
+  NB_CHECK_ARG(src && img && M >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
+  if (M == 0) return 0;
+  const long long n = ((M + 127) / 128) * 128 * (C >> 3);
+  tile_pack_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, M, C, scale, static_cast<uint8_t*>(img));
+  NB_LAUNCH_OK("tile_pack_kernel");
+  return 0;
+}
+int nerf_b200_exp_tile_unpack(const void* img, int64_t M, int C, float scale, float* dst, void* stream) {
+  NB_CHECK_ARG(dst && img && M >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
+  if (M == 0) return 0;
+  tile_unpack_kernel<<<cdiv(M * (C >> 3), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img), M, C, scale, dst);
+  NB_LAUNCH_OK("tile_unpack_kernel");
+  return 0;
+}
+int nerf_b200_exp_tile_colsum(const void* img, int64_t n_tiles, int C, float scale, float* colsum, void* stream) {
+  NB_CHECK_ARG(colsum && img && n_tiles >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
+  if (n_tiles == 0) return 0;
+  const int grid = (int)(n_tiles < 4 * num_sms() ? n_tiles : 4 * num_sms());
+  tile_colsum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img), n_tiles, C, scale, colsum);
+  NB_LAUNCH_OK("tile_colsum_kernel");
+  return 0;
+}
+int nerf_b200_exp_wgrad_tiles(const void* ximg, const void* yimg, int64_t n_tiles, int Mc, int Nc, float scale, float* dW, int ldw, void* stream) {
+  NB_CHECK_ARG(ximg && yimg && dW && n_tiles >= 0, "null pointer");
+  NB_CHECK_ARG((Mc == 128 || Mc == 256) && (Nc == 64 || Nc == 128 || Nc == 256) && ldw >= Nc, "unsupported shape Mc=%d Nc=%d ldw=%d", Mc, Nc, ldw);
+  if (n_tiles == 0) return 0;
+  if (int rc = smem_optin((const void*)wgrad_tiles_kernel, WG_TOTAL)) return rc;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  wgrad_tiles_kernel<<<grid, WG_THREADS, WG_TOTAL, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(ximg), static_cast<const uint8_t*>(yimg),
+                                                                                 n_tiles, Mc, Nc, scale, dW, ldw);
+  NB_LAUNCH_OK("wgrad_tiles_kernel");
+  return 0;
+}
+int nerf_b200_exp_dgrad_tiles(const void* ximg, const void* wimg, const void* himg, int64_t n_tiles, int Kc, void* oimg, void* stream) {
+  NB_CHECK_ARG(ximg && wimg && oimg && n_tiles >= 0, "null pointer");
+  NB_CHECK_ARG(Kc == 128 || Kc == 256, "unsupported reduction width Kc=%d", Kc);
+  if (n_tiles == 0) return 0;
+  if (int rc = smem_optin((const void*)dgrad_tiles_kernel, DG_TOTAL)) return rc;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  dgrad_tiles_kernel<<<grid, DG_THREADS, DG_TOTAL, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(ximg), static_cast<const uint8_t*>(wimg),
+                                                                                 static_cast<const uint8_t*>(himg), n_tiles, Kc, static_cast<uint8_t*>(oimg));
+  NB_LAUNCH_OK("dgrad_tiles_kernel");
   return 0;
 }
 
