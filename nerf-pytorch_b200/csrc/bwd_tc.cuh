@@ -24,26 +24,24 @@ __host__ __device__ __forceinline__ uint32_t img_off(int r, int col) {
 }
 __host__ __device__ __forceinline__ size_t img_bytes(int cols) { return (size_t)(cols >> 6) * 16384; }
 
-// fp32 row-major [M, C] (ld = C) -> tile images, value * scale rounded to fp16; rows >= M are zero
-__global__ void tile_pack_kernel(const float* __restrict__ src, long long M, int C, float scale, uint8_t* __restrict__ img) {
+// fp32 row-major [M, ncols] (row stride ld) -> tile images of C >= ncols columns (zero padded), value * scale rounded
+// to fp16; rows >= M are zero
+__global__ void tile_pack_kernel(const float* __restrict__ src, int ld, long long M, int ncols, int C, float scale, uint8_t* __restrict__ img) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;          // one thread per 8-column chunk
   const int cpr = C >> 3;
   const long long Mpad = ((M + 127) / 128) * 128;
   if (i >= Mpad * cpr) return;
   const long long row = i / cpr;
   const int c8 = (int)(i - row * cpr);
-  uint32_t h[4] = {0u, 0u, 0u, 0u};
-  if (row < M) {
-    const float* s = src + row * C + c8 * 8;
+  float x[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = ptx::cvt_f16x2(s[2 * j] * scale, s[2 * j + 1] * scale);
-  }
+  for (int j = 0; j < 8; ++j) x[j] = (row < M && c8 * 8 + j < ncols) ? src[row * ld + c8 * 8 + j] * scale : 0.f;
   uint8_t* dst = img + (size_t)(row >> 7) * img_bytes(C) + img_off((int)(row & 127), c8 * 8);
-  *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(ptx::cvt_f16x2(x[0], x[1]), ptx::cvt_f16x2(x[2], x[3]), ptx::cvt_f16x2(x[4], x[5]), ptx::cvt_f16x2(x[6], x[7]));
 }
 
-// tile images -> fp32 row-major [M, C], value * scale
-__global__ void tile_unpack_kernel(const uint8_t* __restrict__ img, long long M, int C, float scale, float* __restrict__ dst) {
+// tile images -> fp32 row-major [M, C] (row stride ld), value * scale
+__global__ void tile_unpack_kernel(const uint8_t* __restrict__ img, long long M, int C, float scale, float* __restrict__ dst, int ld) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cpr = C >> 3;
   if (i >= M * cpr) return;
@@ -51,7 +49,7 @@ __global__ void tile_unpack_kernel(const uint8_t* __restrict__ img, long long M,
   const int c8 = (int)(i - row * cpr);
   const uint4 v = *reinterpret_cast<const uint4*>(img + (size_t)(row >> 7) * img_bytes(C) + img_off((int)(row & 127), c8 * 8));
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  float* d = dst + row * C + c8 * 8;
+  float* d = dst + row * ld + c8 * 8;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const __half2 hh = *reinterpret_cast<const __half2*>(&w[j]);
@@ -85,7 +83,7 @@ __global__ void tile_colsum_kernel(const uint8_t* __restrict__ img, long long n_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// wgrad: dW[Mc, Nc] (fp32, row-major, ld = ldw) += scale * sum_t X_t^T Y_t over this CTA's tiles (grid-stride).
+// wgrad: dW[Mc, n_valid <= Nc] (fp32, row-major, ld = ldw) += scale * sum_t X_t^T Y_t over this CTA's tiles (grid-stride).
 // X images have Mc columns (Mc in {128, 256}), Y images Nc columns (Nc in {64, 128, 256}).  Both operands MN-major.
 // Ring: 2 stages of one 64-row half tile of X and of Y (<= 2 x 64 KB); accumulators: TMEM columns [0, Nc) for output
 // rows 0-127 and [256, 256 + Nc) for rows 128-255, kept across all tiles; one fp32 atomic flush per CTA.
@@ -96,7 +94,7 @@ constexpr uint32_t WG_STAGE = 65536, WG_BARS = 2 * WG_STAGE, WG_TOTAL = WG_BARS 
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tiles_kernel(const uint8_t* __restrict__ ximg, const uint8_t* __restrict__ yimg,
                                                                    long long n_tiles, int Mc, int Nc, float scale,
-                                                                   float* __restrict__ dW, int ldw) {
+                                                                   float* __restrict__ dW, int ldw, int n_valid) {
   uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,7 +169,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tiles_kernel(const uint8_
         ptx::tmem_ld_wait();
         float* o = dW + (size_t)(mh * 128 + r) * ldw + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]) * scale);
+        for (int j = 0; j < 32; ++j) if (c0 + j < n_valid) atomicAdd(o + j, __uint_as_float(v[j]) * scale);
       }
   }
   ptx::tc_fence_before();

@@ -420,7 +420,22 @@ static const int BWD_RAYS_PER_SLAB = 512;     // rays recomputed + back-propagat
 
 size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S) {
   const long long rows = (long long)(N < BWD_RAYS_PER_SLAB ? N : BWD_RAYS_PER_SLAB) * S;
-  return (size_t)rows * (63 + 63 + 16 * 256 + 256 + 128 + 8 + 512 + 128 + 3) * 4 + 1024;   // upper bound over supported nets
+  // upper bound over supported nets; the last term: three fp16 tile images of 256 columns (experimental tensor-core GEMMs)
+  return (size_t)rows * (63 + 63 + 16 * 256 + 256 + 128 + 8 + 512 + 128 + 3 + 3 * 128) * 4 + 1024 + 3 * 128 * 512 + 3 * 1024;
+}
+
+// ---- experimental: the backward's large GEMMs on tensor cores (bwd_tc.cuh), NERF_B200_BWD_TC=1; never validated on a GPU ----
+struct TcScratch { uint8_t* a; uint8_t* b; uint8_t* o; float scale; };
+static bool bwd_tc_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("NERF_B200_BWD_TC"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+static int pack_img(const float* src, int ld, long long M, int ncols, int C, float scale, uint8_t* img, cudaStream_t st) {
+  const long long n = ((M + 127) / 128) * 128 * (C >> 3);
+  tile_pack_kernel<<<cdiv(n, 256), 256, 0, st>>>(src, ld, M, ncols, C, scale, img);
+  NB_LAUNCH_OK("tile_pack_kernel");
+  return 0;
 }
 
 static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int N, int K, int beta, cudaStream_t st) {
@@ -434,6 +449,33 @@ static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, i
   dim3 grid(cdiv(K1, GT), cdiv(N, GT), cdiv(M, slab));
   sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, K1, N, slab);
   NB_LAUNCH_OK("sgemm_tn_kernel");
+  return 0;
+}
+// C[K1,N] += A^T B like gemm_tn, through wgrad_tiles_kernel when the shape fits (K1 in {128,256}, N <= 256) and tc != NULL
+static int gemm_tn_any(const TcScratch* tc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int K1, int N, cudaStream_t st) {
+  if (!tc || !(K1 == 128 || K1 == 256) || N > 256 || N < 8) return gemm_tn(A, lda, B, ldb, C, ldc, M, K1, N, st);
+  const int Nc = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  if (int rc = pack_img(A, lda, M, K1, K1, tc->scale, tc->a, st)) return rc;
+  if (int rc = pack_img(B, ldb, M, N, Nc, 1.0f, tc->b, st)) return rc;
+  if (int rc = smem_optin((const void*)wgrad_tiles_kernel, WG_TOTAL)) return rc;
+  const long long n_tiles = (M + 127) / 128;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  wgrad_tiles_kernel<<<grid, WG_THREADS, WG_TOTAL, st>>>(tc->a, tc->b, n_tiles, K1, Nc, 1.0f / tc->scale, C, ldc, N);
+  NB_LAUNCH_OK("wgrad_tiles_kernel");
+  return 0;
+}
+// C[M,N] = A B like gemm_nn (beta = 0), through dgrad_tiles_kernel when N == 256, K in {128,256} and tc != NULL
+static int gemm_nn_any(const TcScratch* tc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int N, int K, int beta, cudaStream_t st) {
+  if (!tc || beta != 0 || N != 256 || !(K == 128 || K == 256)) return gemm_nn(A, lda, B, ldb, C, ldc, M, N, K, beta, st);
+  if (int rc = pack_img(A, lda, M, K, K, tc->scale, tc->a, st)) return rc;
+  if (int rc = pack_img(B, ldb, K, 256, 256, 1.0f, tc->b, st)) return rc;          // W rows = reduction index
+  if (int rc = smem_optin((const void*)dgrad_tiles_kernel, DG_TOTAL)) return rc;
+  const long long n_tiles = (M + 127) / 128;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  dgrad_tiles_kernel<<<grid, DG_THREADS, DG_TOTAL, st>>>(tc->a, tc->b, nullptr, n_tiles, K, tc->o);
+  NB_LAUNCH_OK("dgrad_tiles_kernel");
+  tile_unpack_kernel<<<cdiv(M * 32, 256), 256, 0, st>>>(tc->o, M, 256, 1.0f / tc->scale, C, ldc);
+  NB_LAUNCH_OK("tile_unpack_kernel");
   return 0;
 }
 static int mask_colsum(float* d, int ldd, const float* h, int ldh, long long M, int C, float* colsum, cudaStream_t st) {
@@ -475,6 +517,16 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
     float* dh0 = p;        p += M * W;
     float* dh1 = p;        p += M * W;
     float* d_hv = p;       p += M * W2;
+    TcScratch tcs, *tc = nullptr;
+    if (bwd_tc_enabled() && W == 256) {
+      // three 256-column fp16 tile images (1 KB-aligned) behind the fp32 buffers; one static loss scale for the slab's
+      // activation gradients: |dL/drgb| <= 2 / (3 N)  (tools/bwd_precision_study.py)
+      const size_t ib = (size_t)((M + 127) / 128) * 65536;
+      uint8_t* q = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+      tcs.a = q; tcs.b = q + ib; tcs.o = q + 2 * ib;
+      tcs.scale = exp2f(floorf(log2f(3.0f * (float)N * 512.0f)));
+      tc = &tcs;
+    }
     // 1. recompute the pass in fp32 with saved activations
     pts_kernel<<<cdiv(M, 256), 256, 0, st>>>(ry, rs, zz, M, S, pts);
     NB_LAUNCH_OK("pts_kernel");
@@ -486,21 +538,21 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
     NB_TRY(nerf_b200_raw2outputs_bwd(raw, zz, ry + 3, rs, nz, nn, S, cfg->white_bkgd, g_rgb + n0 * 3, d_raw, stream));
     const float* h_last = sv.h + (size_t)(D - 1) * M * W;
     // 3. rgb_linear (run_nerf_helpers.py:114)
-    NB_TRY(gemm_tn(d_raw, 4, sv.hv, W2, grads->rgb_w, W2, M, 3, W2, st));
+    NB_TRY(gemm_tn_any(tc, d_raw, 4, sv.hv, W2, grads->rgb_w, W2, M, 3, W2, st));
     NB_TRY(mask_colsum(d_raw, 4, nullptr, 0, M, 3, grads->rgb_b, st));
-    NB_TRY(gemm_nn(d_raw, 4, net->rgb_w, W2, d_hv, W2, M, W2, 3, 0, st));
+    NB_TRY(gemm_nn_any(tc, d_raw, 4, net->rgb_w, W2, d_hv, W2, M, W2, 3, 0, st));
     // 4. views_linears[0] on cat([feature, input_views]) (:108-112)
     NB_TRY(mask_colsum(d_hv, W2, sv.hv, W2, M, W2, grads->views_b, st));
-    NB_TRY(gemm_tn(d_hv, W2, sv.feat, W, grads->views_w, W + ICV, M, W2, W, st));
-    NB_TRY(gemm_tn(d_hv, W2, sv.encv, ICV, grads->views_w + W, W + ICV, M, W2, ICV, st));
-    NB_TRY(gemm_nn(d_hv, W2, net->views_w, W + ICV, dh0, W, M, W, W2, 0, st));                // d_feature
+    NB_TRY(gemm_tn_any(tc, d_hv, W2, sv.feat, W, grads->views_w, W + ICV, M, W2, W, st));
+    NB_TRY(gemm_tn_any(tc, d_hv, W2, sv.encv, ICV, grads->views_w + W, W + ICV, M, W2, ICV, st));
+    NB_TRY(gemm_nn_any(tc, d_hv, W2, net->views_w, W + ICV, dh0, W, M, W, W2, 0, st));                // d_feature
     // 5. feature_linear and alpha_linear both read the last hidden layer (:106-107)
-    NB_TRY(gemm_tn(dh0, W, h_last, W, grads->feature_w, W, M, W, W, st));
+    NB_TRY(gemm_tn_any(tc, dh0, W, h_last, W, grads->feature_w, W, M, W, W, st));
     NB_TRY(mask_colsum(dh0, W, nullptr, 0, M, W, grads->feature_b, st));
-    NB_TRY(gemm_tn(d_raw + 3, 4, h_last, W, grads->alpha_w, W, M, 1, W, st));
+    NB_TRY(gemm_tn_any(tc, d_raw + 3, 4, h_last, W, grads->alpha_w, W, M, 1, W, st));
     NB_TRY(mask_colsum(d_raw + 3, 4, nullptr, 0, M, 1, grads->alpha_b, st));
-    NB_TRY(gemm_nn(dh0, W, net->feature_w, W, dh1, W, M, W, W, 0, st));
-    NB_TRY(gemm_nn(d_raw + 3, 4, net->alpha_w, W, dh1, W, M, W, 1, 1, st));
+    NB_TRY(gemm_nn_any(tc, dh0, W, net->feature_w, W, dh1, W, M, W, W, 0, st));
+    NB_TRY(gemm_nn_any(tc, d_raw + 3, 4, net->alpha_w, W, dh1, W, M, W, 1, 1, st));
     // 6. pts_linears, last to first (:99-103); skip layer input = cat([input_pts, h])
     float* dcur = dh1;
     float* dnext = dh0;
@@ -509,13 +561,13 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
       const bool after_skip = (l > 0) && (l - 1 == net->skip);
       const int Kl = (l == 0) ? IC : (after_skip ? W + IC : W);
       if (l == 0) {
-        NB_TRY(gemm_tn(dcur, W, sv.enc, IC, grads->pts_w[0], Kl, M, W, IC, st));
+        NB_TRY(gemm_tn_any(tc, dcur, W, sv.enc, IC, grads->pts_w[0], Kl, M, W, IC, st));
       } else {
         const float* hprev = sv.h + (size_t)(l - 1) * M * W;
         const int off = after_skip ? IC : 0;
-        if (after_skip) NB_TRY(gemm_tn(dcur, W, sv.enc, IC, grads->pts_w[l], Kl, M, W, IC, st));
-        NB_TRY(gemm_tn(dcur, W, hprev, W, grads->pts_w[l] + off, Kl, M, W, W, st));
-        NB_TRY(gemm_nn(dcur, W, net->pts_w[l] + off, Kl, dnext, W, M, W, W, 0, st));
+        if (after_skip) NB_TRY(gemm_tn_any(tc, dcur, W, sv.enc, IC, grads->pts_w[l], Kl, M, W, IC, st));
+        NB_TRY(gemm_tn_any(tc, dcur, W, hprev, W, grads->pts_w[l] + off, Kl, M, W, W, st));
+        NB_TRY(gemm_nn_any(tc, dcur, W, net->pts_w[l] + off, Kl, dnext, W, M, W, W, 0, st));
         float* t = dcur; dcur = dnext; dnext = t;
       }
     }
@@ -570,14 +622,14 @@ int nerf_b200_exp_tile_pack(const float* src, int64_t M, int C, float scale, voi
   NB_CHECK_ARG(src && img && M >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
   if (M == 0) return 0;
   const long long n = ((M + 127) / 128) * 128 * (C >> 3);
-  tile_pack_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, M, C, scale, static_cast<uint8_t*>(img));
+  tile_pack_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, C, M, C, C, scale, static_cast<uint8_t*>(img));
   NB_LAUNCH_OK("tile_pack_kernel");
   return 0;
 }
 int nerf_b200_exp_tile_unpack(const void* img, int64_t M, int C, float scale, float* dst, void* stream) {
   NB_CHECK_ARG(dst && img && M >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
   if (M == 0) return 0;
-  tile_unpack_kernel<<<cdiv(M * (C >> 3), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img), M, C, scale, dst);
+  tile_unpack_kernel<<<cdiv(M * (C >> 3), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img), M, C, scale, dst, C);
   NB_LAUNCH_OK("tile_unpack_kernel");
   return 0;
 }
@@ -596,7 +648,7 @@ int nerf_b200_exp_wgrad_tiles(const void* ximg, const void* yimg, int64_t n_tile
   if (int rc = smem_optin((const void*)wgrad_tiles_kernel, WG_TOTAL)) return rc;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   wgrad_tiles_kernel<<<grid, WG_THREADS, WG_TOTAL, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(ximg), static_cast<const uint8_t*>(yimg),
-                                                                                 n_tiles, Mc, Nc, scale, dW, ldw);
+                                                                                 n_tiles, Mc, Nc, scale, dW, ldw, Nc);
   NB_LAUNCH_OK("wgrad_tiles_kernel");
   return 0;
 }

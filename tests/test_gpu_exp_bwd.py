@@ -89,3 +89,41 @@ def test_dgrad_tiles(G, Kc, mask):
     if mask:
         ref = ref * (f16(H) > 0)
     assert rel_l2(out, ref) < 1e-3          # fp16 rounding of the output image
+
+
+def test_backward_with_tensor_core_gemms_matches_oracle():
+    """NERF_B200_BWD_TC=1 routes the backward's large GEMMs (wgrad / dgrad of the 256- and 128-wide layers) through
+    wgrad_tiles_kernel / dgrad_tiles_kernel with fp16 operands and a static loss scale; the forward recompute, the
+    ReLU masks and the small GEMMs stay fp32, so the gradients should stay within the exact test's budget.
+    Subprocess: the switch is latched at first use."""
+    import subprocess, sys, tempfile
+    code = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import gpu_common as G
+sb = G.synth.ray_batch("lego", 96, seed=4)
+pc, pf = G.synth.nerf_state(0), G.synth.nerf_state(1)
+nets = [G.make_net(pc), G.make_net(pf)]
+target = np.random.default_rng(3).random((96, 3), dtype=np.float32)
+G.nb.set_precision("fp32")
+rgb, _, _, ex = G.nb.render(400, 400, sb["K"], rays=G.dev(sb["rays"]), ndc=False, near=2., far=6., use_viewdirs=True,
+                            network_fn=nets[0], network_fine=nets[1], network_query_fn=G.query_fn(), N_samples=64,
+                            N_importance=128, perturb=0., white_bkgd=True, raw_noise_std=0.)
+loss = G.nb.img2mse(rgb, G.dev(target)) + G.nb.img2mse(ex["rgb0"], G.dev(target))
+loss.backward()
+packed = G.O.pack_rays(400, 400, sb["K"], sb["rays"][0], sb["rays"][1], False, 2.0, 6.0, True)
+l_ref, gc, gf = G.O.render_rays_grads(packed, pc, pf, 64, 128, target, white_bkgd=True)
+errs = []
+for net, g in ((nets[0], gc), (nets[1], gf)):
+    for name, p in net.named_parameters():
+        a, b = p.grad.cpu().numpy().astype(np.float64), g[name].astype(np.float64)
+        errs.append(float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)))
+np.save(sys.argv[1], np.array(errs))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "errs.npy")
+        subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=dict(os.environ, NERF_B200_BWD_TC="1"), timeout=600)
+        errs = np.load(path)
+    assert np.median(errs) < 3e-3, errs
+    assert errs.max() < 5e-2, errs
