@@ -10,15 +10,20 @@
 // Everything else (sampler, epilogue math, heads, compositing) is the code of fused_tc.cuh, per CTA.
 //
 // Cross-CTA protocol (barriers live at the same shared-memory offset in both CTAs):
-//   w_full[6]  local   : this CTA's half chunk landed (cp.async.bulk complete_tx)
-//   p_full[6]  leader  : the peer's relay warp forwards its w_full phase (remote mbarrier arrive)
-//   w_empty[6] both    : tcgen05.commit.cta_group::2 multicast -> both producers may refill the stage
+//   w_full[7]  leader  : both CTAs' tensor-map TMA loads (cta_group::2) count their bytes here (expect_tx = 2 x 8 KB)
+//   w_empty[7] both    : tcgen05.commit.cta_group::2 multicast -> both producers may refill the stage
 //   d_full[2]  both    : multicast commit -> both CTAs' epilogue warps of that slot
 //   act[2]     leader  : 16 arrivals = one per epilogue warp of the slot, 8 local + 8 remote (accumulator drained, A tile written)
 //   enc_full   leader  : 2 arrivals (both sampler warps);  enc_free both: multicast commit after the last encoding chunk
+// Training mode (template parameter EMIT, train_common.cuh): every A tile the epilogue writes (h_l, feat), the
+// encodings and the view layer's post-ReLU output are also copied to a per-tile record in global memory with
+// cp.async.bulk shared -> global, plus the sign bits of the pre-activations; two CTA-local barriers per slot:
+//   st_full[2] local   : 8 arrivals = the slot's epilogue warps wrote the tile (warp e == 0 then issues the bulk store)
+//   st_done[2] local   : the bulk store has finished reading the tile -> the next layer's epilogue may overwrite it
 #pragma once
 #include <cuda.h>
 #include "fused_tc.cuh"
+#include "train_common.cuh"
 
 namespace nb {
 
@@ -34,6 +39,14 @@ constexpr uint32_t P2_HEADS = P2_BIASB + TC_BIAS_CHUNK_BYTES / 2;     // 225792:
 constexpr uint32_t P2_BARS = P2_HEADS + 4128;                         // 229920: mbarriers
 constexpr uint32_t P2_MISC = P2_BARS + 256;                           // 230176: tmem ptr, compositing carry, pass counter
 constexpr uint32_t P2_TOTAL = P2_MISC + 128;                          // 230304
+#ifdef NERF_B200_TRACE
+constexpr bool kTrace2 = true;       // clock64 / heartbeat hooks (tools/trace_march.py); compiled out by default
+#else
+constexpr bool kTrace2 = false;
+#endif
+
+// training-mode save buffers of one pass (train_common.cuh)
+struct TrainSaveDev { uint8_t* act; uint8_t* mask; int nst_plan; uint32_t rec_act, rec_mask; };
 static_assert(P2_TOTAL <= SM_ALLOC, "pair kernel shared-memory map exceeds the allocation");
 
 // ring units per pass of layer l (all even)
@@ -42,7 +55,9 @@ __host__ __device__ __forceinline__ int tc2_layer_units(int l, int D, int skip) 
   return (l == D + 1) ? nch / 2 : nch;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p, const __grid_constant__ CUtensorMap wmap) {
+template <bool EMIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march_tc2_kernel(const MarchParams p, const __grid_constant__ CUtensorMap wmap,
+                                                                                          const TrainSaveDev sv) {
   uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -61,16 +76,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   const uint32_t bar_act = sb + P2_BARS + 128;        // [2] (leader)
   const uint32_t bar_encfull = sb + P2_BARS + 144;    //     (leader)
   const uint32_t bar_encfree = sb + P2_BARS + 152;
+  const uint32_t bar_stfull = sb + P2_BARS + 160;     // [2] (EMIT)
+  const uint32_t bar_stdone = sb + P2_BARS + 176;     // [2] (EMIT)
   // arrive on a barrier that lives in the leader CTA
   // debug heartbeat: trace[blockIdx.x * 32 + role] = last wait this role entered (trace may be mapped host memory)
-  auto hb_ = [&](int role, long long code) { if (p.trace && lane == 0 && blockIdx.x < 32) { volatile long long* t = p.trace; t[3000 + blockIdx.x * 32 + role] = code; } };
+  auto hb_ = [&](int role, long long code) { if (kTrace2 && p.trace && lane == 0 && blockIdx.x < 32) { volatile long long* t = p.trace; t[3000 + blockIdx.x * 32 + role] = code; } };
   // One arrival per warp; every lane has fenced its own writes (fence.proxy.async) before the __syncwarp.  The peer's
   // data is consumed by the peer SM's own tensor core, so the remote arrive needs no cluster-scope release.
   auto arrive_leader = [&](uint32_t bar) {
     __syncwarp();
     if (lane == 0) {
       if (leader) ptx::mbar_arrive(bar);
-      else if (p.dbg & 2) ptx::mbar_arrive_cluster(ptx::mapa(bar, 0));      // A/B: .release.cluster (slow)
       else ptx::mbar_arrive_remote(ptx::mapa(bar, 0));
     }
   };
@@ -104,6 +120,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 16); }
     ptx::mbar_init(bar_encfull, 2);
     ptx::mbar_init(bar_encfree, 2);
+    if (EMIT) for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_stfull + 8 * x, 8); ptx::mbar_init(bar_stdone + 8 * x, 1); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish2(); }
@@ -155,8 +172,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     const uint64_t bias_desc = ptx::umma_desc(sb + P2_BIASB, 256, ptx::UMMA_SW32);
     const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem, 0);
     for (int st = 0; st < nst; ++st) {
-      const bool tr = p.trace && blockIdx.x == 0 && st == 1;
-      const bool trs = p.trace && blockIdx.x == 0 && lane == 0 && st < 48;
+      const bool tr = kTrace2 && p.trace && blockIdx.x == 0 && st == 1;
+      const bool trs = kTrace2 && p.trace && blockIdx.x == 0 && lane == 0 && st < 48;
       if (trs) p.trace[2200 + 2 * st] = clock64();
       ptx::mbar_wait_cluster(bar_encfull, st & 1);
       if (trs) p.trace[2201 + 2 * st] = clock64();
@@ -174,13 +191,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           if (tr) t_a = clock64();
           hb_(1, 4000000 + st * 10000 + l * 100 + X * 50);
           // slot X's accumulator drained and its A tile written by both CTAs' epilogue warps
-          if (p.dbg & 1) {
-            if (X == 0) { ptx::mbar_wait(bar_act, actph0); actph0 ^= 1; }
-            else { ptx::mbar_wait(bar_act + 8, actph1); actph1 ^= 1; }
-          } else {
-            if (X == 0) { ptx::mbar_wait_cluster(bar_act, actph0); actph0 ^= 1; }
-            else { ptx::mbar_wait_cluster(bar_act + 8, actph1); actph1 ^= 1; }
-          }
+          if (X == 0) { ptx::mbar_wait_cluster(bar_act, actph0); actph0 ^= 1; }
+          else { ptx::mbar_wait_cluster(bar_act + 8, actph1); actph1 ^= 1; }
           if (tr) t_b = clock64();
           hb_(1, 5000000 + st * 10000 + l * 100 + X * 50);
           ptx::tc_fence_after();
@@ -280,8 +292,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       composite_rows(p, pend, valid_, lr_, rl_, nr_, row_begin, s, X, q, lane, a_carry);
     };
     const int defer_l = (NL > 1) ? 1 : 0;
+    // training mode: bulk-store bookkeeping of this slot (phases of st_full / st_done, "a store is in flight")
+    uint32_t sfph = 0, sdph = 0;
+    bool st_pending = false;
+    // the previous store of this slot has finished reading the A tile: it may be overwritten
+    auto emit_wait_prev = [&]() {
+      if (EMIT && st_pending) {
+        if (e == 0 && lane == 0) { ptx::bulk_wait_read0(); ptx::mbar_arrive(bar_stdone + 8 * X); }
+        ptx::mbar_wait(bar_stdone + 8 * X, sdph);
+        sdph ^= 1;
+      }
+    };
+    // all 8 warps of the slot have written (and proxy-fenced) their part of the tile: warp e == 0 copies `bytes` from
+    // shared-memory offset `src` to the record field at `dst`
+    auto emit_store = [&](uint8_t* dst, uint32_t src, uint32_t bytes) {
+      if (EMIT) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_stfull + 8 * X);
+        if (e == 0) {
+          ptx::mbar_wait(bar_stfull + 8 * X, sfph);
+          sfph ^= 1;
+          if (lane == 0) {
+            for (uint32_t o = 0; o < bytes; o += 16384u) ptx::bulk_s2g(dst + o, src + o, 16384u);
+            ptx::bulk_commit();
+          }
+          __syncwarp();
+        }
+        st_pending = true;
+      }
+    };
     for (int st = 0; st < nst; ++st) {
       float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f, hp3 = 0.f;           // head partial sums of this thread's columns
+      uint8_t* const arec = EMIT ? sv.act + (size_t)((blockIdx.x * sv.nst_plan + st) * 2 + X) * sv.rec_act : nullptr;
+      uint8_t* const mrec = EMIT ? sv.mask + (size_t)((blockIdx.x * sv.nst_plan + st) * 2 + X) * sv.rec_mask : nullptr;
       const int lr = st * TC_ST + X * TC_TILE + r;                // row index inside this CTA's range
       const bool valid = lr < nrows;
       const int rl = (valid ? lr : nrows - 1) / p.S;              // local ray
@@ -289,13 +332,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       if (n_ray > p.N - 1) n_ray = p.N - 1;                       // (padding CTA of an odd pair / empty range)
       if (n_ray < 0) n_ray = 0;
       for (int l = 0; l < NL; ++l) {
-        const bool tr = p.trace && blockIdx.x == 0 && st == 1 && e == 0 && lane == 0;
+        const bool tr = kTrace2 && p.trace && blockIdx.x == 0 && st == 1 && e == 0 && lane == 0;
         long long* trp = p.trace + 2048 + 4 * (X * 16 + l);
         if (tr) trp[0] = clock64();
         ptx::mbar_wait(bar_dfull + 8 * X, dph);
         dph ^= 1;
         ptx::tc_fence_after();
         if (tr) trp[1] = clock64();
+        emit_wait_prev();
         if (l <= D) {
           // pts layer (ReLU) or feature layer (no activation): 128 columns per warp in 4 batches,
           // the TMEM load of batch b+1 in flight while batch b is converted and stored
@@ -303,6 +347,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           const bool write_act = !(last_pts && !p.use_viewdirs);
           const int colw = ch * 128;
           uint32_t va[32], vb[32];
+          uint32_t mk[4] = {0u, 0u, 0u, 0u};                       // EMIT: sign bits of this thread's 128 pre-activations
           ptx::tmem_ld_x32(t_lane + colw, va);
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
@@ -313,6 +358,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
             if (b < 3) ptx::tmem_ld_x32(t_lane + col0 + 32, vn);
             float x[32];
             as_float32(v, x);
+            if (EMIT && l < D) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mk[b] = mask_push(mk[b], x[j]);
+            }
             if (last_pts) {
               if (p.use_viewdirs) {                               // alpha_linear (run_nerf_helpers.py:106)
 #pragma unroll
@@ -353,10 +402,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           }
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
-          const long long t_f = (p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) ? clock64() : 0;
+          const long long t_f = (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) ? clock64() : 0;
           arrive_leader(bar_act + 8 * X);
+          if (EMIT) {
+            if (l < D) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+            emit_store(arec + rec_act_h(l), act_base, 65536u);     // h_l (l < D) or feat (l == D)
+          }
           if (tr) trp[2] = clock64();
-          if (p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) { p.trace[2500 + blockIdx.x * 32 + (warp - 4) * 2] = t_f; p.trace[2501 + blockIdx.x * 32 + (warp - 4) * 2] = clock64(); }
+          if (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) { p.trace[2500 + blockIdx.x * 32 + (warp - 4) * 2] = t_f; p.trace[2501 + blockIdx.x * 32 + (warp - 4) * 2] = clock64(); }
         } else {
           // views_linears[0] (N=128): 64 columns per warp; + per-ray view bias, ReLU, rgb_linear
           const float* vbrow = p.vb + n_ray * 128;
@@ -368,22 +421,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           arrive_leader(bar_act + 8 * X);                      // accumulator drained: next super-tile may start
+          uint32_t mkv[2] = {0u, 0u};                             // EMIT: sign bits of this thread's 64 pre-activations
+          // EMIT: post-ReLU fp16 copy of this thread's 64 columns into K-block (2 + ch) of the (dead) A tile
+          const uint32_t hvoff = ch ? 16384u : 32768u;            // relative to swk[] (which points at K-block 2 * ch)
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             const int col0 = ch * 64 + b * 32;
             const uint32_t (&v)[32] = b ? vb : va;
             const float4* vb4 = reinterpret_cast<const float4*>(vbrow + col0);
             const uint32_t w0 = a_heads + (uint32_t)(256 + col0) * 4u;
+            uint32_t hh[4];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 bb = vb4[j];
-              const float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
-              const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
+              const float a0 = __uint_as_float(v[4 * j + 0]) + bb.x, a1 = __uint_as_float(v[4 * j + 1]) + bb.y;
+              const float a2 = __uint_as_float(v[4 * j + 2]) + bb.z, a3 = __uint_as_float(v[4 * j + 3]) + bb.w;
+              const float h0 = fmaxf(a0, 0.f), h1 = fmaxf(a1, 0.f), h2 = fmaxf(a2, 0.f), h3 = fmaxf(a3, 0.f);
+              if (EMIT) {
+                mkv[b] = mask_push(mask_push(mask_push(mask_push(mkv[b], a0), a1), a2), a3);
+                hh[(j & 1) * 2] = ptx::cvt_f16x2(h0, h1); hh[(j & 1) * 2 + 1] = ptx::cvt_f16x2(h2, h3);
+                if (j & 1) ptx::st_shared_v4(swk[b * 4 + (j >> 1)] + hvoff, hh[0], hh[1], hh[2], hh[3]);
+              }
               const float4 wr = lds128(w0 + 16 * j), wg = lds128(w0 + 512 + 16 * j), wb = lds128(w0 + 1024 + 16 * j);
               hp0 = fmaf(h0, wr.x, hp0); hp0 = fmaf(h1, wr.y, hp0); hp0 = fmaf(h2, wr.z, hp0); hp0 = fmaf(h3, wr.w, hp0);
               hp1 = fmaf(h0, wg.x, hp1); hp1 = fmaf(h1, wg.y, hp1); hp1 = fmaf(h2, wg.z, hp1); hp1 = fmaf(h3, wg.w, hp1);
               hp2 = fmaf(h0, wb.x, hp2); hp2 = fmaf(h1, wb.y, hp2); hp2 = fmaf(h2, wb.z, hp2); hp2 = fmaf(h3, wb.w, hp2);
             }
+          }
+          if (EMIT) {
+            *reinterpret_cast<uint2*>(mrec + (uint32_t)D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u) = make_uint2(mkv[0], mkv[1]);
+            ptx::fence_proxy_async_smem();
+            emit_store(arec + rec_act_hv(D), act_base + 32768u, 32768u);
           }
         }
         if (l == defer_l && st > 0 && ch == 0) composite_st(st - 1);
@@ -405,14 +473,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       }
     }
     if (ch == 0 && nst > 0) composite_st(nst - 1);                 // the last super-tile's rows
+    if (EMIT && e == 0 && lane == 0) ptx::bulk_wait_all();         // this thread's bulk stores (shared memory must outlive them)
   } else {
     // =========================== sampler (warp 3) ===========================
     const int t = threadIdx.x - 96;                               // 0..31
     for (int st = 0; st < nst; ++st) {
-      const bool trs = p.trace && blockIdx.x == 0 && t == 0 && st < 48;
+      const bool trs = kTrace2 && p.trace && blockIdx.x == 0 && t == 0 && st < 48;
       if (trs) p.trace[2300 + 2 * st] = clock64();
       ptx::mbar_wait(bar_encfree, (st & 1) ^ 1);
       if (trs) p.trace[2301 + 2 * st] = clock64();
+      if (EMIT) { if (t == 0) ptx::bulk_wait_read0(); __syncwarp(); }   // the previous super-tile's encodings have been copied out
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
         const int X = i >> 2, tr_ = t + 32 * (i & 3);             // tile slot, tile row
@@ -433,8 +503,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       }
       ptx::fence_proxy_async_smem();
       arrive_leader(bar_encfull);
+      if (EMIT && t == 0) {                                         // encodings of both slots -> their tile records
+        for (int X = 0; X < 2; ++X)
+          ptx::bulk_s2g(sv.act + (size_t)((blockIdx.x * sv.nst_plan + st) * 2 + X) * sv.rec_act, sb + SM_ENC + X * 16384, 16384u);
+        ptx::bulk_commit();
+      }
       if (trs) p.trace[2400 + st] = clock64();
     }
+    if (EMIT && t == 0) ptx::bulk_wait_all();
   }
 
 
