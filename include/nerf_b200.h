@@ -157,61 +157,76 @@ int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg*
                               float* z_fine, float* z_std, const NerfPassOut* fine,
                               void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- backward of one network pass (recompute): dL/dtheta accumulated into fp32 grads laid out
- *      like the reference parameters (see NerfNetGrads); g_rgb [N,3] = dL/drgb_map ---------------- */
+/* ---- training mode of the fused pass: besides its outputs (out->raw is required) the pass leaves, per 128-row
+ *      tile, a record of fp16 activation images (encodings, post-ReLU h_l, feature, view layer) and the sign
+ *      bits of the pre-activations (csrc/train_common.cuh) -- what the reference's autograd saves
+ *      (run_nerf_helpers.py:96-119), but written once, in the MMA operand layout, by cp.async.bulk from the
+ *      shared-memory tiles the forward produces anyway.  use_viewdirs networks, tensor-core precision. ---- */
+typedef struct NerfTrainSave {
+  void*  act;   size_t act_bytes;    /* activation records: nerf_b200_train_record_bytes(...)            */
+  void*  mask;  size_t mask_bytes;   /* ReLU sign-bit records                                            */
+} NerfTrainSave;
+int nerf_b200_train_record_bytes(int64_t N, int S, const NerfNetParams* net, size_t* act_bytes, size_t* mask_bytes);
+int nerf_b200_march_train(const float* rays, const float* z_vals, const float* noise, int64_t N, int S,
+                          const NerfNetParams* net, const void* packed, const NerfRenderCfg* cfg,
+                          const NerfPassOut* out, void* workspace, size_t workspace_bytes,
+                          const NerfTrainSave* save, void* stream);
+/* nerf_b200_render_rays_fwd with both passes in training mode (the render call of run_nerf.py:760-762,
+ * retraw=True): coarse->raw and fine->raw are required. */
+int nerf_b200_render_rays_fwd_train(const float* rays, int64_t N, const NerfRenderCfg* cfg,
+                                    const NerfNetParams* net_coarse, const void* packed_coarse,
+                                    const NerfNetParams* net_fine, const void* packed_fine,
+                                    const float* t_vals, const float* u_det,
+                                    const float* t_rand, const float* u_rand,
+                                    const float* noise0, const float* noise1,
+                                    float* z_coarse, const NerfPassOut* coarse,
+                                    float* z_fine, float* z_std, const NerfPassOut* fine,
+                                    void* workspace, size_t workspace_bytes,
+                                    const NerfTrainSave* save_coarse, const NerfTrainSave* save_fine, void* stream);
+
+/* ---- backward of one network pass: what loss.backward() (run_nerf.py:775) does through
+ *      run_nerf.py:381-386 / :397-403.  dL/dtheta is ACCUMULATED (+=) into fp32 grads laid out like the
+ *      reference parameters; g_rgb [N,3] = dL/drgb_map (the only output the reference's loss reads,
+ *      run_nerf.py:765-772); no gradient flows to rays or z (run_nerf.py:394). ---------------------------- */
 typedef struct NerfNetGrads {
   float* pts_w[NERF_B200_MAX_D]; float* pts_b[NERF_B200_MAX_D];
   float* feature_w; float* feature_b; float* alpha_w; float* alpha_b;
   float* views_w;   float* views_b;   float* rgb_w;   float* rgb_b;
   float* output_w;  float* output_b;
 } NerfNetGrads;
+/* tensor-core backward (csrc/bwd_tc2.cuh): compositing adjoint, tcgen05 dgrad chain with loss-scaled fp16
+ * activation gradients, layer-major tcgen05 weight gradient; consumes the records of the training-mode pass
+ * and its raw [N,S,4]. */
+int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* noise, int64_t N, int S,
+                           const NerfNetParams* net, const void* packed, const NerfRenderCfg* cfg,
+                           const float* raw, const NerfTrainSave* save, const float* g_rgb,
+                           const NerfNetGrads* grads, void* workspace, size_t workspace_bytes, void* stream);
+size_t nerf_b200_march_bwd_tc_workspace_bytes(int64_t N, int S, const NerfNetParams* net);
+/* introspection (tests / tools): offsets of the intermediates inside the 1 KB-aligned workspace and the tile plan:
+ * out[12] = off_d_raw, off_grad_records, rec_act_bytes, rec_mask_bytes, rec_grad_bytes, grid, rays_per_cta, nst,
+ * n_tiles, off_amax, off_dsum, off_partial */
+int nerf_b200_march_bwd_tc_layout(int64_t N, int S, const NerfNetParams* net, int64_t* out);
+/* exact mode (csrc/bwd_simt.cuh): fp32 recompute with saved activations + fp32 CUDA-core GEMMs; any network
+ * the exact forward supports (with or without view directions). */
 int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noise, int64_t N, int S,
                         const NerfNetParams* net, const void* packed, const NerfRenderCfg* cfg,
                         const float* g_rgb, const NerfNetGrads* grads, void* workspace,
                         size_t workspace_bytes, void* stream);
-size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S);
+size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S, const NerfNetParams* net);
 
-/* ---- tcgen05 self-test: out[128,N] = fp16(A[128,K]) * fp16(W[N,K])^T with fp32 accumulation, through
- *      the same operand layouts / descriptors / TMEM loads as nerf_b200_march (K % 32 == 0, K <= 256,
- *      N in {128,256}); scratch >= N*K*2 bytes. ---------------------------------------------------- */
-int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch,
-                            size_t scratch_bytes, void* stream);
-
-/* ---- tcgen05 "TN" self-test (groundwork for the tensor-core weight-gradient GEMM, no reference counterpart):
- *      out[256,256] = fp16(X[128,256])^T * fp16(Y[128,256]) with fp32 accumulation; both operands are read as
- *      MN-major SWIZZLE_128B tiles straight from the forward's activation layout (lbo = 16384, sbo = 1024). -- */
-int nerf_b200_selftest_gemm_tn(const float* X, const float* Y, float* out, int lbo_bytes, int sbo_bytes, void* stream);
-
-/* ---- EXPERIMENTAL (round-2 groundwork, no reference counterpart, not used by any entry point above): building
- *      blocks of the tensor-core backward over "tile images" -- [128 x C] fp16 tiles (C in {64,128,256}) stored in
- *      global memory byte-for-byte in the shared-memory activation layout (csrc/bwd_tc.cuh).  A [M x C] matrix takes
- *      ceil(M/128) * C * 256 bytes.
- *        tile_pack   : fp32 row-major [M,C] * scale -> images          tile_unpack: images * scale -> fp32 [M,C]
- *        tile_colsum : colsum[c] += scale * sum_rows X[r][c]           (bias gradients)
- *        wgrad_tiles : dW[Mc,Nc] (ld = ldw, fp32, atomically accumulated) += scale * sum_tiles X_t^T Y_t
- *        dgrad_tiles : OUT_t[128,256] = relu_mask(H_t)( X_t[128,Kc] * W[Kc,256] ), W and OUT as images, H nullable ---- */
-int nerf_b200_exp_tile_pack(const float* src, int64_t M, int C, float scale, void* img, void* stream);
-int nerf_b200_exp_tile_unpack(const void* img, int64_t M, int C, float scale, float* dst, void* stream);
-int nerf_b200_exp_tile_colsum(const void* img, int64_t n_tiles, int C, float scale, float* colsum, void* stream);
-int nerf_b200_exp_wgrad_tiles(const void* ximg, const void* yimg, int64_t n_tiles, int Mc, int Nc, float scale, float* dW, int ldw, void* stream);
-int nerf_b200_exp_dgrad_tiles(const void* ximg, const void* wimg, const void* himg, int64_t n_tiles, int Kc, void* oimg, void* stream);
-
-/* ---- debug hooks (not part of the drop-in surface): clock64 trace of CTA 0 / super-tile 1 of the next
- *      march launches into a device buffer of 4096 int64 (NULL disables); tcgen05.mma issue-rate probe */
+/* ---- debug hook (NERF_B200_TRACE builds only; a no-op otherwise): clock64 trace of CTA 0 into a device
+ *      buffer of 4096 int64 (NULL disables) ---------------------------------------------------------------- */
 int nerf_b200_debug_set_trace(void* dev_buf_4096_i64);
-int nerf_b200_debug_mma_rate(int reps, int N, int b_sw64, void* out_2_i64, void* stream);
-int nerf_b200_debug_ldtm_rate(int reps, int shape, int nwarps, int mma, void* out_2_i64, void* stream);
-int nerf_b200_debug_issue_probe(int reps, int nmma, int flags, void* out_2_i64, void* stream);
-int nerf_b200_debug_l2_stream(const void* buf, int buf_bytes, int chunk, int stages, int passes, int nblocks, void* out_i64, void* stream);
-int nerf_b200_debug_epi_rate(int reps, int mode, int mma, void* out_2_i64, void* stream);
 
-/* ---- device-time accounting of the dominant kernel (march_tc_kernel) for bench.py's roofline:
+/* ---- device-time accounting of the dominant kernels (march_tc2 / dgrad_tc2 / wgrad_tc) for bench.py's roofline:
  *      when enabled, every launch is bracketed by CUDA events on its own stream; read() synchronises
  *      those events, returns the summed kernel time [ms], the launch count and the algorithmic
  *      FLOPs those launches performed (2 x MACs of the reference layers x rows), and
  *      resets the accumulators. ------------------------------------------------------------------- */
 int nerf_b200_timing_enable(int on);
 int nerf_b200_timing_read(double* kernel_ms, int64_t* launches, double* algorithmic_flops);
+/* same, also split by kind: kind_ms[0] forward passes, [1] dgrad chains, [2] weight-gradient kernels */
+int nerf_b200_timing_read_kinds(double* kernel_ms, int64_t* launches, double* algorithmic_flops, double* kind_ms);
 
 /* ---- number of kernels launched by this library since load (bench.py's gpu_launches) ---------- */
 int64_t nerf_b200_launch_count(void);

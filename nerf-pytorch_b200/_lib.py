@@ -48,6 +48,10 @@ class NerfPassOut(C.Structure):
                 ("weights", c_fp), ("raw", c_fp)]
 
 
+class NerfTrainSave(C.Structure):
+    _fields_ = [("act", c_fp), ("act_bytes", C.c_size_t), ("mask", c_fp), ("mask_bytes", C.c_size_t)]
+
+
 # name -> (restype, argtypes); mirrors include/nerf_b200.h one to one
 SIGNATURES = {
     "nerf_b200_abi_version": (C.c_int, []),
@@ -74,12 +78,32 @@ SIGNATURES = {
                                             c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                             c_fp, C.POINTER(NerfPassOut), c_fp, c_fp, C.POINTER(NerfPassOut),
                                             c_fp, C.c_size_t, c_fp]),
+    "nerf_b200_march_train": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, C.POINTER(NerfNetParams), c_fp,
+                                        C.POINTER(NerfRenderCfg), C.POINTER(NerfPassOut), c_fp, C.c_size_t,
+                                        C.POINTER(NerfTrainSave), c_fp]),
+    "nerf_b200_train_record_bytes": (C.c_int, [C.c_int64, C.c_int, C.POINTER(NerfNetParams), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "nerf_b200_render_rays_fwd_train": (C.c_int, [c_fp, C.c_int64, C.POINTER(NerfRenderCfg),
+                                                  C.POINTER(NerfNetParams), c_fp, C.POINTER(NerfNetParams), c_fp,
+                                                  c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                                  c_fp, C.POINTER(NerfPassOut), c_fp, c_fp, C.POINTER(NerfPassOut),
+                                                  c_fp, C.c_size_t, C.POINTER(NerfTrainSave), C.POINTER(NerfTrainSave), c_fp]),
+    "nerf_b200_march_bwd_tc": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, C.POINTER(NerfNetParams), c_fp,
+                                         C.POINTER(NerfRenderCfg), c_fp, C.POINTER(NerfTrainSave), c_fp,
+                                         C.POINTER(NerfNetGrads), c_fp, C.c_size_t, c_fp]),
+    "nerf_b200_march_bwd_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.POINTER(NerfNetParams)]),
+    "nerf_b200_march_bwd_tc_layout": (C.c_int, [C.c_int64, C.c_int, C.POINTER(NerfNetParams), C.POINTER(C.c_int64)]),
     "nerf_b200_march_bwd": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, C.POINTER(NerfNetParams), c_fp,
                                       C.POINTER(NerfRenderCfg), c_fp, C.POINTER(NerfNetGrads), c_fp, C.c_size_t, c_fp]),
-    "nerf_b200_march_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "nerf_b200_march_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.POINTER(NerfNetParams)]),
     "nerf_b200_timing_enable": (C.c_int, [C.c_int]),
     "nerf_b200_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "nerf_b200_timing_read_kinds": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nerf_b200_debug_set_trace": (C.c_int, [c_fp]),
+}
+
+# bring-up self-tests and micro-benchmarks: libnerf_b200_dev.so (include/nerf_b200_dev.h), never used by the product path
+DEV_SIGNATURES = {
+    "nerf_b200_dev_last_error": (C.c_char_p, []),
     "nerf_b200_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_debug_epi_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_debug_ldtm_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
@@ -87,14 +111,11 @@ SIGNATURES = {
     "nerf_b200_debug_l2_stream": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_selftest_gemm": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, C.c_size_t, c_fp]),
     "nerf_b200_selftest_gemm_tn": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp]),
-    "nerf_b200_exp_tile_pack": (C.c_int, [c_fp, C.c_int64, C.c_int, C.c_float, c_fp, c_fp]),
-    "nerf_b200_exp_tile_unpack": (C.c_int, [c_fp, C.c_int64, C.c_int, C.c_float, c_fp, c_fp]),
-    "nerf_b200_exp_tile_colsum": (C.c_int, [c_fp, C.c_int64, C.c_int, C.c_float, c_fp, c_fp]),
-    "nerf_b200_exp_wgrad_tiles": (C.c_int, [c_fp, c_fp, C.c_int64, C.c_int, C.c_int, C.c_float, c_fp, C.c_int, c_fp]),
-    "nerf_b200_exp_dgrad_tiles": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, c_fp, c_fp]),
 }
 
 _lib = None
+_dev = None
+DEV_LIB_PATH = os.path.join(_HERE, "libnerf_b200_dev.so")
 
 
 def load():
@@ -114,6 +135,27 @@ def load():
         raise RuntimeError("nerf_b200: ABI version mismatch between the Python host and libnerf_b200.so")
     _lib = lib
     return lib
+
+
+def load_dev():
+    """Load libnerf_b200_dev.so (self-tests / probes used by tests/ and tools/ only)."""
+    global _dev
+    if _dev is not None:
+        return _dev
+    if not os.path.isfile(DEV_LIB_PATH):
+        raise RuntimeError(f"nerf_b200: dev library not built ({DEV_LIB_PATH} missing); run __graft_entry__.build()")
+    lib = C.CDLL(DEV_LIB_PATH)
+    for name, (res, args) in DEV_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _dev = lib
+    return lib
+
+
+def check_dev(rc, what):
+    if rc != 0:
+        msg = load_dev().nerf_b200_dev_last_error()
+        raise RuntimeError(f"nerf_b200_dev.{what} failed ({rc}): {msg.decode() if msg else '?'}")
 
 
 def check(rc, what):

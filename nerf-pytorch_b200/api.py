@@ -14,6 +14,7 @@ ndc_rays :175-192, sample_pdf :196-239.
 from __future__ import annotations
 
 import ctypes as C
+import numbers
 import os
 
 import numpy as np
@@ -22,11 +23,13 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import NerfCamera, NerfNetGrads, NerfNetParams, NerfPassOut, NerfRenderCfg, PREC_FP32, PREC_TC_FP16, check
+from ._lib import (NerfCamera, NerfNetGrads, NerfNetParams, NerfPassOut, NerfRenderCfg, NerfTrainSave, PREC_FP32, PREC_TC_FP16,
+                   check)
 
 __all__ = ["NeRF", "Embedder", "get_embedder", "sample_pdf", "raw2outputs", "run_network", "batchify",
-           "batchify_rays", "render_rays", "render", "create_nerf", "get_rays", "get_rays_np", "ndc_rays",
-           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "launch_count", "DEBUG", "GraphedRender"]
+           "batchify_rays", "render_rays", "render", "create_nerf",
+           "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "set_backward", "get_backward",
+           "launch_count", "DEBUG", "GraphedRender"]
 
 DEBUG = False
 _PRECISION = {"mode": PREC_TC_FP16}
@@ -45,6 +48,18 @@ def get_precision() -> str:
     return "tc_fp16" if _PRECISION["mode"] == PREC_TC_FP16 else "fp32"
 
 
+def set_backward(mode: str):
+    """'tc' (default in tc_fp16 precision: tcgen05 backward from the forward's saved tile records) or 'exact'
+    (fp32 CUDA-core recompute backward; always used in fp32 precision and for networks without view directions)."""
+    if mode not in ("tc", "exact"):
+        raise ValueError(mode)
+    _PRECISION["backward"] = mode
+
+
+def get_backward() -> str:
+    return _PRECISION.get("backward", "tc")
+
+
 def launch_count() -> int:
     return _lib.launch_count()
 
@@ -55,6 +70,12 @@ def launch_count() -> int:
 
 def _stream(t: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _on(t: torch.Tensor):
+    """Make the tensor's device the current CUDA device for the duration of a library call: the C library launches
+    on the process's current device (per-device state lives in csrc/capi.cu: device_state())."""
+    return torch.cuda.device(t.device)
 
 
 def _ptr(t):
@@ -90,7 +111,8 @@ class Embedder:
         x = _f32c(inputs, "embed input")
         flat = x.reshape(-1, 3)
         out = torch.empty((flat.shape[0], self.out_dim), device=x.device, dtype=torch.float32)
-        check(_lib.load().nerf_b200_embed(_ptr(flat), flat.shape[0], self.num_freqs, _ptr(out), _stream(x)), "embed")
+        with _on(x):
+            check(_lib.load().nerf_b200_embed(_ptr(flat), flat.shape[0], self.num_freqs, _ptr(out), _stream(x)), "embed")
         return out.reshape(*x.shape[:-1], self.out_dim)
 
 
@@ -191,11 +213,18 @@ class NeRF(nn.Module):
             g.output_w, g.output_b = grads["output_linear.weight"].data_ptr(), grads["output_linear.bias"].data_ptr()
         return g
 
+    def invalidate_pack(self):
+        """Force the next packed() to re-pack.  Needed after writes that autograd's version counter does not see
+        (`p.data.copy_()`, `p.data.mul_()` -- e.g. EMA or clipping through `.data`); optimizer steps, `copy_` under
+        no_grad, load_state_dict and .to() are detected automatically."""
+        self._pack_epoch = getattr(self, "_pack_epoch", 0) + 1
+
     def packed(self):
-        """fp16 UMMA-swizzled weight stream, re-packed whenever a parameter changed in place
-        (optimizer.step bumps Parameter._version; load_state_dict / .to() change data_ptr)."""
+        """fp16 UMMA-swizzled weight streams (forward chunks + the transposed chunks of the backward), re-packed
+        whenever a parameter changed in place (optimizer.step bumps Parameter._version; load_state_dict / .to()
+        change data_ptr) or invalidate_pack() was called."""
         dev = self._check_device()
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (getattr(self, "_pack_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._pack is not None and self._pack[0] == key:
             return self._pack[1]
         lib = _lib.load()
@@ -205,57 +234,10 @@ class NeRF(nn.Module):
             raise RuntimeError("nerf_b200: " + lib.nerf_b200_last_error().decode())
         buf = self._pack[1] if (self._pack is not None and self._pack[1].numel() == nbytes and self._pack[1].device == dev) \
             else torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        check(lib.nerf_b200_pack_weights(C.byref(n), _ptr(buf), nbytes, _stream(buf)), "pack_weights")
+        with _on(buf):
+            check(lib.nerf_b200_pack_weights(C.byref(n), _ptr(buf), nbytes, _stream(buf)), "pack_weights")
         self._pack = (key, buf)
         return buf
-
-    def load_weights_from_keras(self, weights):
-        """run_nerf_helpers.py:121-148 (import of the original TF/Keras weight list)."""
-        assert self.use_viewdirs, "Not implemented if use_viewdirs=False"
-        dev = self.pts_linears[0].weight.device
-        t = lambda a: torch.from_numpy(np.transpose(a)).to(dev)
-        for i in range(self.D):
-            self.pts_linears[i].weight.data, self.pts_linears[i].bias.data = t(weights[2 * i]), t(weights[2 * i + 1])
-        j = 2 * self.D
-        self.feature_linear.weight.data, self.feature_linear.bias.data = t(weights[j]), t(weights[j + 1])
-        self.views_linears[0].weight.data, self.views_linears[0].bias.data = t(weights[j + 2]), t(weights[j + 3])
-        self.rgb_linear.weight.data, self.rgb_linear.bias.data = t(weights[j + 4]), t(weights[j + 5])
-        self.alpha_linear.weight.data, self.alpha_linear.bias.data = t(weights[j + 6]), t(weights[j + 7])
-
-
-# ------------------------------------------------------------------------------------------------
-# ray helpers (run_nerf_helpers.py:153-192) -- per-image glue, plain torch
-# ------------------------------------------------------------------------------------------------
-
-def get_rays(H, W, K, c2w):
-    c2w = torch.as_tensor(c2w, dtype=torch.float32)
-    dev = c2w.device
-    i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev), indexing="ij")
-    i, j = i.t(), j.t()
-    dirs = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)
-    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
-    rays_o = c2w[:3, -1].expand(rays_d.shape)
-    return rays_o, rays_d
-
-
-def get_rays_np(H, W, K, c2w):
-    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing="xy")
-    dirs = np.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -np.ones_like(i)], -1)
-    rays_d = np.sum(dirs[..., np.newaxis, :] * c2w[:3, :3], -1)
-    rays_o = np.broadcast_to(c2w[:3, -1], np.shape(rays_d))
-    return rays_o, rays_d
-
-
-def ndc_rays(H, W, focal, near, rays_o, rays_d):
-    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
-    rays_o = rays_o + t[..., None] * rays_d
-    o0 = -1. / (W / (2. * focal)) * rays_o[..., 0] / rays_o[..., 2]
-    o1 = -1. / (H / (2. * focal)) * rays_o[..., 1] / rays_o[..., 2]
-    o2 = 1. + 2. * near / rays_o[..., 2]
-    d0 = -1. / (W / (2. * focal)) * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
-    d1 = -1. / (H / (2. * focal)) * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
-    d2 = -2. * near / rays_o[..., 2]
-    return torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,8 +264,9 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
     b2, w2 = bins.reshape(-1, B), weights.reshape(-1, B - 1)
     u, stride = _draw_u((b2.shape[0], N_samples), det, pytest, bins.device)
     out = torch.empty((b2.shape[0], N_samples), device=bins.device, dtype=torch.float32)
-    check(_lib.load().nerf_b200_sample_pdf(_ptr(b2), _ptr(w2), _ptr(u), stride, b2.shape[0], B, N_samples,
-                                           _ptr(out), _stream(bins)), "sample_pdf")
+    with _on(bins):
+        check(_lib.load().nerf_b200_sample_pdf(_ptr(b2), _ptr(w2), _ptr(u), stride, b2.shape[0], B, N_samples,
+                                               _ptr(out), _stream(bins)), "sample_pdf")
     return out.reshape(*lead, N_samples)
 
 
@@ -309,8 +292,9 @@ class _Raw2Outputs(torch.autograd.Function):
         rgb = torch.empty((N, 3), device=dev); disp = torch.empty(N, device=dev); acc = torch.empty(N, device=dev)
         depth = torch.empty(N, device=dev); weights = torch.empty((N, S), device=dev)
         out = NerfPassOut(_ptr(rgb), _ptr(disp), _ptr(acc), _ptr(depth), _ptr(weights), C.c_void_p(0))
-        check(_lib.load().nerf_b200_raw2outputs(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S,
-                                                int(white_bkgd), C.byref(out), _stream(raw)), "raw2outputs")
+        with _on(raw):
+            check(_lib.load().nerf_b200_raw2outputs(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S,
+                                                    int(white_bkgd), C.byref(out), _stream(raw)), "raw2outputs")
         ctx.save_for_backward(raw, z_vals, rays_d, noise if noise is not None else torch.empty(0, device=dev))
         ctx.white_bkgd = bool(white_bkgd)
         ctx.mark_non_differentiable(disp, acc, weights, depth)
@@ -322,9 +306,10 @@ class _Raw2Outputs(torch.autograd.Function):
         noise = noise if noise.numel() else None
         N, S = z_vals.shape
         d_raw = torch.empty_like(raw)
-        check(_lib.load().nerf_b200_raw2outputs_bwd(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S,
-                                                    int(ctx.white_bkgd), _ptr(g_rgb.contiguous().float()), _ptr(d_raw),
-                                                    _stream(raw)), "raw2outputs_bwd")
+        g_rgb = g_rgb.contiguous().float()
+        with _on(raw):
+            check(_lib.load().nerf_b200_raw2outputs_bwd(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S,
+                                                        int(ctx.white_bkgd), _ptr(g_rgb), _ptr(d_raw), _stream(raw)), "raw2outputs_bwd")
         return d_raw, None, None, None, None
 
 
@@ -379,9 +364,10 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     raw = torch.empty((N * S, 4), device=inputs.device, dtype=torch.float32)
     ws_bytes = lib.nerf_b200_march_workspace_bytes(N, S)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=inputs.device)
-    check(lib.nerf_b200_run_network(_ptr(pts), _ptr(vd), N, S, C.byref(n), _ptr(packed), _freqs_of(embed_fn),
-                                    _freqs_of(embeddirs_fn), prec, _ptr(raw), _ptr(ws), ws_bytes, _stream(inputs)),
-          "run_network")
+    with _on(inputs):
+        check(lib.nerf_b200_run_network(_ptr(pts), _ptr(vd), N, S, C.byref(n), _ptr(packed), _freqs_of(embed_fn),
+                                        _freqs_of(embeddirs_fn), prec, _ptr(raw), _ptr(ws), ws_bytes, _stream(inputs)),
+              "run_network")
     return raw.reshape(*inputs.shape[:-1], 4)
 
 
@@ -418,10 +404,31 @@ def _linspace01(n, dev):
     return t
 
 
+def _cfg_struct(cfgd, ray_stride):
+    cfg = NerfRenderCfg()
+    cfg.N_samples, cfg.N_importance = cfgd["N_samples"], cfgd["N_importance"]
+    cfg.multires, cfg.multires_views = cfgd["multires"], cfgd["multires_views"]
+    cfg.lindisp, cfg.perturb, cfg.white_bkgd = int(cfgd["lindisp"]), int(cfgd["perturb"] > 0.), int(cfgd["white_bkgd"])
+    cfg.ray_stride, cfg.precision = ray_stride, _PRECISION["mode"]
+    return cfg
+
+
+def _train_save(lib, N, S, net_params, dev):
+    """Allocate the per-tile records of one training-mode pass (csrc/train_common.cuh) -> (NerfTrainSave, tensors)."""
+    ab, mb = C.c_size_t(0), C.c_size_t(0)
+    check(lib.nerf_b200_train_record_bytes(N, S, C.byref(net_params), C.byref(ab), C.byref(mb)), "train_record_bytes")
+    act = torch.empty(ab.value, dtype=torch.uint8, device=dev)
+    mask = torch.empty(mb.value, dtype=torch.uint8, device=dev)
+    sv = NerfTrainSave(_ptr(act), ab.value, _ptr(mask), mb.value)
+    return sv, act, mask
+
+
 class _RenderRays(torch.autograd.Function):
-    """Forward: nerf_b200_render_rays_fwd (coarse z -> fused pass -> resample -> fused pass).
-    Backward: nerf_b200_march_bwd per pass (fp32 recompute + GEMM backprop), gradients w.r.t. rgb_map and rgb0 only --
-    exactly the terms of the reference's loss (run_nerf.py:765-772); z_samples is detached in the
+    """Forward: nerf_b200_render_rays_fwd (coarse z -> fused pass -> resample -> fused pass); when a parameter needs a
+    gradient and the tensor-core backward is selected, the training-mode variant that also leaves the per-tile
+    activation records.  Backward: per pass nerf_b200_march_bwd_tc (tcgen05 dgrad chain + layer-major wgrad from
+    those records) or, in exact mode, nerf_b200_march_bwd (fp32 recompute + GEMM backprop).  Gradients w.r.t. rgb_map
+    and rgb0 only -- exactly the terms of the reference's loss (run_nerf.py:765-772); z_samples is detached in the
     reference (:394) so nothing flows through the resampling."""
 
     @staticmethod
@@ -431,11 +438,7 @@ class _RenderRays(torch.autograd.Function):
         N = ray_batch.shape[0]
         Sc, Ni = cfgd["N_samples"], cfgd["N_importance"]
         Sf = Sc + Ni
-        cfg = NerfRenderCfg()
-        cfg.N_samples, cfg.N_importance = Sc, Ni
-        cfg.multires, cfg.multires_views = cfgd["multires"], cfgd["multires_views"]
-        cfg.lindisp, cfg.perturb, cfg.white_bkgd = int(cfgd["lindisp"]), int(cfgd["perturb"] > 0.), int(cfgd["white_bkgd"])
-        cfg.ray_stride, cfg.precision = ray_batch.shape[1], _PRECISION["mode"]
+        cfg = _cfg_struct(cfgd, ray_batch.shape[1])
         tc = cfg.precision == PREC_TC_FP16
         pc, pf = net_c.net_params(), (net_f.net_params() if net_f is not None else None)
         pk_c = net_c.packed() if tc else None
@@ -446,27 +449,41 @@ class _RenderRays(torch.autograd.Function):
         z_c = torch.empty((N, Sc), **f32)
         o = {k: torch.empty(s, **f32) for k, s in (("rgb0", (N, 3)), ("disp0", (N,)), ("acc0", (N,)), ("w0", (N, Sc)))}
         retraw, fine = cfgd["retraw"], Ni > 0
-        raw_c = torch.empty((N, Sc, 4), **f32) if ((retraw and not fine) or not tc) else None
+        needs_grad = any(ctx.needs_input_grad[8:])
+        train_tc = bool(tc and needs_grad and get_backward() == "tc" and net_c.use_viewdirs and
+                        (net_f is None or net_f.use_viewdirs))
+        raw_c = torch.empty((N, Sc, 4), **f32) if ((retraw and not fine) or not tc or train_tc) else None
         out_c = NerfPassOut(_ptr(o["rgb0"]), _ptr(o["disp0"]), _ptr(o["acc0"]), C.c_void_p(0), _ptr(o["w0"]), _ptr(raw_c))
         z_f = z_std = raw_f = None
         out_f = None
         if fine:
             z_f, z_std = torch.empty((N, Sf), **f32), torch.empty((N,), **f32)
             o.update(rgb=torch.empty((N, 3), **f32), disp=torch.empty((N,), **f32), acc=torch.empty((N,), **f32))
-            raw_f = torch.empty((N, Sf, 4), **f32) if (retraw or not tc) else None
+            raw_f = torch.empty((N, Sf, 4), **f32) if (retraw or not tc or train_tc) else None
             out_f = NerfPassOut(_ptr(o["rgb"]), _ptr(o["disp"]), _ptr(o["acc"]), C.c_void_p(0), C.c_void_p(0), _ptr(raw_f))
         ws_bytes = lib.nerf_b200_march_workspace_bytes(N, Sf)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.nerf_b200_render_rays_fwd(
-            _ptr(ray_batch), N, C.byref(cfg), C.byref(pc), _ptr(pk_c), C.byref(pf) if pf is not None else None, _ptr(pk_f),
-            _ptr(t_vals), _ptr(u_det), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1),
-            _ptr(z_c), C.byref(out_c), _ptr(z_f), _ptr(z_std), C.byref(out_f) if out_f is not None else None,
-            _ptr(ws), ws_bytes, _stream(ray_batch)), "render_rays_fwd")
-        ctx.cfgd, ctx.nets = cfgd, (net_c, net_f)
+        common = (_ptr(ray_batch), N, C.byref(cfg), C.byref(pc), _ptr(pk_c), C.byref(pf) if pf is not None else None, _ptr(pk_f),
+                  _ptr(t_vals), _ptr(u_det), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1),
+                  _ptr(z_c), C.byref(out_c), _ptr(z_f), _ptr(z_std), C.byref(out_f) if out_f is not None else None,
+                  _ptr(ws), ws_bytes)
+        saved_rec = ()
+        with _on(ray_batch):
+            if train_tc:
+                sv_c, act_c, mask_c = _train_save(lib, N, Sc, pc, dev)
+                saved_rec = (raw_c, act_c, mask_c)
+                sv_f = None
+                if fine:
+                    sv_f, act_f, mask_f = _train_save(lib, N, Sf, pf if pf is not None else pc, dev)
+                    saved_rec += (raw_f, act_f, mask_f)
+                check(lib.nerf_b200_render_rays_fwd_train(*common, C.byref(sv_c), C.byref(sv_f) if sv_f is not None else None,
+                                                          _stream(ray_batch)), "render_rays_fwd_train")
+            else:
+                check(lib.nerf_b200_render_rays_fwd(*common, _stream(ray_batch)), "render_rays_fwd")
+        ctx.cfgd, ctx.nets, ctx.train_tc = cfgd, (net_c, net_f), train_tc
         ctx.save_for_backward(ray_batch, z_c, z_f if fine else torch.empty(0, device=dev),
                               noise0 if noise0 is not None else torch.empty(0, device=dev),
-                              noise1 if noise1 is not None else torch.empty(0, device=dev))
-        ctx.n_params_c = len(list(net_c.parameters()))
+                              noise1 if noise1 is not None else torch.empty(0, device=dev), *saved_rec)
         if fine:
             rets = (o["rgb"], o["disp"], o["acc"], o["rgb0"], o["disp0"], o["acc0"], z_std,
                     raw_f if retraw else torch.empty(0, device=dev))
@@ -479,34 +496,42 @@ class _RenderRays(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *g):
         lib = _lib.load()
-        ray_batch, z_c, z_f, noise0, noise1 = ctx.saved_tensors
+        ray_batch, z_c, z_f, noise0, noise1 = ctx.saved_tensors[:5]
+        rec = ctx.saved_tensors[5:]
         cfgd = ctx.cfgd
         net_c, net_f = ctx.nets
         fine = cfgd["N_importance"] > 0
         N = ray_batch.shape[0]
-        cfg = NerfRenderCfg()
-        cfg.N_samples, cfg.N_importance = cfgd["N_samples"], cfgd["N_importance"]
-        cfg.multires, cfg.multires_views = cfgd["multires"], cfgd["multires_views"]
-        cfg.lindisp, cfg.perturb, cfg.white_bkgd = int(cfgd["lindisp"]), int(cfgd["perturb"] > 0.), int(cfgd["white_bkgd"])
-        cfg.ray_stride, cfg.precision = ray_batch.shape[1], _PRECISION["mode"]
+        cfg = _cfg_struct(cfgd, ray_batch.shape[1])
         g_fine, g_coarse = (g[0], g[3]) if fine else (None, g[0])
         grads_c = _grad_buffers(net_c)
         same_net = fine and (net_f is None)
         grads_f = grads_c if same_net else (_grad_buffers(net_f) if fine else None)
-        passes = [(g_coarse, z_c, noise0, net_c, grads_c)]
+        passes = [(g_coarse, z_c, noise0, net_c, grads_c, rec[0:3])]
         if fine:
-            passes.append((g_fine, z_f, noise1, net_c if same_net else net_f, grads_f))
-        for g_rgb, z, noise, net, gbuf in passes:
-            if g_rgb is None:
-                continue
-            S = z.shape[1]
-            n = net.net_params()
-            gs = net.grad_struct(gbuf)
-            ws_bytes = lib.nerf_b200_march_bwd_workspace_bytes(N, S)
-            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=z.device)
-            check(lib.nerf_b200_march_bwd(_ptr(ray_batch), _ptr(z), _ptr(noise if noise.numel() else None), N, S,
-                                          C.byref(n), _ptr(None), C.byref(cfg), _ptr(g_rgb.contiguous().float()),
-                                          C.byref(gs), _ptr(ws), ws_bytes, _stream(z)), "march_bwd")
+            passes.append((g_fine, z_f, noise1, net_c if same_net else net_f, grads_f, rec[3:6]))
+        with _on(ray_batch):
+            for g_rgb, z, noise, net, gbuf, rc in passes:
+                if g_rgb is None:
+                    continue
+                S = z.shape[1]
+                n = net.net_params()
+                gs = net.grad_struct(gbuf)
+                g_rgb = g_rgb.contiguous().float()
+                nz = _ptr(noise if noise.numel() else None)
+                if ctx.train_tc:
+                    raw, act, mask = rc
+                    sv = NerfTrainSave(_ptr(act), act.numel(), _ptr(mask), mask.numel())
+                    ws_bytes = lib.nerf_b200_march_bwd_tc_workspace_bytes(N, S, C.byref(n))
+                    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=z.device)
+                    check(lib.nerf_b200_march_bwd_tc(_ptr(ray_batch), _ptr(z), nz, N, S, C.byref(n), _ptr(net.packed()), C.byref(cfg),
+                                                     _ptr(raw), C.byref(sv), _ptr(g_rgb), C.byref(gs), _ptr(ws), ws_bytes, _stream(z)),
+                          "march_bwd_tc")
+                else:
+                    ws_bytes = lib.nerf_b200_march_bwd_workspace_bytes(N, S, C.byref(n))
+                    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=z.device)
+                    check(lib.nerf_b200_march_bwd(_ptr(ray_batch), _ptr(z), nz, N, S, C.byref(n), _ptr(None), C.byref(cfg),
+                                                  _ptr(g_rgb), C.byref(gs), _ptr(ws), ws_bytes, _stream(z)), "march_bwd")
         out = [None] * 8
         out += [grads_c[k] for k, _ in net_c.named_parameters()]
         if net_f is not None:
@@ -555,9 +580,9 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     noise1 = _draw_noise((N, N_samples + N_importance), float(raw_noise_std), pytest, dev) if N_importance > 0 else None
     cfgd = dict(N_samples=int(N_samples), N_importance=int(N_importance), multires=int(mr), multires_views=int(mrv),
                 lindisp=bool(lindisp), perturb=float(perturb), white_bkgd=bool(white_bkgd), retraw=bool(retraw))
-    params = list(network_fn.parameters()) + (list(network_fine.parameters()) if network_fine is not None else [])
-    outs = _RenderRays.apply(ray_batch, cfgd, network_fn, network_fine if N_importance > 0 else None,
-                             t_rand, u_rand, noise0, noise1, *params)
+    net_f = network_fine if N_importance > 0 else None          # the reference ignores network_fine without fine samples
+    params = list(network_fn.parameters()) + (list(net_f.parameters()) if net_f is not None else [])
+    outs = _RenderRays.apply(ray_batch, cfgd, network_fn, net_f, t_rand, u_rand, noise0, noise1, *params)
     if N_importance > 0:
         rgb, disp, acc, rgb0, disp0, acc0, z_std, raw = outs
         ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}
@@ -602,54 +627,60 @@ def _render_device(kwargs):
     return net._check_device() if isinstance(net, NeRF) else torch.device("cuda")
 
 
+def _is_scalar(x):
+    """Python / numpy scalar (np.float32 near/far of the LLFF and deepvoxels loaders included), not a tensor."""
+    return not torch.is_tensor(x) and np.ndim(x) == 0 and isinstance(x, (numbers.Real, np.generic))
+
+
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
     """run_nerf.py:69-134: build the [N, 8|11] ray batch, render in `chunk`-ray slices, reshape.
 
-    The batch construction (get_rays for `c2w`, view-direction normalisation, NDC warp, packing) is one
-    kernel (nerf_b200_pack_rays); the torch-op path below is kept only for the two cases the kernel
-    does not cover: per-ray near/far arrays and the `c2w_staticcam` visualisation mode."""
-    scalar_bounds = isinstance(near, (int, float)) and isinstance(far, (int, float))
-    if scalar_bounds and c2w_staticcam is None:
-        lib = _lib.load()
-        if c2w is not None:
-            dev = _render_device(kwargs)
-            N, sh = int(H) * int(W), [int(H), int(W), 3]
-            cam = _camera(H, W, K, c2w)
-            o_ptr = d_ptr = None
-            keep = None
-        else:
-            rays_o, rays_d = rays
-            sh = list(rays_d.shape)
-            keep = (_f32c(rays_o, "rays_o").reshape(-1, 3), _f32c(rays_d, "rays_d").reshape(-1, 3))
-            dev, N = keep[0].device, keep[0].shape[0]
-            cam = _camera(H, W, K)
-            o_ptr, d_ptr = keep
-        packed = torch.empty((N, 11 if use_viewdirs else 8), device=dev, dtype=torch.float32)
-        check(lib.nerf_b200_pack_rays(_ptr(o_ptr), _ptr(d_ptr), None, C.byref(cam), N, 0, int(bool(ndc)), float(near), float(far),
-                                      int(bool(use_viewdirs)), _ptr(packed), _stream(packed)), "pack_rays")
-        rays = packed
+    The batch construction -- get_rays for `c2w` (run_nerf_helpers.py:153-162), view-direction normalisation (:108),
+    NDC warp (run_nerf_helpers.py:175-192), near/far and packing (:117-123) -- is one kernel (nerf_b200_pack_rays) in
+    every mode, `c2w_staticcam` (rays from one camera, view directions from another, :104-107) included; per-ray
+    near/far arrays are written into their two columns afterwards."""
+    lib = _lib.load()
+    ndc = int(bool(ndc))
+    if c2w is not None:
+        dev = _render_device(kwargs)
+        N, sh = int(H) * int(W), [int(H), int(W), 3]
+        given = None
     else:
-        if c2w is not None:
-            rays_o, rays_d = get_rays(H, W, K, c2w)
-        else:
-            rays_o, rays_d = rays
-        if use_viewdirs:
-            viewdirs = rays_d
-            if c2w_staticcam is not None:
-                rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
-            viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
-            viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        rays_o, rays_d = rays
         sh = list(rays_d.shape)
-        if ndc:
-            rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
-        rays_o = torch.reshape(rays_o, [-1, 3]).float()
-        rays_d = torch.reshape(rays_d, [-1, 3]).float()
-        near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
-        rays = torch.cat([rays_o, rays_d, near, far], -1)
-        if use_viewdirs:
-            rays = torch.cat([rays, viewdirs], -1)
-    all_ret = batchify_rays(rays, chunk, **kwargs)
+        given = (_f32c(rays_o, "rays_o").reshape(-1, 3), _f32c(rays_d, "rays_d").reshape(-1, 3))
+        dev, N = given[0].device, given[0].shape[0]
+    scalar_bounds = _is_scalar(near) and _is_scalar(far)
+    nf = (float(near), float(far)) if scalar_bounds else (0., 1.)
+    packed = torch.empty((N, 11 if use_viewdirs else 8), device=dev, dtype=torch.float32)
+
+    def pack(o, d, view_src, cam, out, ndc_, viewdirs_):
+        check(lib.nerf_b200_pack_rays(_ptr(o), _ptr(d), _ptr(view_src), C.byref(cam), N, 0, ndc_, nf[0], nf[1], int(bool(viewdirs_)),
+                                      _ptr(out), _stream(out)), "pack_rays")
+
+    with _on(packed):
+        view_src = None
+        if c2w_staticcam is not None:
+            # view directions come from the `c2w` / given rays, the rays themselves from the static camera (:104-107)
+            if use_viewdirs:
+                if given is not None:
+                    view_src = given[1]
+                else:
+                    tmp = torch.empty((N, 8), device=dev, dtype=torch.float32)
+                    pack(None, None, None, _camera(H, W, K, c2w), tmp, 0, False)
+                    view_src = tmp[:, 3:6].contiguous()
+            pack(None, None, view_src, _camera(H, W, K, c2w_staticcam), packed, ndc, use_viewdirs)
+        elif given is None:
+            pack(None, None, None, _camera(H, W, K, c2w), packed, ndc, use_viewdirs)
+        else:
+            pack(given[0], given[1], None, _camera(H, W, K), packed, ndc, use_viewdirs)
+    if not scalar_bounds:                                                          # :117-118 with array bounds
+        shape_col = lambda x: torch.as_tensor(x, dtype=torch.float32, device=dev).expand(N) if np.ndim(x) == 0 or (torch.is_tensor(x) and x.dim() == 0) \
+            else torch.as_tensor(x, dtype=torch.float32, device=dev).reshape(N)
+        packed[:, 6] = shape_col(near)
+        packed[:, 7] = shape_col(far)
+    all_ret = batchify_rays(packed, chunk, **kwargs)
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
     k_extract = ["rgb_map", "disp_map", "acc_map"]
@@ -735,7 +766,7 @@ class GraphedRender:
         self.n_rays = int(n_rays)
         self.rays = torch.zeros((2, self.n_rays, 3), device=dev, dtype=torch.float32)
         self.rays[1, :, 2] = -1.0                                       # any non-degenerate direction for the warm-up
-        self.host_out = torch.empty((self.n_rays, 5), dtype=torch.float32).pin_memory()
+        self.host_out = torch.empty((self.n_rays, 5), dtype=torch.float32, device="cpu").pin_memory()
         call = lambda: render(H, W, K, rays=self.rays, **render_kwargs)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

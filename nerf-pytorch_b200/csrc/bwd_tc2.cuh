@@ -1,0 +1,608 @@
+// bwd_tc2.cuh -- tensor-core backward of one network pass (row a11: loss.backward() through run_nerf.py:381-386 /
+// :397-403, i.e. autograd's backward of NeRF.forward run_nerf_helpers.py:96-119 and raw2outputs run_nerf.py:262-305).
+//
+// Inputs: the per-tile records the training-mode forward left (train_common.cuh: fp16 activation images + ReLU sign
+// masks), its raw [N,S,4] output, and dL/drgb_map.  Everything below works on 128-row tiles in the forward's own tile
+// order, with activation gradients as loss-scaled fp16 (one power-of-two scale per pass taken from max |dL/drgb_map|,
+// saturating conversions) and fp32 accumulation in TMEM:
+//
+//   raw2outputs_bwd_kernel (small_kernels.cuh)  dL/draw per sample                       
+//   dhv_seed_kernel      d_hv = relu'(hv) * (d_rgb W_rgb) as tile images                 (rgb_linear backward, :114)
+//   dgrad_tc2_kernel     the chain  d_hv -> d_feat -> dA_{D-1} -> ... -> dA_0  as tcgen05 cta_group::2 passes with
+//                        TRANSPOSED weight chunks streamed through the forward's 7 x 8 KB TMA ring; the epilogue applies
+//                        the ReLU mask (and the alpha_linear rank-1 term), writes the next A tile in place and the same
+//                        tile goes to the gradient record with one bulk store.  Same warp roles / barriers as the
+//                        forward pair kernel (fused_tc2.cuh); activation gradients never leave the SM between layers.
+//   wgrad_tc_kernel      dW_l += dA_l^T H_{l-1}: both operands MN-major straight from the images (no re-layout), the
+//                        CTAs are partitioned over the layers so that each holds ONE layer's dW in TMEM across all of
+//                        its tiles (256 x 256 fp32 = all 512 columns) and leaves the SM once; bias gradients are the
+//                        column sums of the dA tiles while they sit in shared memory.
+//   wgrad_reduce_kernel  sums the per-CTA partial dW, un-scales, adds into the gradient tensors
+//   head_grads_kernel    rgb_linear / alpha_linear gradients and per-ray row sums of d_hv (CUDA cores, tiny)
+//   views_enc_wgrad_kernel  views_linears[0].weight[:, W:] from the per-ray sums and gamma(viewdir)
+//
+// TMEM capacity is what shapes this: one layer's dW fills an SM's tensor memory, so the weight gradient cannot share
+// a kernel with a tile-major dgrad chain (ten layers would need ten SMs' worth); hence dgrad is tile-major (on-chip
+// chain) and wgrad layer-major (streams the images once: 2 x 64 KB per tile-layer at 64 MAC/B -- HBM-bound).
+#pragma once
+#include <cuda.h>
+#include "fused_tc.cuh"
+#include "fused_tc2.cuh"
+#include "train_common.cuh"
+
+namespace nb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward weight stream: step 0 = views_linears[0].weight[:, :W]^T (K = W/2: 4 chunks), step 1 = feature_linear^T,
+// step j >= 2 = pts_linears[D+1-j].weight[:, h columns]^T (8 chunks each); every chunk is [N = 256 x K = 32] fp16 in the
+// forward's SWIZZLE_64B K-major image, rank-split like the forward stream (pack_weights)
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int bwd_step_units(int j) { return j == 0 ? 4 : 8; }
+static inline int bwd_stream_chunks(int D) { return 4 + 8 * D; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// max |g| over n floats -> *out (bit pattern; non-negative floats order like unsigned ints).  *out zeroed by the caller.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ g, long long n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = fabsf(g[i]);
+    m = (v > m || v != v) ? v : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, m, o); m = (t > m || t != t) ? t : m; }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// gamma(viewdir) per ray (run_nerf.py:44-46 re-encodes it per sample): out [N, ICV]
+__global__ void encv_kernel(const float* __restrict__ dirs, int stride, long long N, int ICV, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * ICV) return;
+  const long long n = i / ICV;
+  const int c = (int)(i - n * ICV);
+  const float* d = dirs + n * stride;
+  float v;
+  if (c < 3) v = d[c];
+  else { const int f = (c - 3) / 6, q = (c - 3) % 6; const float a = __fmul_rn(d[q % 3], exp2f((float)f)); v = (q < 3) ? sinf(a) : cosf(a); }
+  out[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// seed of the dgrad chain: d_hv[row][c] = scale * (hv[row][c] > 0) * sum_j d_rgb[row][j] W_rgb[j][c]   (c < 128)
+// as the first 32 KB of every tile's gradient record (rows beyond the CTA's range: zeros)
+// ---------------------------------------------------------------------------------------------------------------
+struct SeedParams {
+  const float* d_raw; const uint8_t* mask; uint8_t* grad; const float* rgb_w; const unsigned int* amax;
+  long long N; int S, rays_per_cta, nst_plan, D;
+  uint32_t rec_mask, rec_grad; long long n_tiles;
+};
+
+__global__ void __launch_bounds__(256) dhv_seed_kernel(const SeedParams p) {
+  __shared__ float s_w[3 * 128];
+  for (int i = threadIdx.x; i < 384; i += 256) s_w[i] = p.rgb_w[i];
+  __syncthreads();
+  const float scale = loss_scale_from_absmax(__uint_as_float(*p.amax));
+  const int r = threadIdx.x >> 1, ch = threadIdx.x & 1;
+  for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
+    const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
+    const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
+    const int lr = st * 256 + X * 128 + r;
+    float dr = 0.f, dg = 0.f, db = 0.f;
+    uint2 mk = make_uint2(0xffffffffu, 0xffffffffu);
+    if (lr < nrows) {
+      const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr];
+      dr = d.x * scale; dg = d.y * scale; db = d.z * scale;
+      mk = *reinterpret_cast<const uint2*>(p.mask + (size_t)t * p.rec_mask + (uint32_t)p.D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u);
+    }
+    uint8_t* const g = p.grad + (size_t)t * p.rec_grad;
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+      const int col = ch * 64 + c8 * 8;
+      const uint32_t word = (c8 < 4) ? mk.x : mk.y;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = fmaf(dr, s_w[col + i], fmaf(dg, s_w[128 + col + i], db * s_w[256 + col + i]));
+        v[i] = mask_apply(word, (c8 & 3) * 8 + i, x);
+      }
+      *reinterpret_cast<uint4*>(g + img_off(r, col)) =
+          make_uint4(ptx::cvt_sat_f16x2(v[0], v[1]), ptx::cvt_sat_f16x2(v[2], v[3]), ptx::cvt_sat_f16x2(v[4], v[5]), ptx::cvt_sat_f16x2(v[6], v[7]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dgrad chain (CTA pair, cta_group::2) -- structure, warp roles and barrier protocol of march_tc2_kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct DgradParams {
+  const uint8_t* mask; uint8_t* grad; const float* d_raw; const unsigned int* amax; const float* alpha_w;
+  long long N; int S, rays_per_cta, nst_plan, D;
+  uint32_t rec_mask, rec_grad;
+  unsigned long long pair_half_bytes;       // bytes of one rank's half of the backward chunk stream
+};
+
+constexpr uint32_t DG2_SEED = SM_ENC;                                        // 131072: 32 KB, d_hv of ONE slot
+constexpr uint32_t DG2_ALPHA = SM_WRING + TC2_NST * TC2_STAGE_BYTES;         // 221184: alpha_linear.weight, 1 KB fp32
+constexpr uint32_t DG2_BARS = DG2_ALPHA + 1024;                              // 222208
+constexpr uint32_t DG2_MISC = DG2_BARS + 256;                                // 222464: tmem pointer
+constexpr uint32_t DG2_TOTAL = DG2_MISC + 64;
+static_assert(DG2_TOTAL <= SM_ALLOC, "dgrad shared-memory map exceeds the allocation");
+
+// x[32] (one row, 32 consecutive columns starting at COL0 of this warp's column half) -> saturating fp16 -> four 16-byte
+// stores into the swizzled A tile (sw[] as in store_act32_pre)
+template <int COL0>
+__device__ __forceinline__ void store_grad32_pre(const float (&x)[32], const uint32_t (&sw)[8]) {
+  constexpr uint32_t kb = (uint32_t)(COL0 >> 6) * 16384u;
+  constexpr int c16_0 = (COL0 & 63) >> 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    ptx::st_shared_v4(sw[c16_0 + g] + kb, ptx::cvt_sat_f16x2(x[g * 8 + 0], x[g * 8 + 1]), ptx::cvt_sat_f16x2(x[g * 8 + 2], x[g * 8 + 3]),
+                      ptx::cvt_sat_f16x2(x[g * 8 + 4], x[g * 8 + 5]), ptx::cvt_sat_f16x2(x[g * 8 + 6], x[g * 8 + 7]));
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap gmap) {
+  uint8_t* smem = tc_smem;
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sb & 1023u) != 0) __trap();
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  float* s_alpha = reinterpret_cast<float*>(smem + DG2_ALPHA);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + DG2_MISC);
+  const uint32_t a_alpha = sb + DG2_ALPHA;
+  const uint32_t bar_wfull = sb + DG2_BARS;            // [7] (leader): TMA bytes of both CTAs
+  const uint32_t bar_wempty = sb + DG2_BARS + 56;      // [7] multicast commit
+  const uint32_t bar_dfull = sb + DG2_BARS + 112;      // [2] multicast commit
+  const uint32_t bar_act = sb + DG2_BARS + 128;        // [2] (leader) 16 epilogue warps
+  const uint32_t bar_seedfull = sb + DG2_BARS + 144;   //     (leader) TMA bytes of both CTAs' seed tiles
+  const uint32_t bar_seedfree = sb + DG2_BARS + 152;   //     multicast commit after the last step-0 MMA
+  const uint32_t bar_stfull = sb + DG2_BARS + 160;     // [2] local, 8 epilogue warps
+  const uint32_t bar_stdone = sb + DG2_BARS + 176;     // [2] local
+  auto arrive_leader = [&](uint32_t bar) {
+    __syncwarp();
+    if (lane == 0) {
+      if (leader) ptx::mbar_arrive(bar);
+      else ptx::mbar_arrive_remote(ptx::mapa(bar, 0));
+    }
+  };
+
+  // this CTA's rows: exactly the forward's split (same blockIdx -> same rays -> same tile records)
+  const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, (int)blockIdx.x);
+  const int nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, (int)blockIdx.x);
+  const long long row_begin = (long long)blockIdx.x * p.rays_per_cta * p.S;
+  const int D = p.D, NS = D + 1;
+
+  for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_alpha[i] = p.alpha_w[i];
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC2_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); }
+    for (int x = 0; x < 2; ++x) {
+      ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 16);
+      ptx::mbar_init(bar_stfull + 8 * x, 8); ptx::mbar_init(bar_stdone + 8 * x, 1);
+    }
+    ptx::mbar_init(bar_seedfull, 1);
+    ptx::mbar_init(bar_seedfree, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish2(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    // =========================== weight producer (both CTAs): this CTA's 8 KB half of every unit ===========
+    uint32_t stage = 0, ph = 0;
+    const int half_rows = (int)(p.pair_half_bytes >> 9);
+    for (int st = 0; st < nst; ++st) {
+      int row = (int)rank * half_rows;
+      for (int j = 0; j < NS; ++j) {
+        const int nu = bwd_step_units(j);
+        for (int X = 0; X < 2; ++X) {
+          int prow = row;
+          for (int u = 0; u < nu; ++u) {
+            ptx::mbar_wait(bar_wempty + 8 * stage, ph ^ 1);
+            if (ptx::elect_one()) {
+              if (leader) ptx::mbar_arrive_expect_tx(bar_wfull + 8 * stage, 2 * TC2_STAGE_BYTES);
+              ptx::tma2_load_2d(sb + SM_WRING + stage * TC2_STAGE_BYTES, (const void*)&wmap, 0, prow, bar_wfull + 8 * stage);
+            }
+            __syncwarp();
+            prow += (int)(TC2_STAGE_BYTES >> 9);
+            if (++stage == TC2_NST) { stage = 0; ph ^= 1; }
+          }
+        }
+        row += nu * (int)(TC2_STAGE_BYTES >> 9);
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // =========================== MMA issuer (leader CTA) ===========================
+    uint32_t stage = 0, ph = 0, actph0 = 0, actph1 = 0;
+    const uint64_t adesc0 = ptx::umma_desc(sb, 1024, ptx::UMMA_SW128);
+    const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
+    const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = ptx::umma_idesc_f16(256, 256);
+    for (int st = 0; st < nst; ++st) {
+      for (int j = 0; j < NS; ++j) {
+        const int nu = bwd_step_units(j);
+        for (int X = 0; X < 2; ++X) {
+          const uint32_t d_tmem = tmem0 + X * 256;
+          // slot X's accumulator drained (and, for j >= 1, its A tile written) by both CTAs' epilogue warps
+          if (X == 0) { ptx::mbar_wait_cluster(bar_act, actph0); actph0 ^= 1; }
+          else { ptx::mbar_wait_cluster(bar_act + 8, actph1); actph1 ^= 1; }
+          if (j == 0) ptx::mbar_wait_cluster(bar_seedfull, (uint32_t)((st * 2 + X) & 1));
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            uint32_t s_ = stage, ph_ = ph;
+            const uint64_t bring = bdesc0 + (SM_WRING >> 4);
+            uint32_t acc = 0u;
+            if (j == 0) {
+              const uint64_t aseed = adesc0 + (DG2_SEED >> 4);
+#pragma unroll
+              for (int kc = 0; kc < 4; ++kc) {
+                while (!ptx::mbar_try_wait(bar_wfull + 8 * s_, ph_)) { }
+                const uint64_t bd = bring + s_ * (TC2_STAGE_BYTES >> 4);
+                const uint64_t ad = aseed + (uint64_t)((kc >> 1) * 1024 + (kc & 1) * 4);
+                ptx::mma2_f16_ss(d_tmem, ad, bd, idesc, acc);
+                ptx::mma2_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                acc = 1u;
+                if (kc == 3) ptx::mma2_commit_mc(bar_seedfree, 3);
+                ptx::mma2_commit_mc(bar_wempty + 8 * s_, 3);
+                if (++s_ == TC2_NST) { s_ = 0; ph_ ^= 1; }
+              }
+            } else {
+              const uint64_t aact = adesc0 + ((SM_ACT + X * 65536) >> 4);
+#pragma unroll
+              for (int kc = 0; kc < 8; ++kc) {
+                while (!ptx::mbar_try_wait(bar_wfull + 8 * s_, ph_)) { }
+                const uint64_t bd = bring + s_ * (TC2_STAGE_BYTES >> 4);
+                const uint64_t ad = aact + (uint64_t)((kc >> 1) * 1024 + (kc & 1) * 4);
+                ptx::mma2_f16_ss(d_tmem, ad, bd, idesc, acc);
+                ptx::mma2_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                acc = 1u;
+                ptx::mma2_commit_mc(bar_wempty + 8 * s_, 3);
+                if (++s_ == TC2_NST) { s_ = 0; ph_ ^= 1; }
+              }
+            }
+            ptx::mma2_commit_mc(bar_dfull + 8 * X, 3);
+          }
+          __syncwarp();
+          stage += (uint32_t)nu;
+          while (stage >= TC2_NST) { stage -= TC2_NST; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== seed loader (both CTAs): d_hv tile of (super-tile, slot) -> SEED ===========
+    // one 32 KB box of the gradient-record tensor map per (st, X); bytes of both CTAs are counted on the leader's barrier
+    const int rec_rows = (int)(p.rec_grad >> 9);
+    for (int st = 0; st < nst; ++st) {
+      for (int X = 0; X < 2; ++X) {
+        const int i = st * 2 + X;
+        ptx::mbar_wait(bar_seedfree, (uint32_t)((i & 1) ^ 1));
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_arrive_expect_tx(bar_seedfull, 2u * 32768u);
+          const long long t = ((long long)blockIdx.x * p.nst_plan + st) * 2 + X;
+          ptx::tma2_load_2d(sb + DG2_SEED, (const void*)&gmap, 0, (int)(t * rec_rows), bar_seedfull);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int X = (warp - 4) >> 3, e = (warp - 4) & 7, q = warp & 3, ch = e >> 2;
+    const int r = 32 * q + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + X * 256;
+    const uint32_t act_base = sb + SM_ACT + X * 65536;
+    const float scale = loss_scale_from_absmax(__uint_as_float(*p.amax));
+    arrive_leader(bar_act + 8 * X);                            // accumulator initially free
+    uint32_t dph = 0, sfph = 0, sdph = 0;
+    bool st_pending = false;
+    uint32_t swk[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) swk[c] = act_base + (uint32_t)(ch * 2) * 16384u + act_row_off(r) + (uint32_t)((c ^ (r & 7)) << 4);
+    for (int st = 0; st < nst; ++st) {
+      const int lr = st * TC_ST + X * TC_TILE + r;
+      const bool valid = lr < nrows;
+      const long long t = ((long long)blockIdx.x * p.nst_plan + st) * 2 + X;
+      const uint8_t* const mrec = p.mask + (size_t)t * p.rec_mask;
+      uint8_t* const grec = p.grad + (size_t)t * p.rec_grad;
+      const float dsig = valid ? p.d_raw[(row_begin + lr) * 4 + 3] * scale : 0.f;
+      for (int j = 0; j < NS; ++j) {
+        // ReLU mask of this step's output (the pre-activation of pts layer D - j), fetched before the wait
+        uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+        if (j >= 1) mk = *reinterpret_cast<const uint4*>(mrec + (uint32_t)(D - j) * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u);
+        ptx::mbar_wait(bar_dfull + 8 * X, dph);
+        dph ^= 1;
+        ptx::tc_fence_after();
+        if (st_pending) {                                       // the previous bulk store has finished reading the A tile
+          if (e == 0 && lane == 0) { ptx::bulk_wait_read0(); ptx::mbar_arrive(bar_stdone + 8 * X); }
+          ptx::mbar_wait(bar_stdone + 8 * X, sdph);
+          sdph ^= 1;
+        }
+        const int colw = ch * 128;
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_x32(t_lane + colw, va);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int col0 = colw + b * 32;
+          uint32_t (&v)[32] = (b & 1) ? vb : va;
+          uint32_t (&vn)[32] = (b & 1) ? va : vb;
+          ptx::tmem_ld_wait();
+          if (b < 3) ptx::tmem_ld_x32(t_lane + col0 + 32, vn);
+          float x[32];
+          as_float32(v, x);
+          if (j == 1) {                                         // + d_sigma * alpha_linear.weight (run_nerf_helpers.py:106)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 w = lds128(a_alpha + (uint32_t)(col0 + 4 * i) * 4u);
+              x[4 * i + 0] = fmaf(dsig, w.x, x[4 * i + 0]); x[4 * i + 1] = fmaf(dsig, w.y, x[4 * i + 1]);
+              x[4 * i + 2] = fmaf(dsig, w.z, x[4 * i + 2]); x[4 * i + 3] = fmaf(dsig, w.w, x[4 * i + 3]);
+            }
+          }
+          if (j >= 1) {
+            const uint32_t m = (b == 0) ? mk.x : (b == 1) ? mk.y : (b == 2) ? mk.z : mk.w;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = mask_apply(m, i, x[i]);
+          }
+          if (b == 0) store_grad32_pre<0>(x, swk); else if (b == 1) store_grad32_pre<32>(x, swk);
+          else if (b == 2) store_grad32_pre<64>(x, swk); else store_grad32_pre<96>(x, swk);
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        arrive_leader(bar_act + 8 * X);
+        // the tile (next step's A operand) also goes to the gradient record: wgrad reads it from there
+        if (lane == 0) ptx::mbar_arrive(bar_stfull + 8 * X);
+        if (e == 0) {
+          ptx::mbar_wait(bar_stfull + 8 * X, sfph);
+          sfph ^= 1;
+          if (lane == 0) {
+            uint8_t* dst = grec + rec_grad_step(j);
+            for (uint32_t o = 0; o < 65536u; o += 16384u) ptx::bulk_s2g(dst + o, act_base + o, 16384u);
+            ptx::bulk_commit();
+          }
+          __syncwarp();
+        }
+        st_pending = true;
+      }
+    }
+    if (e == 0 && lane == 0) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad: layer-major.  Job = one weight block dW[Mc x Nc] = sum over tiles of A_t^T B_t, A = a gradient image (Mc
+// columns, gradient record), B = an activation image (Nc columns, activation record); a contiguous range of CTAs
+// serves a job, CTA g of G takes the job's tiles g, g + G, ...  Stage = one 64-row half tile of A and of B.
+// 192 threads: warps 0-3 column sums (bias gradient) while streaming, then the TMEM epilogue; warp 4 producer; warp 5 issuer.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WG2_THREADS = 192, WG2_NSTAGE = 3, WG2_MAX_JOBS = 16;
+constexpr uint32_t WG2_STAGE = 65536, WG2_BARS = WG2_NSTAGE * WG2_STAGE, WG2_TOTAL = WG2_BARS + 128;
+
+struct WgradJob {
+  uint32_t a_off, b_off;        // image offsets inside the gradient / activation record
+  int Mc, Nc;                   // columns of A (128 | 256) and of B (64 | 128 | 256)
+  int cta0, ncta;               // CTA range serving this job
+  float* db;                    // bias gradient (fp32, += scaled column sums of A) or NULL
+  long long part_off;           // float offset of this job's partial blocks [ncta][Mc][Nc]
+};
+struct WgradParams {
+  const uint8_t* act; const uint8_t* grad; uint32_t rec_act, rec_grad;
+  long long N; int S, rays_per_cta, nst_plan; long long n_tiles;
+  const unsigned int* amax; float* partial; int njobs;
+  WgradJob jobs[WG2_MAX_JOBS];
+};
+
+__device__ __forceinline__ bool plan_tile_valid(const WgradParams& p, long long t) {
+  const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan);
+  return st < plan_cta_nst(p.N, p.S, p.rays_per_cta, cta);
+}
+
+__global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradParams p) {
+  uint8_t* smem = tc_smem;
+  const uint32_t sb = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sb & 1023u) != 0) __trap();
+  int ji = -1;
+  for (int i = 0; i < p.njobs; ++i) if ((int)blockIdx.x >= p.jobs[i].cta0 && (int)blockIdx.x < p.jobs[i].cta0 + p.jobs[i].ncta) ji = i;
+  if (ji < 0) return;                                   // (uniform per CTA, before any barrier / allocation)
+  const WgradJob job = p.jobs[ji];
+  const int g = (int)blockIdx.x - job.cta0, G = job.ncta;
+  const uint32_t bar_full = sb + WG2_BARS, bar_empty = sb + WG2_BARS + 32, bar_done = sb + WG2_BARS + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + WG2_BARS + 96);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG2_NSTAGE; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 5); }
+    ptx::mbar_init(bar_done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const int xkb = job.Mc >> 6, ykb = job.Nc >> 6;
+  const uint32_t ybase = (uint32_t)xkb * 8192u;
+  long long my_halves = 0;
+  for (long long t = g; t < p.n_tiles; t += G) if (plan_tile_valid(p, t)) my_halves += 2;
+
+  if (warp == 4) {
+    uint32_t s = 0, ph = 0;
+    for (long long t = g; t < p.n_tiles; t += G) {
+      if (!plan_tile_valid(p, t)) continue;
+      for (int h = 0; h < 2; ++h) {
+        ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(xkb + ykb) * 8192u);
+          const uint8_t* xs = p.grad + (size_t)t * p.rec_grad + job.a_off + h * 8192;
+          const uint8_t* ys = p.act + (size_t)t * p.rec_act + job.b_off + h * 8192;
+          for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s(sb + s * WG2_STAGE + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s);
+          for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s(sb + s * WG2_STAGE + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s);
+        }
+        __syncwarp();
+        if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    uint32_t s = 0, ph = 0;
+    const uint32_t idesc = ptx::umma_idesc_f16_major(128, job.Nc, 1, 1);
+    const int mhalves = job.Mc >> 7;
+    for (long long i = 0; i < my_halves; ++i) {
+      ptx::mbar_wait(bar_full + 8 * s, ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t xb = sb + s * WG2_STAGE, yb = xb + ybase;
+        for (int mh = 0; mh < mhalves; ++mh)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // MN-major SWIZZLE_128B (validated: nerf_b200_selftest_gemm_tn, tests of the tile-image wgrad): LBO = stride
+            // between 64-column groups (8 KB: half-tile K-blocks), SBO = 1 KB (8-row groups), K step of 16 rows = 2 KB
+            const uint64_t ad = ptx::umma_desc_full(xb + (uint32_t)(mh * 2) * 8192u + k * 2048, 8192, 1024, ptx::UMMA_SW128);
+            const uint64_t bd = ptx::umma_desc_full(yb + k * 2048, 8192, 1024, ptx::UMMA_SW128);
+            ptx::mma_f16_ss(tmem + mh * 256, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+        ptx::mma_commit(bar_empty + 8 * s);
+        if (i == my_halves - 1) ptx::mma_commit(bar_done);
+      }
+      __syncwarp();
+      if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
+    }
+  } else {
+    // warps 0-3: bias gradient = column sums of the A half tiles, then the accumulator epilogue
+    uint32_t s = 0, ph = 0;
+    const int tid = threadIdx.x;                        // 0..127: columns 2 tid, 2 tid + 1
+    const bool do_sum = (job.db != nullptr) && (2 * tid < job.Mc);
+    const int c = 2 * tid;
+    const uint32_t coff = (uint32_t)((c >> 6) * 8192 + (c & 7) * 2), cc = (uint32_t)((c & 63) >> 3);
+    float s0 = 0.f, s1 = 0.f;
+    for (long long i = 0; i < my_halves; ++i) {
+      ptx::mbar_wait(bar_full + 8 * s, ph);
+      if (do_sum) {
+        const uint32_t base = sb + s * WG2_STAGE + coff;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
+          const __half2 hh = *reinterpret_cast<const __half2*>(&w);
+          s0 += __low2float(hh); s1 += __high2float(hh);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
+      if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
+    }
+    const float inv = 1.0f / loss_scale_from_absmax(__uint_as_float(*p.amax));
+    if (do_sum && my_halves > 0) { atomicAdd(job.db + c, s0 * inv); atomicAdd(job.db + c + 1, s1 * inv); }
+    float* part = p.partial + job.part_off + (size_t)g * job.Mc * job.Nc;
+    if (my_halves > 0) {
+      ptx::mbar_wait(bar_done, 0);
+      ptx::tc_fence_after();
+    }
+    const int r = 32 * warp + lane;
+    for (int mh = 0; mh < (job.Mc >> 7); ++mh)
+      for (int c0 = 0; c0 < job.Nc; c0 += 32) {
+        uint32_t v[32];
+        if (my_halves > 0) {
+          ptx::tmem_ld_x32(tmem + ((uint32_t)(32 * warp) << 16) + mh * 256 + c0, v);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        float4* o = reinterpret_cast<float4*>(part + (size_t)(mh * 128 + r) * job.Nc + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+// dst[o][i] += inv_scale * sum_g partial[g][o][i]   (i < n_valid; dst row stride ldw)
+struct ReduceJob { long long part_off; int ncta, Mc, Nc, n_valid, ldw; float* dst; };
+struct ReduceParams { const float* partial; const unsigned int* amax; int njobs; ReduceJob jobs[WG2_MAX_JOBS]; };
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams p) {
+  const ReduceJob j = p.jobs[blockIdx.y];
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= j.Mc * j.Nc) return;
+  const int o = idx / j.Nc, i = idx - o * j.Nc;
+  if (i >= j.n_valid) return;
+  const float* src = p.partial + j.part_off + idx;
+  float s = 0.f;
+  for (int g = 0; g < j.ncta; ++g) s += src[(size_t)g * j.Mc * j.Nc];
+  const float inv = 1.0f / loss_scale_from_absmax(__uint_as_float(*p.amax));
+  j.dst[(size_t)o * j.ldw + i] += s * inv;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small head gradients on CUDA cores, tile by tile:
+//   rgb_linear.weight[j][c] += sum_rows d_rgb[row][j] hv[row][c],  rgb_linear.bias[j] += sum d_rgb[row][j]
+//   alpha_linear.weight[c]  += sum_rows d_sigma[row] h_{D-1}[row][c],  alpha_linear.bias += sum d_sigma
+//   dsum[ray][c]            += sum over the ray's rows of d_hv[row][c] / scale      (views_linears view-columns, below)
+// ---------------------------------------------------------------------------------------------------------------
+struct HeadGradParams {
+  const uint8_t* act; const uint8_t* grad; const float* d_raw; const unsigned int* amax;
+  long long N; int S, rays_per_cta, nst_plan, D; uint32_t rec_act, rec_grad; long long n_tiles;
+  float* rgb_w; float* rgb_b; float* alpha_w; float* alpha_b; float* dsum;
+};
+
+__global__ void __launch_bounds__(256) head_grads_kernel(const HeadGradParams p) {
+  __shared__ float4 s_d[128];
+  const int c = threadIdx.x;
+  const float inv = 1.0f / loss_scale_from_absmax(__uint_as_float(*p.amax));
+  float a_w = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
+    const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
+    const int lr0 = st * 256 + X * 128;
+    if (lr0 >= nrows) continue;                         // (uniform) no valid row in this tile
+    const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
+    const int nv = (nrows - lr0 < 128) ? nrows - lr0 : 128;
+    __syncthreads();
+    if (c < 128) s_d[c] = (c < nv) ? reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const uint8_t* arec = p.act + (size_t)t * p.rec_act;
+    const uint8_t* grec = p.grad + (size_t)t * p.rec_grad;
+    const uint8_t* h_last = arec + rec_act_h(p.D - 1);
+    for (int r = 0; r < nv; ++r) a_w = fmaf(s_d[r].w, __half2float(*reinterpret_cast<const __half*>(h_last + img_off(r, c))), a_w);
+    if (c < 128) {
+      const uint8_t* hv = arec + rec_act_hv(p.D);
+      long long ray = (row_begin + lr0) / p.S;
+      int left = (int)((ray + 1) * p.S - (row_begin + lr0));      // rows of `ray` that remain from this tile's first row
+      float run = 0.f;
+      for (int r = 0; r < nv; ++r) {
+        const float h = __half2float(*reinterpret_cast<const __half*>(hv + img_off(r, c)));
+        const float4 d = s_d[r];
+        r0 = fmaf(d.x, h, r0); r1 = fmaf(d.y, h, r1); r2 = fmaf(d.z, h, r2);
+        run += __half2float(*reinterpret_cast<const __half*>(grec + img_off(r, c)));
+        if (--left == 0 || r == nv - 1) { atomicAdd(p.dsum + ray * 128 + c, run * inv); run = 0.f; ++ray; left = p.S; }
+      }
+    } else if (c == 128) {
+      for (int r = 0; r < nv; ++r) { b0 += s_d[r].x; b1 += s_d[r].y; b2 += s_d[r].z; b3 += s_d[r].w; }
+    }
+  }
+  atomicAdd(p.alpha_w + c, a_w);
+  if (c < 128) { atomicAdd(p.rgb_w + c, r0); atomicAdd(p.rgb_w + 128 + c, r1); atomicAdd(p.rgb_w + 256 + c, r2); }
+  if (c == 128) { atomicAdd(p.rgb_b, b0); atomicAdd(p.rgb_b + 1, b1); atomicAdd(p.rgb_b + 2, b2); atomicAdd(p.alpha_b, b3); }
+}
+
+// views_linears[0].weight[c][W + e] += sum_rays dsum[ray][c] * gamma(viewdir_ray)[e]      (run_nerf_helpers.py:108-110)
+__global__ void __launch_bounds__(128) views_enc_wgrad_kernel(const float* __restrict__ dsum, const float* __restrict__ encv, long long N, int ICV,
+                                                            float* __restrict__ views_w, int ld, int col0) {
+  const int e = blockIdx.x, c = threadIdx.x;
+  const long long n0 = (long long)blockIdx.y * 512, n1 = (n0 + 512 < N) ? n0 + 512 : N;
+  float s = 0.f;
+  for (long long n = n0; n < n1; ++n) s = fmaf(dsum[n * 128 + c], encv[n * ICV + e], s);
+  atomicAdd(views_w + (size_t)c * ld + col0 + e, s);
+}
+
+}  // namespace nb

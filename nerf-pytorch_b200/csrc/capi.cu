@@ -6,7 +6,7 @@
 #include "mlp_simt.cuh"
 #include "fused_tc.cuh"
 #include "fused_tc2.cuh"
-#include "bwd_tc.cuh"
+#include "bwd_tc2.cuh"
 #include <stdlib.h>
 
 namespace nb {
@@ -21,7 +21,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 // ---- optional device-time accounting of march_tc_kernel launches (bench.py roofline) ----
-struct TimedLaunch { cudaEvent_t a, b; double flops; };
+struct TimedLaunch { cudaEvent_t a, b; double flops; int kind; };   // kind 0: forward pass, 1: dgrad chain, 2: wgrad
 static bool g_timing = false;
 static TimedLaunch g_timed[4096];
 static int g_ntimed = 0;
@@ -35,7 +35,7 @@ static double net_macs_per_row(const NerfNetParams& n) {
   return m;
 }
 
-static long long* g_trace = nullptr;      // debug: device buffer of 4096 int64 clock stamps (or NULL)
+static long long* g_trace = nullptr;      // debug: device buffer of 4096 int64 clock stamps (NERF_B200_TRACE builds)
 
 static int check_tc_net(const NerfNetParams* net) {
   NB_CHECK_ARG(net != nullptr, "net is NULL");
@@ -52,17 +52,55 @@ static int smem_optin(const void* fn, size_t bytes) {
   return 0;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-  return n;
+// per-device facts (SM count; which kernels already have their > 48 KB shared-memory opt-in): the library may be used
+// on several devices of one process, and cudaFuncSetAttribute is per device
+struct DeviceState { int sms; bool optin_fwd, optin_bwd; };
+static DeviceState* device_state() {
+  static DeviceState st[64];
+  static bool init[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!init[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    st[dev].sms = n > 0 ? n : 148;
+    st[dev].optin_fwd = st[dev].optin_bwd = false;
+    init[dev] = true;
+  }
+  return &st[dev];
+}
+static int num_sms() { return device_state()->sms; }
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// 2-D tensor map over a byte buffer viewed as [rows][256] uint16 (512-byte rows); box = `box_rows` rows (box_rows * 512 bytes)
+static int make_row_map(CUtensorMap* map, const void* base, size_t bytes, int box_rows) {
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    NB_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  NB_CHECK_ARG(bytes % 512 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: buffer must be 16-byte aligned, a multiple of 512 bytes");
+  const cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 512)};
+  const cuuint64_t gstr[1] = {512};
+  const cuuint32_t box[2] = {256, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  return 0;
 }
 
-// shared launcher of the fused tcgen05 pass
+// shared launcher of the fused tcgen05 pass; `save` != NULL selects the training-mode kernel (EMIT)
 static int launch_march(const float* rays, int ray_stride, const float* z_vals, const float* pts,
                         const float* dirs, int dir_stride, const float* noise, long long N, int S,
                         const NerfNetParams* net, const void* packed, int L, int Lv, int white_bkgd, int do_composite,
-                        const NerfPassOut* out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                        const NerfPassOut* out, void* workspace, size_t workspace_bytes, const NerfTrainSave* save, cudaStream_t st) {
   if (int rc = check_tc_net(net)) return rc;
   NB_CHECK_ARG(packed != nullptr, "packed weights are NULL (call nerf_b200_pack_weights)");
   NB_CHECK_ARG(N > 0 && S > 0, "empty ray batch must be handled by the caller (N=%lld S=%d)", N, S);
@@ -74,7 +112,7 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   memset(&p, 0, sizeof(p));
   p.rays = rays; p.ray_stride = ray_stride; p.z_vals = z_vals; p.pts = pts; p.noise = noise;
   p.N = N; p.S = S;
-  p.chunks = pk + PL.off_chunks; p.bias = reinterpret_cast<const float*>(pk + PL.off_bias);
+  p.bias = reinterpret_cast<const float*>(pk + PL.off_bias);
   p.heads = reinterpret_cast<const float*>(pk + PL.off_heads);
   p.biasb = pk + PL.off_biasb;
   p.D = net->D; p.skip = net->skip; p.use_viewdirs = net->use_viewdirs; p.L = L; p.IC = net->input_ch;
@@ -90,65 +128,46 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
     NB_LAUNCH_OK("view_bias_kernel");
     p.vb = vb;
   }
-  // persistent grid: whole rays per CTA, balanced over the SMs
-  const int sms = num_sms();
-  long long rows = N * (long long)S;
-  long long want = (rows + TC_ST - 1) / TC_ST;
-  int grid = (int)(want < sms ? want : sms);
-  if (grid > N) grid = (int)N;
-  if (grid < 1) grid = 1;
-  p.rays_per_cta = (int)((N + grid - 1) / grid);
-  grid = (int)((N + p.rays_per_cta - 1) / p.rays_per_cta);
+  // persistent grid: whole rays per CTA, balanced over the SMs, whole CTA pairs (a padding CTA owns no rays)
+  DeviceState* ds = device_state();
+  const TilePlan plan = make_tile_plan(N, S, ds->sms);
+  p.rays_per_cta = plan.rays_per_cta;
   NB_CHECK_ARG((long long)p.rays_per_cta * S < (1ll << 30), "rays_per_cta * S overflows");
-  // default: the CTA-pair kernel (fused_tc2.cuh, cta_group::2); NERF_B200_PAIR=0 selects the single-CTA kernel
-  // (fused_tc.cuh) that it superseded -- kept for A/B measurements, latched at the first launch.
-  static int pair_mode = -1;
-  if (pair_mode < 0) { const char* e = getenv("NERF_B200_PAIR"); pair_mode = (e && e[0] == '0') ? 0 : 1; }
-  static bool optin = false;
-  if (!optin) {
-    if (int rc = smem_optin((const void*)march_tc_kernel, SM_ALLOC)) return rc;
-    if (int rc = smem_optin((const void*)march_tc2_kernel, SM_ALLOC)) return rc;
-    optin = true;
+  if (!ds->optin_fwd) {
+    if (int rc = smem_optin((const void*)march_tc2_kernel<false>, SM_ALLOC)) return rc;
+    if (int rc = smem_optin((const void*)march_tc2_kernel<true>, SM_ALLOC)) return rc;
+    ds->optin_fwd = true;
   }
-  if (pair_mode) grid = (grid + 1) & ~1;                 // whole pairs; a padding CTA owns no rays
   p.trace = g_trace;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("NERF_B200_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+  TrainSaveDev sv;
+  memset(&sv, 0, sizeof(sv));
+  if (save) {
+    NB_CHECK_ARG(net->use_viewdirs, "training-mode records are implemented for use_viewdirs networks");
+    NB_CHECK_ARG(save->act && save->mask, "training-mode save buffers are NULL");
+    NB_CHECK_ARG(save->act_bytes >= (size_t)plan.n_tiles * rec_act_bytes(net->D) && save->mask_bytes >= (size_t)plan.n_tiles * rec_mask_bytes(net->D),
+                 "training-mode save buffers too small (see nerf_b200_train_record_bytes)");
+    NB_CHECK_ARG((reinterpret_cast<uintptr_t>(save->act) & 15) == 0 && (reinterpret_cast<uintptr_t>(save->mask) & 15) == 0, "save buffers must be 16-byte aligned");
+    sv.act = static_cast<uint8_t*>(save->act); sv.mask = static_cast<uint8_t*>(save->mask);
+    sv.nst_plan = plan.nst; sv.rec_act = rec_act_bytes(net->D); sv.rec_mask = rec_mask_bytes(net->D);
+  }
   TimedLaunch* tl = nullptr;
   if (g_timing && g_ntimed < 4096) {
     tl = &g_timed[g_ntimed++];
     cudaEventCreate(&tl->a); cudaEventCreate(&tl->b);
-    tl->flops = 2.0 * net_macs_per_row(*net) * (double)rows;
+    tl->flops = 2.0 * net_macs_per_row(*net) * (double)(N * (long long)S);
+    tl->kind = 0;
     cudaEventRecord(tl->a, st);
   }
-  if (pair_mode) {
-    // tensor map over the rank-split chunk stream, viewed as [rows][256] uint16 (512-byte rows)
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      NB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-      NB_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-      encode = reinterpret_cast<EncodeFn>(fn);
-    }
-    CUtensorMap wmap;                           // box = 16 stream rows = 8 KB = one ring stage
-    const cuuint64_t gdim[2] = {256, (cuuint64_t)(PL.chunk_bytes / 512)};
-    const cuuint64_t gstr[1] = {512};
-    const cuuint32_t box[2] = {256, 16}, estr[2] = {1, 1};
-    uint8_t* pair_stream = const_cast<uint8_t*>(pk + PL.off_pair);
-    p.chunks = pair_stream;                     // the pair kernel walks the rank-split stream
-    p.pair_half_bytes = PL.chunk_bytes / 2;
-    CUresult cr = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pair_stream, gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NB_CHECK_ARG(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    march_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p, wmap);
-  }
-  else march_tc_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(p);
+  // tensor map over the rank-split chunk stream (512-byte rows); box = 16 rows = 8 KB = one ring stage
+  CUtensorMap wmap;
+  const uint8_t* pair_stream = pk + PL.off_pair;
+  p.chunks = pair_stream;
+  p.pair_half_bytes = PL.chunk_bytes / 2;
+  if (int rc = make_row_map(&wmap, pair_stream, PL.chunk_bytes, 16)) return rc;
+  if (save) march_tc2_kernel<true><<<plan.grid, TC_THREADS, SM_ALLOC, st>>>(p, wmap, sv);
+  else march_tc2_kernel<false><<<plan.grid, TC_THREADS, SM_ALLOC, st>>>(p, wmap, sv);
   if (tl) cudaEventRecord(tl->b, st);
-  NB_LAUNCH_OK("march_tc_kernel");
+  NB_LAUNCH_OK("march_tc2_kernel");
   return 0;
 }
 
@@ -164,17 +183,23 @@ int64_t nerf_b200_launch_count(void) { return g_launches; }
 
 int nerf_b200_timing_enable(int on) { g_timing = on != 0; return 0; }
 int nerf_b200_timing_read(double* kernel_ms, int64_t* launches, double* algorithmic_flops) {
-  double ms = 0, fl = 0;
+  return nerf_b200_timing_read_kinds(kernel_ms, launches, algorithmic_flops, nullptr);
+}
+// kind_ms[3]: device time of the forward passes, the dgrad chains and the wgrad kernels (NULL: not wanted)
+int nerf_b200_timing_read_kinds(double* kernel_ms, int64_t* launches, double* algorithmic_flops, double* kind_ms) {
+  double ms = 0, fl = 0, km[3] = {0, 0, 0};
   for (int i = 0; i < g_ntimed; ++i) {
     NB_CUDA(cudaEventSynchronize(g_timed[i].b));
     float t = 0;
     NB_CUDA(cudaEventElapsedTime(&t, g_timed[i].a, g_timed[i].b));
     ms += t; fl += g_timed[i].flops;
+    if (g_timed[i].kind >= 0 && g_timed[i].kind < 3) km[g_timed[i].kind] += t;
     cudaEventDestroy(g_timed[i].a); cudaEventDestroy(g_timed[i].b);
   }
   if (kernel_ms) *kernel_ms = ms;
   if (launches) *launches = g_ntimed;
   if (algorithmic_flops) *algorithmic_flops = fl;
+  if (kind_ms) { kind_ms[0] = km[0]; kind_ms[1] = km[1]; kind_ms[2] = km[2]; }
   g_ntimed = 0;
   return 0;
 }
@@ -205,7 +230,7 @@ int nerf_b200_pack_weights(const NerfNetParams* net, void* packed, size_t packed
   const int IC = net->input_ch, W = net->W;
   auto add = [&](const float* src, int ld, int k0, int kvalid, int nrows) {
     PackChunk& c = job.c[job.n++];
-    c.src = src; c.ld = ld; c.k0 = k0; c.kvalid = kvalid < 0 ? 0 : (kvalid > 32 ? 32 : kvalid); c.nrows = nrows; c.dst_off = off;
+    c.src = src; c.sn = ld; c.sk = 1; c.k0 = k0; c.kvalid = kvalid < 0 ? 0 : (kvalid > 32 ? 32 : kvalid); c.nrows = nrows; c.dst_off = off;
     off += (unsigned)nrows * 64;
   };
   PackBiasJob bj;
@@ -241,6 +266,33 @@ int nerf_b200_pack_weights(const NerfNetParams* net, void* packed, size_t packed
         NB_CUDA(cudaMemcpy2DAsync(dst + reg_bytes / 2, 4096, base + PL.off_chunks + reg_bytes + (size_t)r * 4096, 8192, 4096, 8, cudaMemcpyDeviceToDevice, st));
     }
   }
+  if (PL.bwd_bytes) {
+    // backward (dgrad) stream, bwd_tc2.cuh: chunk [n][k] = W[k0 + k][col0 + n] -- the transposed weights, so that the
+    // chain dA_{l-1} = dA_l W_l runs through the forward's operand layouts.  Step 0: views_linears[0].weight[:, :W]
+    // (K = W/2), step 1: feature_linear, then pts_linears[D-1] ... [1] restricted to their h columns.
+    PackJob bj2;
+    bj2.n = 0;
+    unsigned boff = (unsigned)PL.off_bwd;
+    auto addT = [&](const float* src, int ld, int col0, int k0) {
+      PackChunk& c = bj2.c[bj2.n++];
+      c.src = src + col0; c.sn = 1; c.sk = ld; c.k0 = k0; c.kvalid = 32; c.nrows = 256; c.dst_off = boff;
+      boff += 256u * 64u;
+    };
+    for (int c = 0; c < 4; ++c) addT(net->views_w, W + net->input_ch_views, 0, 32 * c);
+    for (int c = 0; c < 8; ++c) addT(net->feature_w, W, 0, 32 * c);
+    for (int l = net->D - 1; l >= 1; --l) {
+      const bool sk = (net->skip >= 0 && l == net->skip + 1);
+      for (int c = 0; c < 8; ++c) addT(net->pts_w[l], sk ? W + IC : W, sk ? IC : 0, 32 * c);
+    }
+    NB_CHECK_ARG(bj2.n == 4 + 8 * net->D && boff == PL.off_bwd + PL.bwd_bytes, "internal: backward chunk table mismatch");
+    dim3 g2(4, bj2.n);
+    pack_chunks_kernel<<<g2, 256, 0, st>>>(bj2, static_cast<uint8_t*>(packed));
+    NB_LAUNCH_OK("pack_chunks_kernel (backward stream)");
+    uint8_t* base = static_cast<uint8_t*>(packed);
+    for (int r = 0; r < 2; ++r)
+      NB_CUDA(cudaMemcpy2DAsync(base + PL.off_bwd_pair + (size_t)r * (PL.bwd_bytes / 2), 8192, base + PL.off_bwd + (size_t)r * 8192, 16384, 8192,
+                                PL.bwd_bytes / 16384, cudaMemcpyDeviceToDevice, st));
+  }
   PackTables t;
   t.net = *net; t.off_bias = PL.off_bias; t.off_heads = PL.off_heads; t.off_vdir = PL.off_vdir;
   pack_tables_kernel<<<8, 256, 0, st>>>(t, static_cast<uint8_t*>(packed));
@@ -269,7 +321,7 @@ int nerf_b200_run_network(const float* pts, const float* viewdirs, int64_t N, in
   memset(&out, 0, sizeof(out));
   out.raw = raw;
   return launch_march(nullptr, 0, nullptr, pts, viewdirs, 3, nullptr, N, S, net, packed, multires, multires_views, 0, 0,
-                      &out, workspace, workspace_bytes, st);
+                      &out, workspace, workspace_bytes, nullptr, st);
 }
 
 int nerf_b200_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int d_stride, const float* noise,
@@ -359,15 +411,16 @@ size_t nerf_b200_march_workspace_bytes(int64_t N, int S) {
   return (tc > exact ? tc : exact) + 256;
 }
 
-int nerf_b200_march(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
-                    const void* packed, const NerfRenderCfg* cfg, const NerfPassOut* out, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+static int march_impl(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
+                      const void* packed, const NerfRenderCfg* cfg, const NerfPassOut* out, void* workspace,
+                      size_t workspace_bytes, const NerfTrainSave* save, void* stream) {
   NB_CHECK_ARG(rays && z_vals && net && cfg && out, "NULL pointer");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   NB_CHECK_ARG(cfg->ray_stride >= (net->use_viewdirs ? 11 : 8), "ray_stride %d too small", cfg->ray_stride);
   if (cfg->precision == NERF_B200_PREC_FP32) {
     // exact mode (validation path): materialise pts -> fp32 CUDA-core MLP -> raw2outputs kernel
+    NB_CHECK_ARG(save == nullptr, "training-mode records belong to the tensor-core path");
     const long long M = N * (long long)S;
     const size_t need = (size_t)M * 12 + (out->raw ? 0 : (size_t)M * 16);
     NB_CHECK_ARG(workspace && workspace_bytes >= need, "exact-mode workspace too small: need %zu bytes", need);
@@ -385,15 +438,37 @@ int nerf_b200_march(const float* rays, const float* z_vals, const float* noise, 
     return 0;
   }
   return launch_march(rays, cfg->ray_stride, z_vals, nullptr, rays + 8, cfg->ray_stride, noise, N, S, net, packed,
-                      cfg->multires, cfg->multires_views, cfg->white_bkgd, 1, out, workspace, workspace_bytes, st);
+                      cfg->multires, cfg->multires_views, cfg->white_bkgd, 1, out, workspace, workspace_bytes, save, st);
 }
 
-int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfNetParams* net_coarse,
-                              const void* packed_coarse, const NerfNetParams* net_fine, const void* packed_fine,
-                              const float* t_vals, const float* u_det, const float* t_rand, const float* u_rand,
-                              const float* noise0, const float* noise1, float* z_coarse, const NerfPassOut* coarse,
-                              float* z_fine, float* z_std, const NerfPassOut* fine, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+int nerf_b200_march(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
+                    const void* packed, const NerfRenderCfg* cfg, const NerfPassOut* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return march_impl(rays, z_vals, noise, N, S, net, packed, cfg, out, workspace, workspace_bytes, nullptr, stream);
+}
+
+int nerf_b200_march_train(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
+                          const void* packed, const NerfRenderCfg* cfg, const NerfPassOut* out, void* workspace,
+                          size_t workspace_bytes, const NerfTrainSave* save, void* stream) {
+  NB_CHECK_ARG(save != nullptr && out && out->raw, "training mode needs the save buffers and out->raw (the compositing adjoint reads raw)");
+  return march_impl(rays, z_vals, noise, N, S, net, packed, cfg, out, workspace, workspace_bytes, save, stream);
+}
+
+int nerf_b200_train_record_bytes(int64_t N, int S, const NerfNetParams* net, size_t* act_bytes, size_t* mask_bytes) {
+  if (int rc = check_tc_net(net)) return rc;
+  NB_CHECK_ARG(N >= 0 && S >= 1, "bad N / S");
+  const TilePlan plan = make_tile_plan(N > 0 ? N : 1, S, num_sms());
+  if (act_bytes) *act_bytes = (size_t)plan.n_tiles * rec_act_bytes(net->D);
+  if (mask_bytes) *mask_bytes = (size_t)plan.n_tiles * rec_mask_bytes(net->D);
+  return 0;
+}
+
+static int render_rays_fwd_impl(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfNetParams* net_coarse,
+                                const void* packed_coarse, const NerfNetParams* net_fine, const void* packed_fine,
+                                const float* t_vals, const float* u_det, const float* t_rand, const float* u_rand,
+                                const float* noise0, const float* noise1, float* z_coarse, const NerfPassOut* coarse,
+                                float* z_fine, float* z_std, const NerfPassOut* fine, void* workspace,
+                                size_t workspace_bytes, const NerfTrainSave* save_coarse, const NerfTrainSave* save_fine, void* stream) {
   NB_CHECK_ARG(rays && cfg && net_coarse && t_vals && z_coarse && coarse, "NULL pointer");
   if (N == 0) return 0;
   const int Sc = cfg->N_samples, Ni = cfg->N_importance;
@@ -402,7 +477,7 @@ int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg*
   // z sampling (run_nerf.py:357-379)
   if (int rc = nerf_b200_coarse_z(rays, cfg->ray_stride, t_vals, cfg->perturb ? t_rand : nullptr, N, Sc, cfg->lindisp, z_coarse, stream)) return rc;
   // coarse pass (:381-386)
-  if (int rc = nerf_b200_march(rays, z_coarse, noise0, N, Sc, net_coarse, packed_coarse, cfg, coarse, workspace, workspace_bytes, stream)) return rc;
+  if (int rc = march_impl(rays, z_coarse, noise0, N, Sc, net_coarse, packed_coarse, cfg, coarse, workspace, workspace_bytes, save_coarse, stream)) return rc;
   if (Ni == 0) return 0;
   NB_CHECK_ARG(coarse->weights && z_fine && fine, "N_importance > 0 needs coarse->weights, z_fine and fine outputs");
   // hierarchical sampling (:392-396, :412); det <=> perturb == 0 (:393)
@@ -412,30 +487,41 @@ int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg*
   // fine pass on all S_c + N_importance samples (:397-403); network_fine None -> coarse net (:399)
   const NerfNetParams* nf = net_fine ? net_fine : net_coarse;
   const void* pf = net_fine ? packed_fine : packed_coarse;
-  return nerf_b200_march(rays, z_fine, noise1, N, Sc + Ni, nf, pf, cfg, fine, workspace, workspace_bytes, stream);
+  return march_impl(rays, z_fine, noise1, N, Sc + Ni, nf, pf, cfg, fine, workspace, workspace_bytes, save_fine, stream);
+}
+
+int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfNetParams* net_coarse,
+                              const void* packed_coarse, const NerfNetParams* net_fine, const void* packed_fine,
+                              const float* t_vals, const float* u_det, const float* t_rand, const float* u_rand,
+                              const float* noise0, const float* noise1, float* z_coarse, const NerfPassOut* coarse,
+                              float* z_fine, float* z_std, const NerfPassOut* fine, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return render_rays_fwd_impl(rays, N, cfg, net_coarse, packed_coarse, net_fine, packed_fine, t_vals, u_det, t_rand, u_rand, noise0, noise1,
+                              z_coarse, coarse, z_fine, z_std, fine, workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+// the same call in training mode: both passes also leave their per-tile records (activation images + ReLU masks) for
+// nerf_b200_march_bwd_tc, and must write raw (coarse->raw, fine->raw)
+int nerf_b200_render_rays_fwd_train(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfNetParams* net_coarse,
+                                    const void* packed_coarse, const NerfNetParams* net_fine, const void* packed_fine,
+                                    const float* t_vals, const float* u_det, const float* t_rand, const float* u_rand,
+                                    const float* noise0, const float* noise1, float* z_coarse, const NerfPassOut* coarse,
+                                    float* z_fine, float* z_std, const NerfPassOut* fine, void* workspace,
+                                    size_t workspace_bytes, const NerfTrainSave* save_coarse, const NerfTrainSave* save_fine, void* stream) {
+  NB_CHECK_ARG(cfg && cfg->precision == NERF_B200_PREC_TC_FP16, "training-mode records belong to the tensor-core path");
+  NB_CHECK_ARG(save_coarse && coarse && coarse->raw, "training mode needs save_coarse and coarse->raw");
+  NB_CHECK_ARG(cfg->N_importance == 0 || (save_fine && fine && fine->raw), "training mode needs save_fine and fine->raw");
+  return render_rays_fwd_impl(rays, N, cfg, net_coarse, packed_coarse, net_fine, packed_fine, t_vals, u_det, t_rand, u_rand, noise0, noise1,
+                              z_coarse, coarse, z_fine, z_std, fine, workspace, workspace_bytes, save_coarse, save_fine, stream);
 }
 
 // ---- exact-mode backward of one pass (see bwd_simt.cuh) -------------------------------------------
 static const int BWD_RAYS_PER_SLAB = 512;     // rays recomputed + back-propagated per slab (bounds the workspace)
 
-size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S) {
+size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S, const NerfNetParams* net) {
+  if (!net) return 0;
   const long long rows = (long long)(N < BWD_RAYS_PER_SLAB ? N : BWD_RAYS_PER_SLAB) * S;
-  // upper bound over supported nets; the last term: three fp16 tile images of 256 columns (experimental tensor-core GEMMs)
-  return (size_t)rows * (63 + 63 + 16 * 256 + 256 + 128 + 8 + 512 + 128 + 3 + 3 * 128) * 4 + 1024 + 3 * 128 * 512 + 3 * 1024;
-}
-
-// ---- experimental: the backward's large GEMMs on tensor cores (bwd_tc.cuh), NERF_B200_BWD_TC=1; never validated on a GPU ----
-struct TcScratch { uint8_t* a; uint8_t* b; uint8_t* o; float scale; };
-static bool bwd_tc_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("NERF_B200_BWD_TC"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on == 1;
-}
-static int pack_img(const float* src, int ld, long long M, int ncols, int C, float scale, uint8_t* img, cudaStream_t st) {
-  const long long n = ((M + 127) / 128) * 128 * (C >> 3);
-  tile_pack_kernel<<<cdiv(n, 256), 256, 0, st>>>(src, ld, M, ncols, C, scale, img);
-  NB_LAUNCH_OK("tile_pack_kernel");
-  return 0;
+  return (size_t)rows * (3 + bwd_floats_per_row(*net)) * 4 + 1024;
 }
 
 static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int N, int K, int beta, cudaStream_t st) {
@@ -449,33 +535,6 @@ static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, i
   dim3 grid(cdiv(K1, GT), cdiv(N, GT), cdiv(M, slab));
   sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, K1, N, slab);
   NB_LAUNCH_OK("sgemm_tn_kernel");
-  return 0;
-}
-// C[K1,N] += A^T B like gemm_tn, through wgrad_tiles_kernel when the shape fits (K1 in {128,256}, N <= 256) and tc != NULL
-static int gemm_tn_any(const TcScratch* tc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int K1, int N, cudaStream_t st) {
-  if (!tc || !(K1 == 128 || K1 == 256) || N > 256 || N < 8) return gemm_tn(A, lda, B, ldb, C, ldc, M, K1, N, st);
-  const int Nc = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
-  if (int rc = pack_img(A, lda, M, K1, K1, tc->scale, tc->a, st)) return rc;
-  if (int rc = pack_img(B, ldb, M, N, Nc, 1.0f, tc->b, st)) return rc;
-  if (int rc = smem_optin((const void*)wgrad_tiles_kernel, WG_TOTAL)) return rc;
-  const long long n_tiles = (M + 127) / 128;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  wgrad_tiles_kernel<<<grid, WG_THREADS, WG_TOTAL, st>>>(tc->a, tc->b, n_tiles, K1, Nc, 1.0f / tc->scale, C, ldc, N);
-  NB_LAUNCH_OK("wgrad_tiles_kernel");
-  return 0;
-}
-// C[M,N] = A B like gemm_nn (beta = 0), through dgrad_tiles_kernel when N == 256, K in {128,256} and tc != NULL
-static int gemm_nn_any(const TcScratch* tc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int N, int K, int beta, cudaStream_t st) {
-  if (!tc || beta != 0 || N != 256 || !(K == 128 || K == 256)) return gemm_nn(A, lda, B, ldb, C, ldc, M, N, K, beta, st);
-  if (int rc = pack_img(A, lda, M, K, K, tc->scale, tc->a, st)) return rc;
-  if (int rc = pack_img(B, ldb, K, 256, 256, 1.0f, tc->b, st)) return rc;          // W rows = reduction index
-  if (int rc = smem_optin((const void*)dgrad_tiles_kernel, DG_TOTAL)) return rc;
-  const long long n_tiles = (M + 127) / 128;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  dgrad_tiles_kernel<<<grid, DG_THREADS, DG_TOTAL, st>>>(tc->a, tc->b, nullptr, n_tiles, K, tc->o);
-  NB_LAUNCH_OK("dgrad_tiles_kernel");
-  tile_unpack_kernel<<<cdiv(M * 32, 256), 256, 0, st>>>(tc->o, M, 256, 1.0f / tc->scale, C, ldc);
-  NB_LAUNCH_OK("tile_unpack_kernel");
   return 0;
 }
 static int mask_colsum(float* d, int ldd, const float* h, int ldh, long long M, int C, float* colsum, cudaStream_t st) {
@@ -492,12 +551,11 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
                         void* workspace, size_t workspace_bytes, void* stream) {
   (void)packed;
   NB_CHECK_ARG(rays && z_vals && net && cfg && g_rgb && grads, "NULL pointer");
-  NB_CHECK_ARG(net->use_viewdirs, "backward is implemented for use_viewdirs networks (the reference's shipped configs)");
   NB_CHECK_ARG(net->W <= SIMT_THREADS && net->W % 4 == 0 && net->D <= NERF_B200_MAX_D, "unsupported network shape");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int W = net->W, W2 = W / 2, IC = net->input_ch, ICV = net->input_ch_views, D = net->D, rs = cfg->ray_stride;
-  NB_CHECK_ARG(workspace && workspace_bytes >= nerf_b200_march_bwd_workspace_bytes(N, S), "march_bwd workspace too small");
+  NB_CHECK_ARG(workspace && workspace_bytes >= nerf_b200_march_bwd_workspace_bytes(N, S, net), "march_bwd workspace too small");
   for (int64_t n0 = 0; n0 < N; n0 += BWD_RAYS_PER_SLAB) {
     const int64_t nn = (N - n0 < BWD_RAYS_PER_SLAB) ? N - n0 : BWD_RAYS_PER_SLAB;
     const long long M = nn * (long long)S;
@@ -517,42 +575,40 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
     float* dh0 = p;        p += M * W;
     float* dh1 = p;        p += M * W;
     float* d_hv = p;       p += M * W2;
-    TcScratch tcs, *tc = nullptr;
-    if (bwd_tc_enabled() && W == 256) {
-      // three 256-column fp16 tile images (1 KB-aligned) behind the fp32 buffers; one static loss scale for the slab's
-      // activation gradients: |dL/drgb| <= 2 / (3 N)  (tools/bwd_precision_study.py)
-      const size_t ib = (size_t)((M + 127) / 128) * 65536;
-      uint8_t* q = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
-      tcs.a = q; tcs.b = q + ib; tcs.o = q + 2 * ib;
-      tcs.scale = exp2f(floorf(log2f(3.0f * (float)N * 512.0f)));
-      tc = &tcs;
-    }
+    if (!net->use_viewdirs) { sv.encv = nullptr; sv.feat = nullptr; sv.hv = nullptr; }
     // 1. recompute the pass in fp32 with saved activations
     pts_kernel<<<cdiv(M, 256), 256, 0, st>>>(ry, rs, zz, M, S, pts);
     NB_LAUNCH_OK("pts_kernel");
     const size_t sm = simt_smem_bytes(*net);
     NB_TRY(smem_optin((const void*)mlp_simt_kernel, sm));
-    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, ry + 8, rs, M, S, *net, cfg->multires, cfg->multires_views, raw, sv);
+    mlp_simt_kernel<<<cdiv(M, SIMT_ROWS), SIMT_THREADS, sm, st>>>(pts, net->use_viewdirs ? ry + 8 : nullptr, rs, M, S, *net, cfg->multires, cfg->multires_views, raw, sv);
     NB_LAUNCH_OK("mlp_simt_kernel");
     // 2. compositing adjoint -> dL/draw
     NB_TRY(nerf_b200_raw2outputs_bwd(raw, zz, ry + 3, rs, nz, nn, S, cfg->white_bkgd, g_rgb + n0 * 3, d_raw, stream));
     const float* h_last = sv.h + (size_t)(D - 1) * M * W;
-    // 3. rgb_linear (run_nerf_helpers.py:114)
-    NB_TRY(gemm_tn_any(tc, d_raw, 4, sv.hv, W2, grads->rgb_w, W2, M, 3, W2, st));
-    NB_TRY(mask_colsum(d_raw, 4, nullptr, 0, M, 3, grads->rgb_b, st));
-    NB_TRY(gemm_nn_any(tc, d_raw, 4, net->rgb_w, W2, d_hv, W2, M, W2, 3, 0, st));
-    // 4. views_linears[0] on cat([feature, input_views]) (:108-112)
-    NB_TRY(mask_colsum(d_hv, W2, sv.hv, W2, M, W2, grads->views_b, st));
-    NB_TRY(gemm_tn_any(tc, d_hv, W2, sv.feat, W, grads->views_w, W + ICV, M, W2, W, st));
-    NB_TRY(gemm_tn_any(tc, d_hv, W2, sv.encv, ICV, grads->views_w + W, W + ICV, M, W2, ICV, st));
-    NB_TRY(gemm_nn_any(tc, d_hv, W2, net->views_w, W + ICV, dh0, W, M, W, W2, 0, st));                // d_feature
-    // 5. feature_linear and alpha_linear both read the last hidden layer (:106-107)
-    NB_TRY(gemm_tn_any(tc, dh0, W, h_last, W, grads->feature_w, W, M, W, W, st));
-    NB_TRY(mask_colsum(dh0, W, nullptr, 0, M, W, grads->feature_b, st));
-    NB_TRY(gemm_tn_any(tc, d_raw + 3, 4, h_last, W, grads->alpha_w, W, M, 1, W, st));
-    NB_TRY(mask_colsum(d_raw + 3, 4, nullptr, 0, M, 1, grads->alpha_b, st));
-    NB_TRY(gemm_nn_any(tc, dh0, W, net->feature_w, W, dh1, W, M, W, W, 0, st));
-    NB_TRY(gemm_nn_any(tc, d_raw + 3, 4, net->alpha_w, W, dh1, W, M, W, 1, 1, st));
+    if (net->use_viewdirs) {
+      // 3. rgb_linear (run_nerf_helpers.py:114)
+      NB_TRY(gemm_tn(d_raw, 4, sv.hv, W2, grads->rgb_w, W2, M, 3, W2, st));
+      NB_TRY(mask_colsum(d_raw, 4, nullptr, 0, M, 3, grads->rgb_b, st));
+      NB_TRY(gemm_nn(d_raw, 4, net->rgb_w, W2, d_hv, W2, M, W2, 3, 0, st));
+      // 4. views_linears[0] on cat([feature, input_views]) (:108-112)
+      NB_TRY(mask_colsum(d_hv, W2, sv.hv, W2, M, W2, grads->views_b, st));
+      NB_TRY(gemm_tn(d_hv, W2, sv.feat, W, grads->views_w, W + ICV, M, W2, W, st));
+      NB_TRY(gemm_tn(d_hv, W2, sv.encv, ICV, grads->views_w + W, W + ICV, M, W2, ICV, st));
+      NB_TRY(gemm_nn(d_hv, W2, net->views_w, W + ICV, dh0, W, M, W, W2, 0, st));                // d_feature
+      // 5. feature_linear and alpha_linear both read the last hidden layer (:106-107)
+      NB_TRY(gemm_tn(dh0, W, h_last, W, grads->feature_w, W, M, W, W, st));
+      NB_TRY(mask_colsum(dh0, W, nullptr, 0, M, W, grads->feature_b, st));
+      NB_TRY(gemm_tn(d_raw + 3, 4, h_last, W, grads->alpha_w, W, M, 1, W, st));
+      NB_TRY(mask_colsum(d_raw + 3, 4, nullptr, 0, M, 1, grads->alpha_b, st));
+      NB_TRY(gemm_nn(dh0, W, net->feature_w, W, dh1, W, M, W, W, 0, st));
+      NB_TRY(gemm_nn(d_raw + 3, 4, net->alpha_w, W, dh1, W, M, W, 1, 1, st));
+    } else {
+      // 3'. output_linear (:117): only its first four rows ever reach the loss (run_nerf.py:187 note); rows >= 4 get zero gradient
+      NB_TRY(gemm_tn(d_raw, 4, h_last, W, grads->output_w, W, M, 4, W, st));
+      NB_TRY(mask_colsum(d_raw, 4, nullptr, 0, M, 4, grads->output_b, st));
+      NB_TRY(gemm_nn(d_raw, 4, net->output_w, W, dh1, W, M, W, 4, 0, st));
+    }
     // 6. pts_linears, last to first (:99-103); skip layer input = cat([input_pts, h])
     float* dcur = dh1;
     float* dnext = dh0;
@@ -561,13 +617,13 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
       const bool after_skip = (l > 0) && (l - 1 == net->skip);
       const int Kl = (l == 0) ? IC : (after_skip ? W + IC : W);
       if (l == 0) {
-        NB_TRY(gemm_tn_any(tc, dcur, W, sv.enc, IC, grads->pts_w[0], Kl, M, W, IC, st));
+        NB_TRY(gemm_tn(dcur, W, sv.enc, IC, grads->pts_w[0], Kl, M, W, IC, st));
       } else {
         const float* hprev = sv.h + (size_t)(l - 1) * M * W;
         const int off = after_skip ? IC : 0;
-        if (after_skip) NB_TRY(gemm_tn_any(tc, dcur, W, sv.enc, IC, grads->pts_w[l], Kl, M, W, IC, st));
-        NB_TRY(gemm_tn_any(tc, dcur, W, hprev, W, grads->pts_w[l] + off, Kl, M, W, W, st));
-        NB_TRY(gemm_nn_any(tc, dcur, W, net->pts_w[l] + off, Kl, dnext, W, M, W, W, 0, st));
+        if (after_skip) NB_TRY(gemm_tn(dcur, W, sv.enc, IC, grads->pts_w[l], Kl, M, W, IC, st));
+        NB_TRY(gemm_tn(dcur, W, hprev, W, grads->pts_w[l] + off, Kl, M, W, W, st));
+        NB_TRY(gemm_nn(dcur, W, net->pts_w[l] + off, Kl, dnext, W, M, W, W, 0, st));
         float* t = dcur; dcur = dnext; dnext = t;
       }
     }
@@ -575,122 +631,208 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
   return 0;
 }
 
-int nerf_b200_debug_set_trace(void* dev_buf_4096_i64) { g_trace = static_cast<long long*>(dev_buf_4096_i64); return 0; }
+// ---- tensor-core backward of one pass (bwd_tc2.cuh) ------------------------------------------------
+namespace {
+struct BwdTcLayout { size_t off_amax, off_draw, off_encv, off_dsum, off_partial, off_grad, total; long long part_floats; };
+struct BwdTcJobs { int n; WgradJob w[WG2_MAX_JOBS]; ReduceJob r[WG2_MAX_JOBS]; int total_ctas; long long part_floats; };
 
-int nerf_b200_debug_mma_rate(int reps, int N, int b_sw64, void* out_2_i64, void* stream) {
-  const size_t sm = 65536 + 32768 + 256 + 1024;
-  if (int rc = smem_optin((const void*)mma_rate_kernel, sm)) return rc;
-  mma_rate_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(reps, N, b_sw64, static_cast<long long*>(out_2_i64));
-  NB_LAUNCH_OK("mma_rate_kernel");
-  return 0;
+// jobs of the weight gradient and their CTA ranges (proportional to the bytes each job streams per tile)
+BwdTcJobs make_bwd_jobs(const NerfNetParams& n, const NerfNetGrads* g, int sms) {
+  BwdTcJobs J;
+  memset(&J, 0, sizeof(J));
+  const int D = n.D, W = n.W, IC = n.input_ch, ICV = n.input_ch_views;
+  auto add = [&](uint32_t a_off, int Mc, uint32_t b_off, int Nc, float* dst, int ldw, int n_valid, float* db) {
+    WgradJob& w = J.w[J.n];
+    ReduceJob& r = J.r[J.n];
+    w.a_off = a_off; w.b_off = b_off; w.Mc = Mc; w.Nc = Nc; w.db = db;
+    r.Mc = Mc; r.Nc = Nc; r.n_valid = n_valid; r.ldw = ldw; r.dst = dst;
+    ++J.n;
+  };
+  // views_linears[0].weight[:, :W] = d_hv^T feat;  feature_linear = d_feat^T h_{D-1}
+  add(0, 128, rec_act_h(D), 256, g ? g->views_w : nullptr, W + ICV, W, g ? g->views_b : nullptr);
+  add(rec_grad_step(0), 256, rec_act_h(D - 1), 256, g ? g->feature_w : nullptr, W, W, g ? g->feature_b : nullptr);
+  for (int l = D - 1; l >= 1; --l) {
+    const bool sk = (n.skip >= 0 && l == n.skip + 1);
+    add(rec_grad_dA(l, D), 256, rec_act_h(l - 1), 256, g ? g->pts_w[l] + (sk ? IC : 0) : nullptr, sk ? W + IC : W, W, g ? g->pts_b[l] : nullptr);
+    if (sk) add(rec_grad_dA(l, D), 256, 0, 64, g ? g->pts_w[l] : nullptr, W + IC, IC, nullptr);        // the [input_pts] columns
+  }
+  add(rec_grad_dA(0, D), 256, 0, 64, g ? g->pts_w[0] : nullptr, IC, IC, g ? g->pts_b[0] : nullptr);
+  double tot = 0;
+  for (int i = 0; i < J.n; ++i) tot += J.w[i].Mc + J.w[i].Nc;
+  int used = 0, big = 0;
+  for (int i = 0; i < J.n; ++i) {
+    int c = (int)((double)sms * (J.w[i].Mc + J.w[i].Nc) / tot);
+    if (c < 1) c = 1;
+    J.w[i].ncta = c;
+    used += c;
+    if (J.w[i].Mc + J.w[i].Nc > J.w[big].Mc + J.w[big].Nc) big = i;
+  }
+  for (int i = 0; used < sms; i = (i + 1) % J.n) if (J.w[i].Mc + J.w[i].Nc == J.w[big].Mc + J.w[big].Nc) { ++J.w[i].ncta; ++used; }
+  int cta = 0;
+  long long pf = 0;
+  for (int i = 0; i < J.n; ++i) {
+    J.w[i].cta0 = cta; cta += J.w[i].ncta;
+    J.w[i].part_off = pf; J.r[i].part_off = pf; J.r[i].ncta = J.w[i].ncta;
+    pf += (long long)J.w[i].ncta * J.w[i].Mc * J.w[i].Nc;
+  }
+  J.total_ctas = cta; J.part_floats = pf;
+  return J;
 }
 
-int nerf_b200_debug_epi_rate(int reps, int mode, int mma, void* out_2_i64, void* stream) {
-  const size_t sm = 65536 + 49152 + 1024 + 256 + 1024;
-  if (int rc = smem_optin((const void*)epi_rate_kernel, sm)) return rc;
-  epi_rate_kernel<<<1, 384, sm, (cudaStream_t)stream>>>(reps, mode, mma, static_cast<long long*>(out_2_i64));
-  NB_LAUNCH_OK("epi_rate_kernel");
-  return 0;
+BwdTcLayout make_bwd_layout(long long N, int S, const NerfNetParams& n, const TilePlan& plan, long long part_floats) {
+  BwdTcLayout L;
+  auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  size_t o = 0;
+  L.off_amax = o;    o = up(o + 256);
+  L.off_draw = o;    o = up(o + (size_t)N * S * 16);
+  L.off_encv = o;    o = up(o + (size_t)N * (n.input_ch_views > 0 ? n.input_ch_views : 1) * 4);
+  L.off_dsum = o;    o = up(o + (size_t)N * 128 * 4);
+  L.off_partial = o; o = up(o + (size_t)part_floats * 4);
+  L.off_grad = o;    o = up(o + (size_t)plan.n_tiles * rec_grad_bytes(n.D));
+  L.total = o; L.part_floats = part_floats;
+  return L;
+}
+}  // namespace
+
+size_t nerf_b200_march_bwd_tc_workspace_bytes(int64_t N, int S, const NerfNetParams* net) {
+  if (!net || check_tc_net(net) || !net->use_viewdirs || N <= 0 || S <= 0) return 0;
+  const int sms = num_sms();
+  const TilePlan plan = make_tile_plan(N, S, sms);
+  const BwdTcJobs J = make_bwd_jobs(*net, nullptr, sms);
+  return make_bwd_layout(N, S, *net, plan, J.part_floats).total + 1024;
 }
 
-int nerf_b200_debug_ldtm_rate(int reps, int shape, int nwarps, int mma, void* out_2_i64, void* stream) {
-  const size_t sm = 49152 + 256 + 1024;
-  if (int rc = smem_optin((const void*)ldtm_rate_kernel, sm)) return rc;
-  ldtm_rate_kernel<<<1, 384, sm, (cudaStream_t)stream>>>(reps, shape, nwarps, mma, static_cast<long long*>(out_2_i64));
-  NB_LAUNCH_OK("ldtm_rate_kernel");
-  return 0;
-}
-
-int nerf_b200_debug_issue_probe(int reps, int nmma, int flags, void* out_2_i64, void* stream) {
-  const size_t sm = 65536 + 32768 + 256 + 1024;
-  if (int rc = smem_optin((const void*)issue_probe_kernel, sm)) return rc;
-  issue_probe_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(reps, nmma, flags, static_cast<long long*>(out_2_i64));
-  NB_LAUNCH_OK("issue_probe_kernel");
-  return 0;
-}
-
-int nerf_b200_debug_l2_stream(const void* buf, int buf_bytes, int chunk, int stages, int passes, int nblocks, void* out_i64, void* stream) {
-  const size_t sm = (size_t)stages * chunk + 512 + 1024;
-  if (int rc = smem_optin((const void*)l2_stream_probe_kernel, sm)) return rc;
-  l2_stream_probe_kernel<<<nblocks, 64, sm, (cudaStream_t)stream>>>(static_cast<const uint8_t*>(buf), buf_bytes, chunk, stages, passes, static_cast<long long*>(out_i64));
-  NB_LAUNCH_OK("l2_stream_probe_kernel");
-  return 0;
-}
-
-// ---- experimental building blocks of the tensor-core backward (bwd_tc.cuh); not used by any default path ----
-int nerf_b200_exp_tile_pack(const float* src, int64_t M, int C, float scale, void* img, void* stream) {
-  NB_CHECK_ARG(src && img && M >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
-  if (M == 0) return 0;
-  const long long n = ((M + 127) / 128) * 128 * (C >> 3);
-  tile_pack_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, C, M, C, C, scale, static_cast<uint8_t*>(img));
-  NB_LAUNCH_OK("tile_pack_kernel");
-  return 0;
-}
-int nerf_b200_exp_tile_unpack(const void* img, int64_t M, int C, float scale, float* dst, void* stream) {
-  NB_CHECK_ARG(dst && img && M >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
-  if (M == 0) return 0;
-  tile_unpack_kernel<<<cdiv(M * (C >> 3), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img), M, C, scale, dst, C);
-  NB_LAUNCH_OK("tile_unpack_kernel");
-  return 0;
-}
-int nerf_b200_exp_tile_colsum(const void* img, int64_t n_tiles, int C, float scale, float* colsum, void* stream) {
-  NB_CHECK_ARG(colsum && img && n_tiles >= 0 && (C == 64 || C == 128 || C == 256), "bad arguments (C must be 64, 128 or 256)");
-  if (n_tiles == 0) return 0;
-  const int grid = (int)(n_tiles < 4 * num_sms() ? n_tiles : 4 * num_sms());
-  tile_colsum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img), n_tiles, C, scale, colsum);
-  NB_LAUNCH_OK("tile_colsum_kernel");
-  return 0;
-}
-int nerf_b200_exp_wgrad_tiles(const void* ximg, const void* yimg, int64_t n_tiles, int Mc, int Nc, float scale, float* dW, int ldw, void* stream) {
-  NB_CHECK_ARG(ximg && yimg && dW && n_tiles >= 0, "null pointer");
-  NB_CHECK_ARG((Mc == 128 || Mc == 256) && (Nc == 64 || Nc == 128 || Nc == 256) && ldw >= Nc, "unsupported shape Mc=%d Nc=%d ldw=%d", Mc, Nc, ldw);
-  if (n_tiles == 0) return 0;
-  if (int rc = smem_optin((const void*)wgrad_tiles_kernel, WG_TOTAL)) return rc;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  wgrad_tiles_kernel<<<grid, WG_THREADS, WG_TOTAL, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(ximg), static_cast<const uint8_t*>(yimg),
-                                                                                 n_tiles, Mc, Nc, scale, dW, ldw, Nc);
-  NB_LAUNCH_OK("wgrad_tiles_kernel");
-  return 0;
-}
-int nerf_b200_exp_dgrad_tiles(const void* ximg, const void* wimg, const void* himg, int64_t n_tiles, int Kc, void* oimg, void* stream) {
-  NB_CHECK_ARG(ximg && wimg && oimg && n_tiles >= 0, "null pointer");
-  NB_CHECK_ARG(Kc == 128 || Kc == 256, "unsupported reduction width Kc=%d", Kc);
-  if (n_tiles == 0) return 0;
-  if (int rc = smem_optin((const void*)dgrad_tiles_kernel, DG_TOTAL)) return rc;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  dgrad_tiles_kernel<<<grid, DG_THREADS, DG_TOTAL, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(ximg), static_cast<const uint8_t*>(wimg),
-                                                                                 static_cast<const uint8_t*>(himg), n_tiles, Kc, static_cast<uint8_t*>(oimg));
-  NB_LAUNCH_OK("dgrad_tiles_kernel");
+// introspection for tests and tools: where nerf_b200_march_bwd_tc keeps its intermediates inside the (1 KB-aligned)
+// workspace and how the tiles are laid out.  out[0..11] = off_d_raw, off_grad_records, rec_act_bytes, rec_mask_bytes,
+// rec_grad_bytes, grid, rays_per_cta, nst, n_tiles, off_amax, off_dsum, off_partial
+int nerf_b200_march_bwd_tc_layout(int64_t N, int S, const NerfNetParams* net, int64_t* out) {
+  if (int rc = check_tc_net(net)) return rc;
+  NB_CHECK_ARG(out && N > 0 && S > 0 && net->use_viewdirs, "bad arguments");
+  const int sms = num_sms();
+  const TilePlan plan = make_tile_plan(N, S, sms);
+  const BwdTcJobs J = make_bwd_jobs(*net, nullptr, sms);
+  const BwdTcLayout LY = make_bwd_layout(N, S, *net, plan, J.part_floats);
+  out[0] = (int64_t)LY.off_draw; out[1] = (int64_t)LY.off_grad; out[2] = rec_act_bytes(net->D); out[3] = rec_mask_bytes(net->D);
+  out[4] = rec_grad_bytes(net->D); out[5] = plan.grid; out[6] = plan.rays_per_cta; out[7] = plan.nst; out[8] = plan.n_tiles;
+  out[9] = (int64_t)LY.off_amax; out[10] = (int64_t)LY.off_dsum; out[11] = (int64_t)LY.off_partial;
   return 0;
 }
 
-int nerf_b200_selftest_gemm_tn(const float* X, const float* Y, float* out, int lbo_bytes, int sbo_bytes, void* stream) {
-  NB_CHECK_ARG(X && Y && out, "null pointer");
-  NB_CHECK_ARG(lbo_bytes >= 0 && sbo_bytes >= 0 && lbo_bytes % 16 == 0 && sbo_bytes % 16 == 0, "lbo / sbo must be multiples of 16 bytes");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int sm = 131072 + 256 + 1024;
-  if (int rc = smem_optin((const void*)selftest_gemm_tn_kernel, sm)) return rc;
-  selftest_gemm_tn_kernel<<<1, 128, sm, st>>>(X, Y, out, (uint32_t)lbo_bytes, (uint32_t)sbo_bytes);
-  NB_LAUNCH_OK("selftest_gemm_tn_kernel");
-  return 0;
-}
-
-int nerf_b200_selftest_gemm(const float* A, const float* W, int K, int N, float* out, void* scratch, size_t scratch_bytes, void* stream) {
-  NB_CHECK_ARG(A && W && out && scratch, "NULL pointer");
-  NB_CHECK_ARG(K % 32 == 0 && K >= 32 && K <= 256 && (N == 128 || N == 256), "bad K/N");
-  NB_CHECK_ARG(scratch_bytes >= (size_t)N * K * 2, "scratch too small");
+int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
+                           const void* packed, const NerfRenderCfg* cfg, const float* raw, const NerfTrainSave* save,
+                           const float* g_rgb, const NerfNetGrads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  NB_CHECK_ARG(rays && z_vals && net && packed && cfg && raw && save && g_rgb && grads, "NULL pointer");
+  if (int rc = check_tc_net(net)) return rc;
+  NB_CHECK_ARG(net->use_viewdirs, "the tensor-core backward serves use_viewdirs networks (exact mode serves the others)");
+  NB_CHECK_ARG(net->W == 256, "the tensor-core backward supports netwidth == 256");
+  if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  PackJob job;
-  job.n = 0;
-  for (int c = 0; c < K / 32; ++c) { PackChunk& pc = job.c[job.n++]; pc.src = W; pc.ld = K; pc.k0 = 32 * c; pc.kvalid = 32; pc.nrows = N; pc.dst_off = (unsigned)c * N * 64; }
-  dim3 grid(4, job.n);
-  pack_chunks_kernel<<<grid, 256, 0, st>>>(job, static_cast<uint8_t*>(scratch));
-  NB_LAUNCH_OK("pack_chunks_kernel");
-  const size_t sm = 65536 + 16384 + 256 + 1024;
-  if (int rc = smem_optin((const void*)selftest_gemm_kernel, sm)) return rc;
-  selftest_gemm_kernel<<<1, 128, sm, st>>>(A, static_cast<const uint8_t*>(scratch), K, N, out);
-  NB_LAUNCH_OK("selftest_gemm_kernel");
+  DeviceState* ds = device_state();
+  const int sms = ds->sms, D = net->D, rs = cfg->ray_stride;
+  const TilePlan plan = make_tile_plan(N, S, sms);
+  BwdTcJobs J = make_bwd_jobs(*net, grads, sms);
+  const BwdTcLayout LY = make_bwd_layout(N, S, *net, plan, J.part_floats);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  NB_CHECK_ARG(workspace && workspace_bytes >= LY.total + (size_t)(ws - static_cast<uint8_t*>(workspace)), "march_bwd_tc workspace too small (%zu < %zu)", workspace_bytes, LY.total + 1024);
+  NB_CHECK_ARG(save->act && save->mask && save->act_bytes >= (size_t)plan.n_tiles * rec_act_bytes(D) && save->mask_bytes >= (size_t)plan.n_tiles * rec_mask_bytes(D),
+               "training-mode records missing or too small");
+  const PackLayout PL = make_pack_layout(*net);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  unsigned int* amax = reinterpret_cast<unsigned int*>(ws + LY.off_amax);
+  float* d_raw = reinterpret_cast<float*>(ws + LY.off_draw);
+  float* encv = reinterpret_cast<float*>(ws + LY.off_encv);
+  float* dsum = reinterpret_cast<float*>(ws + LY.off_dsum);
+  float* partial = reinterpret_cast<float*>(ws + LY.off_partial);
+  uint8_t* grec = ws + LY.off_grad;
+  const uint8_t* act = static_cast<const uint8_t*>(save->act);
+  const uint8_t* mask = static_cast<const uint8_t*>(save->mask);
+  if (!ds->optin_bwd) {
+    NB_TRY(smem_optin((const void*)dgrad_tc2_kernel, SM_ALLOC));
+    NB_TRY(smem_optin((const void*)wgrad_tc_kernel, WG2_TOTAL));
+    ds->optin_bwd = true;
+  }
+  // 1. loss scale from max |dL/drgb_map|; compositing adjoint -> dL/draw
+  NB_CUDA(cudaMemsetAsync(amax, 0, 256, st));
+  NB_CUDA(cudaMemsetAsync(dsum, 0, (size_t)N * 128 * 4, st));
+  absmax_kernel<<<cdiv(N * 3, 1024) < 64 ? cdiv(N * 3, 1024) : 64, 256, 0, st>>>(g_rgb, N * 3, amax);
+  NB_LAUNCH_OK("absmax_kernel");
+  NB_TRY(nerf_b200_raw2outputs_bwd(raw, z_vals, rays + 3, rs, noise, N, S, cfg->white_bkgd, g_rgb, d_raw, stream));
+  // 2. seed of the chain: d_hv tiles
+  SeedParams sp;
+  sp.d_raw = d_raw; sp.mask = mask; sp.grad = grec; sp.rgb_w = net->rgb_w; sp.amax = amax;
+  sp.N = N; sp.S = S; sp.rays_per_cta = plan.rays_per_cta; sp.nst_plan = plan.nst; sp.D = D;
+  sp.rec_mask = rec_mask_bytes(D); sp.rec_grad = rec_grad_bytes(D); sp.n_tiles = plan.n_tiles;
+  dhv_seed_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(sp);
+  NB_LAUNCH_OK("dhv_seed_kernel");
+  // 3. dgrad chain (CTA pairs, the forward's tile order)
+  const long long rows = N * (long long)S;
+  {
+    DgradParams dp;
+    dp.mask = mask; dp.grad = grec; dp.d_raw = d_raw; dp.amax = amax; dp.alpha_w = net->alpha_w;
+    dp.N = N; dp.S = S; dp.rays_per_cta = plan.rays_per_cta; dp.nst_plan = plan.nst; dp.D = D;
+    dp.rec_mask = rec_mask_bytes(D); dp.rec_grad = rec_grad_bytes(D);
+    dp.pair_half_bytes = PL.bwd_bytes / 2;
+    CUtensorMap wmap, gmap;
+    NB_TRY(make_row_map(&wmap, pk + PL.off_bwd_pair, PL.bwd_bytes, 16));
+    NB_TRY(make_row_map(&gmap, grec, (size_t)plan.n_tiles * rec_grad_bytes(D), 64));
+    TimedLaunch* tl = nullptr;
+    if (g_timing && g_ntimed < 4096) {
+      tl = &g_timed[g_ntimed++];
+      cudaEventCreate(&tl->a); cudaEventCreate(&tl->b);
+      tl->flops = 2.0 * ((double)(net->W / 2) * net->W + (double)D * net->W * net->W) * (double)rows;
+      tl->kind = 1;
+      cudaEventRecord(tl->a, st);
+    }
+    dgrad_tc2_kernel<<<plan.grid, TC_THREADS, SM_ALLOC, st>>>(dp, wmap, gmap);
+    if (tl) cudaEventRecord(tl->b, st);
+    NB_LAUNCH_OK("dgrad_tc2_kernel");
+  }
+  // 4. weight gradients (layer-major) + bias gradients, then the reduction of the per-CTA partial blocks
+  {
+    WgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.act = act; wp.grad = grec; wp.rec_act = rec_act_bytes(D); wp.rec_grad = rec_grad_bytes(D);
+    wp.N = N; wp.S = S; wp.rays_per_cta = plan.rays_per_cta; wp.nst_plan = plan.nst; wp.n_tiles = plan.n_tiles;
+    wp.amax = amax; wp.partial = partial; wp.njobs = J.n;
+    for (int i = 0; i < J.n; ++i) wp.jobs[i] = J.w[i];
+    TimedLaunch* tl = nullptr;
+    if (g_timing && g_ntimed < 4096) {
+      tl = &g_timed[g_ntimed++];
+      cudaEventCreate(&tl->a); cudaEventCreate(&tl->b);
+      tl->flops = 2.0 * (net_macs_per_row(*net) - (double)net->W - 3.0 * (net->W / 2) - (double)net->input_ch_views * (net->W / 2)) * (double)rows;
+      tl->kind = 2;
+      cudaEventRecord(tl->a, st);
+    }
+    wgrad_tc_kernel<<<J.total_ctas, WG2_THREADS, WG2_TOTAL, st>>>(wp);
+    if (tl) cudaEventRecord(tl->b, st);
+    NB_LAUNCH_OK("wgrad_tc_kernel");
+    ReduceParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.partial = partial; rp.amax = amax; rp.njobs = J.n;
+    for (int i = 0; i < J.n; ++i) rp.jobs[i] = J.r[i];
+    dim3 rg(256, J.n);
+    wgrad_reduce_kernel<<<rg, 256, 0, st>>>(rp);
+    NB_LAUNCH_OK("wgrad_reduce_kernel");
+  }
+  // 5. the small heads: rgb_linear, alpha_linear, the view columns of views_linears[0]
+  {
+    const int ICV = net->input_ch_views;
+    encv_kernel<<<cdiv(N * ICV, 256), 256, 0, st>>>(rays + 8, rs, N, ICV, encv);
+    NB_LAUNCH_OK("encv_kernel");
+    HeadGradParams hp;
+    hp.act = act; hp.grad = grec; hp.d_raw = d_raw; hp.amax = amax;
+    hp.N = N; hp.S = S; hp.rays_per_cta = plan.rays_per_cta; hp.nst_plan = plan.nst; hp.D = D;
+    hp.rec_act = rec_act_bytes(D); hp.rec_grad = rec_grad_bytes(D); hp.n_tiles = plan.n_tiles;
+    hp.rgb_w = grads->rgb_w; hp.rgb_b = grads->rgb_b; hp.alpha_w = grads->alpha_w; hp.alpha_b = grads->alpha_b; hp.dsum = dsum;
+    head_grads_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(hp);
+    NB_LAUNCH_OK("head_grads_kernel");
+    dim3 vg(ICV, cdiv(N, 512));
+    views_enc_wgrad_kernel<<<vg, 128, 0, st>>>(dsum, encv, N, ICV, grads->views_w, net->W + ICV, net->W);
+    NB_LAUNCH_OK("views_enc_wgrad_kernel");
+  }
   return 0;
 }
+
+int nerf_b200_debug_set_trace(void* dev_buf_4096_i64) { g_trace = static_cast<long long*>(dev_buf_4096_i64); return 0; }
 
 }  // extern "C"

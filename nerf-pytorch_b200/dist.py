@@ -67,13 +67,14 @@ def broadcast_params(params, src: int = 0, group=None):
     params = list(params)
     if dist.get_world_size(group) == 1 or not params:
         return
-    flat = torch.cat([p.data.reshape(-1) for p in params])
-    dist.broadcast(flat, src=src, group=group)
-    off = 0
-    for p in params:
-        n = p.numel()
-        p.data.copy_(flat[off:off + n].view_as(p.data))
-        off += n
+    with torch.no_grad():
+        flat = torch.cat([p.reshape(-1) for p in params])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.copy_(flat[off:off + n].view_as(p))        # in-place on the Parameter: bumps its version -> NeRF.packed() re-packs
+            off += n
 
 
 def render_sharded(render_fn, rays: torch.Tensor, gather: bool = True, **kw):

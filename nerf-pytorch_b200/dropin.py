@@ -14,8 +14,10 @@ import torch
 
 from . import api
 
+# get_rays / ndc_rays / get_rays_np stay the reference's own (per-image glue of train(), run_nerf.py:677-757; inside render()
+# the same arithmetic is nerf_b200_pack_rays).
 PATCHED = ["render", "render_rays", "batchify_rays", "batchify", "run_network", "raw2outputs", "create_nerf",
-           "sample_pdf", "get_embedder", "Embedder", "NeRF", "get_rays", "ndc_rays"]
+           "sample_pdf", "get_embedder", "Embedder", "NeRF"]
 
 
 def patch(module, set_default_device=True):

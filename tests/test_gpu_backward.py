@@ -1,5 +1,6 @@
-"""Gradient parity: dL/dtheta of all 48 parameter tensors through render_rays (loss = mse(rgb_map) + mse(rgb0),
-run_nerf.py:765-772) vs the reference's autograd (golden fixtures) and vs the oracle's hand-derived adjoint."""
+"""Gradient parity of the EXACT backward (fp32 CUDA-core recompute, set_backward('exact')): dL/dtheta of all 48 parameter
+tensors through render_rays (loss = mse(rgb_map) + mse(rgb0), run_nerf.py:765-772) vs the reference's autograd (golden
+fixtures) and vs the oracle's hand-derived adjoint.  The tensor-core backward is covered by tests/test_gpu_train.py."""
 import numpy as np
 import pytest
 import torch
@@ -19,6 +20,7 @@ def grads_for(G, fx, prec):
     nets = [G.make_net(G.synth.nerf_state(int(fx["seed_w"]), bool(fx["sharpen"]))),
             G.make_net(G.synth.nerf_state(int(fx["seed_w"]) + 1, bool(fx["sharpen"])))]
     G.nb.set_precision(prec)
+    G.nb.set_backward("exact")
     try:
         rgb, disp, acc, ex = G.nb.render(int(fx["H"]), int(fx["W"]), fx["K"], chunk=32768, rays=G.dev(fx["rays"]), ndc=False,
                                          near=2., far=6., use_viewdirs=True, network_fn=nets[0], network_fine=nets[1],
@@ -30,6 +32,7 @@ def grads_for(G, fx, prec):
         loss.backward()
     finally:
         G.nb.set_precision("tc_fp16")
+        G.nb.set_backward("tc")
     return float(loss.item()), nets
 
 

@@ -20,14 +20,14 @@ def G():
 def test_tcgen05_selftest_gemm(G, K, N):
     """Operand layouts (128B-swizzled A written by threads, 64B-swizzled weight chunks via bulk copy),
     UMMA descriptors and TMEM loads: D = fp16(A) fp16(W)^T with fp32 accumulation."""
-    lib = G._lib.load()
+    lib = G._lib.load_dev()
     rng = np.random.default_rng(K * 1000 + N)
     A = rng.standard_normal((128, K)).astype(np.float32)
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     a, w = G.dev(A), G.dev(W)
     out = torch.zeros((128, N), device=G.DEV)
     scratch = torch.zeros(N * K * 2, dtype=torch.uint8, device=G.DEV)
-    G._lib.check(lib.nerf_b200_selftest_gemm(G.ptr(a), G.ptr(w), K, N, G.ptr(out), G.ptr(scratch), scratch.numel(), G.stream()), "selftest")
+    G._lib.check_dev(lib.nerf_b200_selftest_gemm(G.ptr(a), G.ptr(w), K, N, G.ptr(out), G.ptr(scratch), scratch.numel(), G.stream()), "selftest")
     torch.cuda.synchronize()
     ref = A.astype(np.float16).astype(np.float64) @ W.astype(np.float16).astype(np.float64).T
     err = np.abs(out.cpu().numpy() - ref).max()
@@ -37,13 +37,13 @@ def test_tcgen05_selftest_gemm(G, K, N):
 def test_tcgen05_selftest_gemm_tn(G):
     """MN-major operands straight from the activation layout (the weight-gradient GEMM's access pattern):
     out[256,256] = fp16(X)^T fp16(Y) over 128 sample rows, LBO = K-block stride, SBO = 8-row group stride."""
-    lib = G._lib.load()
+    lib = G._lib.load_dev()
     rng = np.random.default_rng(11)
     X = rng.standard_normal((128, 256)).astype(np.float32)
     Y = rng.standard_normal((128, 256)).astype(np.float32)
     x, y = G.dev(X), G.dev(Y)
     out = torch.zeros((256, 256), device=G.DEV)
-    G._lib.check(lib.nerf_b200_selftest_gemm_tn(G.ptr(x), G.ptr(y), G.ptr(out), 16384, 1024, G.stream()), "selftest_tn")
+    G._lib.check_dev(lib.nerf_b200_selftest_gemm_tn(G.ptr(x), G.ptr(y), G.ptr(out), 16384, 1024, G.stream()), "selftest_tn")
     torch.cuda.synchronize()
     ref = X.astype(np.float16).astype(np.float64).T @ Y.astype(np.float16).astype(np.float64)
     assert rel_l2(out.cpu().numpy(), ref) < 1e-5

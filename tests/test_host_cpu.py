@@ -142,10 +142,11 @@ def _cuobjdump(*args):
 
 
 def test_built_kernels_use_blackwell_tensor_and_tma_instructions(nb):
-    """Static evidence in the cross-compiled sm_100a SASS (no GPU needed): the default fused kernel issues
-    cta_group::2 tcgen05.mma, loads weights with tensor-map TMA, reads accumulators with tcgen05.ld and commits through
-    multicast mbarrier arrives; the superseded single-CTA kernel uses the cta_group::1 forms.  Guards against a silent
-    regression to mma.sync / plain loads."""
+    """Static evidence in the cross-compiled sm_100a SASS (no GPU needed): the fused forward (inference and training
+    instantiations) and the dgrad chain issue cta_group::2 tcgen05.mma, load weights with tensor-map TMA, read
+    accumulators with tcgen05.ld and commit through multicast mbarrier arrives; the training-mode forward and the dgrad
+    chain copy their tiles out with bulk stores; the weight-gradient kernel issues tcgen05.mma on bulk-loaded tiles.
+    Guards against a silent regression to mma.sync / plain loads."""
     sass = _cuobjdump("-sass")
     funcs = {}
     cur = None
@@ -159,27 +160,30 @@ def test_built_kernels_use_blackwell_tensor_and_tma_instructions(nb):
         names = [k for k in funcs if sub in k]
         assert len(names) == 1, (sub, names)
         return "\n".join(funcs[names[0]])
-    pair, single = body("march_tc2_kernel"), body("march_tc_kernel")
+    infer, train, dgrad, wgrad = body("march_tc2_kernelILb0"), body("march_tc2_kernelILb1"), body("dgrad_tc2_kernel"), body("wgrad_tc_kernel")
     for mnem in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "LDTM.x32", "UTCBAR.2CTA.MULTICAST", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "ELECT", "F2FP.RELU"):
-        assert mnem in pair, mnem
-    for mnem in ("UTCHMMA", "UBLKCP", "LDTM.x32", "UTCBAR", "ELECT"):
-        assert mnem in single, mnem
-    assert "HMMA.16816" not in pair and "HMMA.16816" not in single          # no mma.sync path
-    assert "UTCHMMA" in body("selftest_gemm_tn_kernel")
+        assert mnem in infer and mnem in train, mnem
+    for mnem in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "LDTM.x32", "UTCBAR.2CTA.MULTICAST", "ELECT", "F2FP.SATFINITE", "UBLKCP.G.S"):
+        assert mnem in dgrad, mnem
+    assert "UBLKCP.G.S" in train and "UBLKCP.G.S" not in infer          # shared -> global bulk stores: training mode only
+    for mnem in ("UTCHMMA", "UBLKCP", "LDTM.x32", "UTCBAR"):
+        assert mnem in wgrad, mnem
+    for b in (infer, train, dgrad, wgrad):
+        assert "HMMA.16816" not in b                                    # no mma.sync path
 
 
 def test_fused_kernels_fit_their_resource_budget(nb):
-    """640 threads x 96 registers is the whole register file (allocation granularity: 4 warps); the fused kernels must
-    not exceed it, and their spill stack stays small (sincosf slow path + the deferred raw values)."""
+    """640 threads x 96 registers is the whole register file; the fused kernels must not exceed it, and their spill
+    stack stays small (sincosf slow path + the deferred raw values)."""
     usage = _cuobjdump("-res-usage")
     found = {}
     lines = usage.splitlines()
     for i, ln in enumerate(lines):
-        m = re.search(r"Function (\S*march_tc2?_kernel\S*):", ln)
+        m = re.search(r"Function (\S*(?:march_tc2|dgrad_tc2)_kernel\S*):", ln)
         if m and i + 1 < len(lines):
             r = re.search(r"REG:(\d+) STACK:(\d+)", lines[i + 1])
             found[m.group(1)] = (int(r.group(1)), int(r.group(2)))
-    assert len(found) == 2, found
+    assert len(found) == 3, found
     for name, (reg, stack) in found.items():
         assert reg <= 96, (name, reg)
         assert stack <= 160, (name, stack)

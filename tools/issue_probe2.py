@@ -2,7 +2,7 @@ import ctypes as C, os, sys, torch
 sys.path.insert(0, os.getcwd())
 import __graft_entry__ as ge; ge.build()
 from nerf_pytorch_b200 import _lib
-lib = _lib.load(); dev = torch.device("cuda:0")
+lib = _lib.load_dev(); dev = torch.device("cuda:0")
 out = torch.zeros(2, dtype=torch.int64, device=dev)
 reps = 256
 for nmma in (2, 4, 8):

@@ -2,7 +2,7 @@ import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge; ge.build()
 from nerf_pytorch_b200 import _lib
-lib = _lib.load(); dev = torch.device("cuda:0")
+lib = _lib.load_dev(); dev = torch.device("cuda:0")
 buf = torch.zeros(1179648, dtype=torch.uint8, device=dev)       # the packed weight stream size (1152 KB)
 out = torch.zeros(256, dtype=torch.int64, device=dev)
 for nb in (148, 74, 16, 1):

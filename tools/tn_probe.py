@@ -5,7 +5,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge; ge.build()
 from nerf_pytorch_b200 import _lib
-lib = _lib.load(); dev = torch.device("cuda:0")
+lib = _lib.load_dev(); dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 X = torch.randn(128, 256, generator=g); Y = torch.randn(128, 256, generator=g)
 ref = (X.half().double().T @ Y.half().double()).numpy()
