@@ -214,6 +214,16 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
                         size_t workspace_bytes, void* stream);
 size_t nerf_b200_march_bwd_workspace_bytes(int64_t N, int S, const NerfNetParams* net);
 
+/* ---- the two ends of the optimisation step (csrc/train_step.cuh) ------------------------------
+ *      mse_seed : img2mse (run_nerf_helpers.py:9; run_nerf.py:764-772): *loss_accum += mean((rgb - target)^2) and
+ *                 g_rgb = 2 (rgb - target) / (3 N) * grad_scale  (grad_scale = 1 / world_size under data parallelism)
+ *      adam_step: torch.optim.Adam(betas, eps) (run_nerf.py:207, :776) over one flat fp32 parameter buffer, with the
+ *                 reference's learning-rate decay (run_nerf.py:778-783) evaluated on the device; state = float[4]:
+ *                 [1] = steps taken so far, [2] = rate of the last step.  grads are multiplied by grad_mul first. ---- */
+int nerf_b200_mse_seed(const float* rgb, const float* target, int64_t N, float grad_scale, float* g_rgb, float* loss_accum, void* stream);
+int nerf_b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                        float lr0, float decay_rate, float decay_steps, float beta1, float beta2, float eps, float grad_mul, void* stream);
+
 /* ---- debug hook (NERF_B200_TRACE builds only; a no-op otherwise): clock64 trace of CTA 0 into a device
  *      buffer of 4096 int64 (NULL disables) ---------------------------------------------------------------- */
 int nerf_b200_debug_set_trace(void* dev_buf_4096_i64);

@@ -95,6 +95,9 @@ SIGNATURES = {
     "nerf_b200_march_bwd": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, C.POINTER(NerfNetParams), c_fp,
                                       C.POINTER(NerfRenderCfg), c_fp, C.POINTER(NerfNetGrads), c_fp, C.c_size_t, c_fp]),
     "nerf_b200_march_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.POINTER(NerfNetParams)]),
+    "nerf_b200_mse_seed": (C.c_int, [c_fp, c_fp, C.c_int64, C.c_float, c_fp, c_fp, c_fp]),
+    "nerf_b200_adam_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, c_fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, c_fp]),
     "nerf_b200_timing_enable": (C.c_int, [C.c_int]),
     "nerf_b200_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "nerf_b200_timing_read_kinds": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

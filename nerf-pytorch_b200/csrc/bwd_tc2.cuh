@@ -18,7 +18,8 @@
 //                        its tiles (256 x 256 fp32 = all 512 columns) and leaves the SM once; bias gradients are the
 //                        column sums of the dA tiles while they sit in shared memory.
 //   wgrad_reduce_kernel  sums the per-CTA partial dW, un-scales, adds into the gradient tensors
-//   head_grads_kernel    rgb_linear / alpha_linear gradients and per-ray row sums of d_hv (CUDA cores, tiny)
+//   head_grads_kernel    rgb_linear gradients (CUDA cores, tiny); alpha_linear's and the per-ray row sums of d_hv are computed
+//                        by the wgrad kernel's spare warps from the tiles it streams anyway
 //   views_enc_wgrad_kernel  views_linears[0].weight[:, W:] from the per-ray sums and gamma(viewdir)
 //
 // TMEM capacity is what shapes this: one layer's dW fills an SM's tensor memory, so the weight gradient cannot share
@@ -384,7 +385,7 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
 // 192 threads: warps 0-3 column sums (bias gradient) while streaming, then the TMEM epilogue; warp 4 producer; warp 5 issuer.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int WG2_THREADS = 192, WG2_NSTAGE = 3, WG2_MAX_JOBS = 16;
-constexpr uint32_t WG2_STAGE = 65536, WG2_BARS = WG2_NSTAGE * WG2_STAGE, WG2_TOTAL = WG2_BARS + 128;
+constexpr uint32_t WG2_STAGE = 65536, WG2_BARS = WG2_NSTAGE * WG2_STAGE, WG2_DSIG = WG2_BARS + 128, WG2_TOTAL = WG2_DSIG + WG2_NSTAGE * 256;
 
 struct WgradJob {
   uint32_t a_off, b_off;        // image offsets inside the gradient / activation record
@@ -392,11 +393,14 @@ struct WgradJob {
   int cta0, ncta;               // CTA range serving this job
   float* db;                    // bias gradient (fp32, += scaled column sums of A) or NULL
   long long part_off;           // float offset of this job's partial blocks [ncta][Mc][Nc]
+  int aux;                      // 1: A = d_hv  -> per-ray row sums into aux_dst [N,128] (view columns of views_linears[0])
+                                // 2: B = h_{D-1} -> aux_dst[c] += sum_rows d_sigma[row] B[row][c]  (alpha_linear.weight), aux_b += sum d_sigma
+  float* aux_dst; float* aux_b;
 };
 struct WgradParams {
   const uint8_t* act; const uint8_t* grad; uint32_t rec_act, rec_grad;
   long long N; int S, rays_per_cta, nst_plan; long long n_tiles;
-  const unsigned int* amax; float* partial; int njobs;
+  const unsigned int* amax; float* partial; const float* d_raw; int njobs;
   WgradJob jobs[WG2_MAX_JOBS];
 };
 
@@ -474,30 +478,81 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
       if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
     }
   } else {
-    // warps 0-3: bias gradient = column sums of the A half tiles, then the accumulator epilogue
+    // warps 0-3: while the tiles stream through shared memory -- bias gradient = column sums of the A half tiles; job
+    // extras (aux): per-ray row sums of d_hv, or alpha_linear's weight gradient from the B tile; then the accumulator epilogue
     uint32_t s = 0, ph = 0;
     const int tid = threadIdx.x;                        // 0..127: columns 2 tid, 2 tid + 1
     const bool do_sum = (job.db != nullptr) && (2 * tid < job.Mc);
     const int c = 2 * tid;
     const uint32_t coff = (uint32_t)((c >> 6) * 8192 + (c & 7) * 2), cc = (uint32_t)((c & 63) >> 3);
-    float s0 = 0.f, s1 = 0.f;
-    for (long long i = 0; i < my_halves; ++i) {
-      ptx::mbar_wait(bar_full + 8 * s, ph);
-      if (do_sum) {
-        const uint32_t base = sb + s * WG2_STAGE + coff;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
-          const __half2 hh = *reinterpret_cast<const __half2*>(&w);
-          s0 += __low2float(hh); s1 += __high2float(hh);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
-      if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
-    }
     const float inv = 1.0f / loss_scale_from_absmax(__uint_as_float(*p.amax));
+    float* s_dsig = reinterpret_cast<float*>(smem + WG2_DSIG);
+    float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, bsum = 0.f;
+    for (long long t = g; t < p.n_tiles; t += G) {
+      if (!plan_tile_valid(p, t)) continue;
+      const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
+      const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
+      const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
+      for (int h = 0; h < 2; ++h) {
+        const int lr0 = st * 256 + X * 128 + h * 64;
+        if (job.aux == 2) {                             // d_sigma of this half tile's rows -> shared memory
+          if (tid < 64) {
+            const float v = (lr0 + tid < nrows) ? p.d_raw[(row_begin + lr0 + tid) * 4 + 3] : 0.f;
+            s_dsig[s * 64 + tid] = v;
+            bsum += v;
+          }
+          ptx::named_bar_sync(1, 128);
+        }
+        ptx::mbar_wait(bar_full + 8 * s, ph);
+        if (do_sum) {
+          const uint32_t base = sb + s * WG2_STAGE + coff;
+          if (job.aux == 1) {
+            long long ray = (row_begin + lr0) / p.S;
+            int left = (int)((ray + 1) * p.S - (row_begin + lr0));
+            float r0 = 0.f, r1 = 0.f;
+#pragma unroll 4
+            for (int r = 0; r < 64; ++r) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
+              const __half2 hh = *reinterpret_cast<const __half2*>(&w);
+              const float x0 = __low2float(hh), x1 = __high2float(hh);
+              s0 += x0; s1 += x1; r0 += x0; r1 += x1;
+              if (--left == 0 || r == 63) {
+                if (ray < p.N && lr0 + r < nrows) { atomicAdd(job.aux_dst + ray * 128 + c, r0 * inv); atomicAdd(job.aux_dst + ray * 128 + c + 1, r1 * inv); }
+                r0 = r1 = 0.f; ++ray; left = p.S;
+              }
+            }
+          } else {
+#pragma unroll 8
+            for (int r = 0; r < 64; ++r) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
+              const __half2 hh = *reinterpret_cast<const __half2*>(&w);
+              s0 += __low2float(hh); s1 += __high2float(hh);
+            }
+          }
+        }
+        if (job.aux == 2) {                             // B half tile (h_{D-1}, 256 columns): columns 2 tid, 2 tid + 1
+          const uint32_t base = sb + s * WG2_STAGE + ybase + coff;
+          const float* ds = s_dsig + s * 64;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
+            const __half2 hh = *reinterpret_cast<const __half2*>(&w);
+            const float d = ds[r];
+            a0 = fmaf(d, __low2float(hh), a0); a1 = fmaf(d, __high2float(hh), a1);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
+        if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
+      }
+    }
+    if (job.aux == 2 && my_halves > 0) {
+      atomicAdd(job.aux_dst + c, a0); atomicAdd(job.aux_dst + c + 1, a1);
+      if (tid < 64) { bsum = warp_sum(bsum); if (lane == 0) atomicAdd(job.aux_b, bsum); }
+    }
     if (do_sum && my_halves > 0) { atomicAdd(job.db + c, s0 * inv); atomicAdd(job.db + c + 1, s1 * inv); }
     float* part = p.partial + job.part_off + (size_t)g * job.Mc * job.Nc;
     if (my_halves > 0) {
@@ -544,55 +599,57 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// small head gradients on CUDA cores, tile by tile:
-//   rgb_linear.weight[j][c] += sum_rows d_rgb[row][j] hv[row][c],  rgb_linear.bias[j] += sum d_rgb[row][j]
-//   alpha_linear.weight[c]  += sum_rows d_sigma[row] h_{D-1}[row][c],  alpha_linear.bias += sum d_sigma
-//   dsum[ray][c]            += sum over the ray's rows of d_hv[row][c] / scale      (views_linears view-columns, below)
+// rgb_linear gradients on CUDA cores (3 x 128 outputs: too small for the tensor pipe), tile by tile:
+//   rgb_linear.weight[j][c] += sum_rows d_rgb[row][j] hv[row][c],   rgb_linear.bias[j] += sum_rows d_rgb[row][j]
+// One warp per row (a 256-byte hv row = 32 lanes x 4 columns), 8 rows in flight per block; the other small heads
+// (alpha_linear, the view columns of views_linears[0]) ride along in the wgrad kernel, whose tiles already hold their operands.
 // ---------------------------------------------------------------------------------------------------------------
 struct HeadGradParams {
-  const uint8_t* act; const uint8_t* grad; const float* d_raw; const unsigned int* amax;
-  long long N; int S, rays_per_cta, nst_plan, D; uint32_t rec_act, rec_grad; long long n_tiles;
-  float* rgb_w; float* rgb_b; float* alpha_w; float* alpha_b; float* dsum;
+  const uint8_t* act; const float* d_raw;
+  long long N; int S, rays_per_cta, nst_plan, D; uint32_t rec_act; long long n_tiles;
+  float* rgb_w; float* rgb_b;
 };
 
 __global__ void __launch_bounds__(256) head_grads_kernel(const HeadGradParams p) {
-  __shared__ float4 s_d[128];
-  const int c = threadIdx.x;
-  const float inv = 1.0f / loss_scale_from_absmax(__uint_as_float(*p.amax));
-  float a_w = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  __shared__ float s_acc[8][12 * 32 + 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane * 4;
+  float a[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) a[i] = 0.f;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f;
   for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
     const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
     const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
     const int lr0 = st * 256 + X * 128;
-    if (lr0 >= nrows) continue;                         // (uniform) no valid row in this tile
+    if (lr0 >= nrows) continue;
     const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
     const int nv = (nrows - lr0 < 128) ? nrows - lr0 : 128;
-    __syncthreads();
-    if (c < 128) s_d[c] = (c < nv) ? reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const uint8_t* arec = p.act + (size_t)t * p.rec_act;
-    const uint8_t* grec = p.grad + (size_t)t * p.rec_grad;
-    const uint8_t* h_last = arec + rec_act_h(p.D - 1);
-    for (int r = 0; r < nv; ++r) a_w = fmaf(s_d[r].w, __half2float(*reinterpret_cast<const __half*>(h_last + img_off(r, c))), a_w);
-    if (c < 128) {
-      const uint8_t* hv = arec + rec_act_hv(p.D);
-      long long ray = (row_begin + lr0) / p.S;
-      int left = (int)((ray + 1) * p.S - (row_begin + lr0));      // rows of `ray` that remain from this tile's first row
-      float run = 0.f;
-      for (int r = 0; r < nv; ++r) {
-        const float h = __half2float(*reinterpret_cast<const __half*>(hv + img_off(r, c)));
-        const float4 d = s_d[r];
-        r0 = fmaf(d.x, h, r0); r1 = fmaf(d.y, h, r1); r2 = fmaf(d.z, h, r2);
-        run += __half2float(*reinterpret_cast<const __half*>(grec + img_off(r, c)));
-        if (--left == 0 || r == nv - 1) { atomicAdd(p.dsum + ray * 128 + c, run * inv); run = 0.f; ++ray; left = p.S; }
-      }
-    } else if (c == 128) {
-      for (int r = 0; r < nv; ++r) { b0 += s_d[r].x; b1 += s_d[r].y; b2 += s_d[r].z; b3 += s_d[r].w; }
+    const uint8_t* hv = p.act + (size_t)t * p.rec_act + rec_act_hv(p.D);
+#pragma unroll 4
+    for (int r = warp; r < nv; r += 8) {
+      const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + r];
+      const uint2 w = *reinterpret_cast<const uint2*>(hv + img_off(r, c));
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&w.x), h23 = *reinterpret_cast<const __half2*>(&w.y);
+      const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = fmaf(d.x, h[i], a[i]); a[4 + i] = fmaf(d.y, h[i], a[4 + i]); a[8 + i] = fmaf(d.z, h[i], a[8 + i]); }
+      b0 += d.x; b1 += d.y; b2 += d.z;
     }
   }
-  atomicAdd(p.alpha_w + c, a_w);
-  if (c < 128) { atomicAdd(p.rgb_w + c, r0); atomicAdd(p.rgb_w + 128 + c, r1); atomicAdd(p.rgb_w + 256 + c, r2); }
-  if (c == 128) { atomicAdd(p.rgb_b, b0); atomicAdd(p.rgb_b + 1, b1); atomicAdd(p.rgb_b + 2, b2); atomicAdd(p.alpha_b, b3); }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) s_acc[warp][i * 32 + lane] = a[i];
+  if (lane == 0) { s_acc[warp][384] = b0; s_acc[warp][385] = b1; s_acc[warp][386] = b2; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 387; i += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_acc[w][i];
+    if (i < 384) {                                      // i = (j * 4 + k) * 32 + lane  ->  weight[j][lane * 4 + k]
+      const int j = i / 128, k = (i / 32) & 3, ln = i & 31;
+      atomicAdd(p.rgb_w + j * 128 + ln * 4 + k, v);
+    } else atomicAdd(p.rgb_b + (i - 384), v);
+  }
 }
 
 // views_linears[0].weight[c][W + e] += sum_rays dsum[ray][c] * gamma(viewdir_ray)[e]      (run_nerf_helpers.py:108-110)

@@ -7,6 +7,7 @@
 #include "fused_tc.cuh"
 #include "fused_tc2.cuh"
 #include "bwd_tc2.cuh"
+#include "train_step.cuh"
 #include <stdlib.h>
 
 namespace nb {
@@ -644,7 +645,7 @@ BwdTcJobs make_bwd_jobs(const NerfNetParams& n, const NerfNetGrads* g, int sms) 
   auto add = [&](uint32_t a_off, int Mc, uint32_t b_off, int Nc, float* dst, int ldw, int n_valid, float* db) {
     WgradJob& w = J.w[J.n];
     ReduceJob& r = J.r[J.n];
-    w.a_off = a_off; w.b_off = b_off; w.Mc = Mc; w.Nc = Nc; w.db = db;
+    w.a_off = a_off; w.b_off = b_off; w.Mc = Mc; w.Nc = Nc; w.db = db; w.aux = 0; w.aux_dst = nullptr; w.aux_b = nullptr;
     r.Mc = Mc; r.Nc = Nc; r.n_valid = n_valid; r.ldw = ldw; r.dst = dst;
     ++J.n;
   };
@@ -731,6 +732,8 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
   const int sms = ds->sms, D = net->D, rs = cfg->ray_stride;
   const TilePlan plan = make_tile_plan(N, S, sms);
   BwdTcJobs J = make_bwd_jobs(*net, grads, sms);
+  J.w[0].aux = 1;                                   // views job: per-ray row sums of d_hv (aux_dst set below)
+  J.w[1].aux = 2; J.w[1].aux_dst = grads->alpha_w; J.w[1].aux_b = grads->alpha_b;   // feature job: alpha_linear gradients
   const BwdTcLayout LY = make_bwd_layout(N, S, *net, plan, J.part_floats);
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   NB_CHECK_ARG(workspace && workspace_bytes >= LY.total + (size_t)(ws - static_cast<uint8_t*>(workspace)), "march_bwd_tc workspace too small (%zu < %zu)", workspace_bytes, LY.total + 1024);
@@ -793,7 +796,8 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     memset(&wp, 0, sizeof(wp));
     wp.act = act; wp.grad = grec; wp.rec_act = rec_act_bytes(D); wp.rec_grad = rec_grad_bytes(D);
     wp.N = N; wp.S = S; wp.rays_per_cta = plan.rays_per_cta; wp.nst_plan = plan.nst; wp.n_tiles = plan.n_tiles;
-    wp.amax = amax; wp.partial = partial; wp.njobs = J.n;
+    wp.amax = amax; wp.partial = partial; wp.d_raw = d_raw; wp.njobs = J.n;
+    J.w[0].aux_dst = dsum;
     for (int i = 0; i < J.n; ++i) wp.jobs[i] = J.w[i];
     TimedLaunch* tl = nullptr;
     if (g_timing && g_ntimed < 4096) {
@@ -820,16 +824,39 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     encv_kernel<<<cdiv(N * ICV, 256), 256, 0, st>>>(rays + 8, rs, N, ICV, encv);
     NB_LAUNCH_OK("encv_kernel");
     HeadGradParams hp;
-    hp.act = act; hp.grad = grec; hp.d_raw = d_raw; hp.amax = amax;
+    hp.act = act; hp.d_raw = d_raw;
     hp.N = N; hp.S = S; hp.rays_per_cta = plan.rays_per_cta; hp.nst_plan = plan.nst; hp.D = D;
-    hp.rec_act = rec_act_bytes(D); hp.rec_grad = rec_grad_bytes(D); hp.n_tiles = plan.n_tiles;
-    hp.rgb_w = grads->rgb_w; hp.rgb_b = grads->rgb_b; hp.alpha_w = grads->alpha_w; hp.alpha_b = grads->alpha_b; hp.dsum = dsum;
-    head_grads_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(hp);
+    hp.rec_act = rec_act_bytes(D); hp.n_tiles = plan.n_tiles;
+    hp.rgb_w = grads->rgb_w; hp.rgb_b = grads->rgb_b;
+    head_grads_kernel<<<(int)(plan.n_tiles < 2 * sms ? plan.n_tiles : 2 * sms), 256, 0, st>>>(hp);
     NB_LAUNCH_OK("head_grads_kernel");
     dim3 vg(ICV, cdiv(N, 512));
     views_enc_wgrad_kernel<<<vg, 128, 0, st>>>(dsum, encv, N, ICV, grads->views_w, net->W + ICV, net->W);
     NB_LAUNCH_OK("views_enc_wgrad_kernel");
   }
+  return 0;
+}
+
+// ---- the two ends of the optimisation step (train_step.cuh) ------------------------------------------
+int nerf_b200_mse_seed(const float* rgb, const float* target, int64_t N, float grad_scale, float* g_rgb, float* loss_accum, void* stream) {
+  NB_CHECK_ARG(rgb && target && g_rgb && loss_accum, "NULL pointer");
+  if (N == 0) return 0;
+  const long long n3 = N * 3;
+  mse_seed_kernel<<<cdiv(n3, 256) < 64 ? cdiv(n3, 256) : 64, 256, 0, (cudaStream_t)stream>>>(rgb, target, n3, 1.0f / (float)n3, grad_scale, g_rgb, loss_accum);
+  NB_LAUNCH_OK("mse_seed_kernel");
+  return 0;
+}
+
+int nerf_b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                        float lr0, float decay_rate, float decay_steps, float beta1, float beta2, float eps, float grad_mul, void* stream) {
+  NB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state, "NULL pointer");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = cdiv(n, 1024) < 4 * num_sms() ? cdiv(n, 1024) : 4 * num_sms();
+  adam_flat_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, lr0, decay_rate, decay_steps, beta1, beta2, eps, grad_mul);
+  NB_LAUNCH_OK("adam_flat_kernel");
+  adam_advance_kernel<<<1, 1, 0, st>>>(state, lr0, decay_rate, decay_steps);
+  NB_LAUNCH_OK("adam_advance_kernel");
   return 0;
 }
 

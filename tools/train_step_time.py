@@ -1,13 +1,19 @@
-"""Time one training step (forward render + loss + backward + Adam) on the C2 workload."""
-import os, sys, time
+"""Time one training step (run_nerf.py:760-776: render with retraw, two MSE terms, backward, Adam) on the C2 workload through
+the public API (eager autograd path), CUDA-event timed, with the device time of the three tensor-core kernels split out.
+Writes gpurun_out/train_step.json.   usage: train_step_time.py [N_rays] [steps] [backward: tc|exact]"""
+import ctypes as C, json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge; ge.build()
 import nerf_pytorch_b200 as nb
+from nerf_pytorch_b200 import _lib
 from nerf_pytorch_b200.api import _QueryFn
 from oracle import synth
 dev = torch.device("cuda:0")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+nb.set_backward(sys.argv[3] if len(sys.argv) > 3 else "tc")
+lib = _lib.load()
 nets = []
 for seed in (0, 1):
     m = nb.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
@@ -24,9 +30,25 @@ def step():
     loss = nb.img2mse(rgb, target) + nb.img2mse(ex["rgb0"], target)
     loss.backward(); opt.step()
     return loss
-for _ in range(2): step()
-torch.cuda.synchronize(); t0 = time.perf_counter()
-K = 3
-for _ in range(K): l = step()
-torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / K
-print(f"train step N={N}: {dt*1e3:.1f} ms  -> {N/dt:.0f} rays/s  (loss {float(l):.4f})")
+for _ in range(3): step()
+torch.cuda.synchronize()
+l0 = nb.launch_count(); step(); launches = nb.launch_count() - l0
+lib.nerf_b200_timing_enable(1)
+ms = []
+for _ in range(K):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); l = step(); b.record(); torch.cuda.synchronize()
+    ms.append(a.elapsed_time(b))
+kms, kn, kfl = C.c_double(), C.c_int64(), C.c_double()
+kinds = (C.c_double * 3)()
+lib.nerf_b200_timing_read_kinds(C.byref(kms), C.byref(kn), C.byref(kfl), kinds)
+lib.nerf_b200_timing_enable(0)
+med = float(np.median(ms))
+res = {"N": N, "steps": K, "backward": nb.get_backward(), "ms_per_step_median": med, "ms_per_step_min": float(min(ms)), "rays_per_s": N / (med * 1e-3),
+       "library_launches_per_step": int(launches), "loss": float(l),
+       "kernel_ms_per_step": {"forward_passes": kinds[0] / K, "dgrad_chains": kinds[1] / K, "wgrad": kinds[2] / K},
+       "train_flop_per_ray": 893190144, "tflops_algorithmic": N * 893190144 / (med * 1e-3) / 1e12,
+       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/train_step.json", "w"), indent=1)
+print(json.dumps(res))
