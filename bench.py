@@ -482,10 +482,33 @@ def main():
         if world > 1:
             # strong scaling: the SAME global 4096-ray batch split over the ranks, one flat all-reduce per step
             n_local = N_RAYS // world
+            # correctness of the split, observed in this run: DP gradient (N/G rays per rank, loss scaled 1/G, all-reduce) vs the
+            # full 4096-ray batch on one GPU, deterministic sampling
+            ckw = dict(tkw); ckw.update(perturb=0.)
+            cn1, cn2 = make_nets(), make_nets()
+            k1 = dict(ckw); k1.update(network_fn=cn1[0], network_fine=cn1[1])
+            k2 = dict(ckw); k2.update(network_fn=cn2[0], network_fine=cn2[1])
+            t_full = FusedTrainStep(sb["H"], sb["W"], sb["K"], N_RAYS, k1, use_graph=False, data_parallel=False)
+            t_dp = FusedTrainStep(sb["H"], sb["W"], sb["K"], n_local, k2, use_graph=False)
+            rays0 = torch.from_numpy(synth.ray_batch("lego", N_RAYS, seed=0)["rays"]).to(dev)       # the same batch on every rank
+            t_full.rays.copy_(rays0); t_full.target.copy_(tgt_host.to(dev))
+            t_dp.rays.copy_(rays0[:, rank * n_local:(rank + 1) * n_local]); t_dp.target.copy_(tgt_host.to(dev)[rank * n_local:(rank + 1) * n_local])
+            t_full._fwd_bwd(); t_dp._fwd_bwd()
+            dist.all_reduce(t_dp.flat_g, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            gd, gf = t_dp.flat_g.double(), t_full.flat_g.double()
+            dp_check = {"grad_rel_l2_vs_single_gpu_full_batch": float((gd - gf).norm() / gf.norm()), "grad_cosine": float((gd @ gf) / (gd.norm() * gf.norm())),
+                        "loss_dp_sum_over_ranks_vs_full": None}
+            lsum = t_dp.state[0:1].clone() / world
+            dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+            dp_check["loss_dp_mean_over_ranks"] = float(lsum.item()); dp_check["loss_full_batch"] = float(t_full.state[0].item())
+            del t_full, t_dp, cn1, cn2
+            torch.cuda.empty_cache()
             ms_dp, ms_dp_mean, ms_dp_host, _, kinds_dp, _ = run_train(n_local, True)
             extra["train_dp"] = {"metric": "rays/sec (train step, data parallel, fixed global batch)", "value": N_RAYS / (ms_dp * 1e-3), "unit": "rays/s",
                                  "ms_per_step": ms_dp, "scaling": "strong", "global_batch": N_RAYS, "rays_per_gpu": n_local,
                                  "collective": "one ncclAllReduce(SUM) of the flat fp32 gradient buffer: 1 191 688 elements = 4.77 MB per step",
+                                 "check": dp_check,
                                  "kernel_ms_per_step": {"forward_passes_training_mode": kinds_dp[0], "dgrad_chains": kinds_dp[1], "wgrad": kinds_dp[2]}}
             # full-frame render, ray-sharded, all-gather of [rays, 5]
             Hf = Wf = 800
@@ -505,9 +528,16 @@ def main():
                         ret = nb.batchify_rays(packed, 32768, **{k: v for k, v in kw.items() if k not in ("ndc", "near", "far", "use_viewdirs")})
                         loc = torch.cat([ret["rgb_map"], ret["disp_map"][:, None], ret["acc_map"][:, None]], -1)
                         return nbdist.gather_pixels(loc, n_pix)
+                full = frame()
+                fcheck = None
+                if rank == 0:                                   # the gathered frame vs rank 0 rendering every ray itself
+                    with torch.no_grad():
+                        rgb1, disp1, acc1, _ = nb.render(Hf, Wf, Kf, chunk=32768, c2w=c2w, **kw)
+                    one = torch.cat([rgb1.reshape(-1, 3), disp1.reshape(-1, 1), acc1.reshape(-1, 1)], -1)
+                    fcheck = float((torch.nan_to_num(full) - torch.nan_to_num(one)).abs().max().item())
                 ms_f, _ = timed(frame, max(3, args.steps // 5), 2)
                 extra["frame"] = {"metric": "rays/sec (800x800 frame, ray-sharded render + all-gather)", "value": n_pix / (ms_f * 1e-3), "unit": "rays/s",
-                                  "ms_per_frame": ms_f, "scaling": "strong", "rays_per_frame": n_pix,
+                                  "ms_per_frame": ms_f, "scaling": "strong", "rays_per_frame": n_pix, "max_abs_diff_vs_single_gpu_render": fcheck,
                                   "collective": "all_gather of [rays/G, 5] fp32 stripes = 12.8 MB per frame; rays generated per rank from the 72-byte camera (pixel0 offset), no scatter"}
     clocks = sampler.stop()
 

@@ -449,8 +449,9 @@ class _RenderRays(torch.autograd.Function):
         z_c = torch.empty((N, Sc), **f32)
         o = {k: torch.empty(s, **f32) for k, s in (("rgb0", (N, 3)), ("disp0", (N,)), ("acc0", (N,)), ("w0", (N, Sc)))}
         retraw, fine = cfgd["retraw"], Ni > 0
-        needs_grad = any(ctx.needs_input_grad[8:])
-        train_tc = bool(tc and needs_grad and get_backward() == "tc" and net_c.use_viewdirs and
+        # cfgd["want_grad"]: grad mode was on at the call AND a parameter requires a gradient (inside Function.forward grad mode is
+        # always off, and ctx.needs_input_grad stays True under torch.no_grad()): only then the training-mode kernel runs
+        train_tc = bool(tc and cfgd["want_grad"] and get_backward() == "tc" and net_c.use_viewdirs and
                         (net_f is None or net_f.use_viewdirs))
         raw_c = torch.empty((N, Sc, 4), **f32) if ((retraw and not fine) or not tc or train_tc) else None
         out_c = NerfPassOut(_ptr(o["rgb0"]), _ptr(o["disp0"]), _ptr(o["acc0"]), C.c_void_p(0), _ptr(o["w0"]), _ptr(raw_c))
@@ -582,6 +583,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                 lindisp=bool(lindisp), perturb=float(perturb), white_bkgd=bool(white_bkgd), retraw=bool(retraw))
     net_f = network_fine if N_importance > 0 else None          # the reference ignores network_fine without fine samples
     params = list(network_fn.parameters()) + (list(net_f.parameters()) if net_f is not None else [])
+    cfgd["want_grad"] = bool(torch.is_grad_enabled() and any(p.requires_grad for p in params))
     outs = _RenderRays.apply(ray_batch, cfgd, network_fn, net_f, t_rand, u_rand, noise0, noise1, *params)
     if N_importance > 0:
         rgb, disp, acc, rgb0, disp0, acc0, z_std, raw = outs

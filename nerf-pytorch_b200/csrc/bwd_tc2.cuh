@@ -504,46 +504,62 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
           ptx::named_bar_sync(1, 128);
         }
         ptx::mbar_wait(bar_full + 8 * s, ph);
-        if (do_sum) {
-          const uint32_t base = sb + s * WG2_STAGE + coff;
-          if (job.aux == 1) {
-            long long ray = (row_begin + lr0) / p.S;
-            int left = (int)((ray + 1) * p.S - (row_begin + lr0));
-            float r0 = 0.f, r1 = 0.f;
-#pragma unroll 4
+        // one row of this thread's column pair in a half-tile image that starts at shared-memory address `b_`
+#define NB_LDPAIR(b_, r_, w_) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w_) : "r"((b_) + (uint32_t)(((r_) >> 3) * 1024 + ((r_) & 7) * 128) + ((cc ^ (uint32_t)((r_) & 7)) << 4)))
+        if (do_sum || job.aux == 2) {
+          const uint32_t abase = sb + s * WG2_STAGE + coff, bbase = abase + ybase;
+          float h0 = 0.f, h1 = 0.f;                     // column sums of this half tile of A
+          if (job.aux == 2) {
+            // A = d_feat (bias gradient) and B = h_{D-1} (x d_sigma -> alpha_linear.weight) in one sweep
+            const float* ds = s_dsig + s * 64;
+#pragma unroll 8
             for (int r = 0; r < 64; ++r) {
-              uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
-              const __half2 hh = *reinterpret_cast<const __half2*>(&w);
-              const float x0 = __low2float(hh), x1 = __high2float(hh);
-              s0 += x0; s1 += x1; r0 += x0; r1 += x1;
-              if (--left == 0 || r == 63) {
-                if (ray < p.N && lr0 + r < nrows) { atomicAdd(job.aux_dst + ray * 128 + c, r0 * inv); atomicAdd(job.aux_dst + ray * 128 + c + 1, r1 * inv); }
-                r0 = r1 = 0.f; ++ray; left = p.S;
-              }
+              uint32_t wa, wb;
+              NB_LDPAIR(abase, r, wa);
+              NB_LDPAIR(bbase, r, wb);
+              const __half2 ha = *reinterpret_cast<const __half2*>(&wa), hb = *reinterpret_cast<const __half2*>(&wb);
+              const float d = ds[r];
+              h0 += __low2float(ha); h1 += __high2float(ha);
+              a0 = fmaf(d, __low2float(hb), a0); a1 = fmaf(d, __high2float(hb), a1);
             }
           } else {
 #pragma unroll 8
             for (int r = 0; r < 64; ++r) {
               uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
+              NB_LDPAIR(abase, r, w);
               const __half2 hh = *reinterpret_cast<const __half2*>(&w);
-              s0 += __low2float(hh); s1 += __high2float(hh);
+              h0 += __low2float(hh); h1 += __high2float(hh);
+            }
+          }
+          s0 += h0; s1 += h1;
+          if (job.aux == 1 && do_sum) {
+            // per-ray row sums of d_hv.  Rows past the CTA's range are zero in the image (dhv_seed_kernel), so when the valid
+            // rows of this half tile belong to ONE ray (always for S % 64 == 0) its sum is the half-tile column sum
+            const int nvalid = (nrows - lr0 < 64) ? nrows - lr0 : 64;
+            if (nvalid > 0) {
+              const long long m0 = row_begin + lr0;
+              const long long ray_a = m0 / p.S, ray_b = (m0 + nvalid - 1) / p.S;
+              if (ray_a == ray_b) {
+                atomicAdd(job.aux_dst + ray_a * 128 + c, h0 * inv); atomicAdd(job.aux_dst + ray_a * 128 + c + 1, h1 * inv);
+              } else {                                  // general S: walk the rows, flush at every ray boundary
+                long long ray = ray_a;
+                int left = (int)((ray + 1) * p.S - m0);
+                float r0 = 0.f, r1 = 0.f;
+                for (int r = 0; r < nvalid; ++r) {
+                  uint32_t w;
+                  NB_LDPAIR(abase, r, w);
+                  const __half2 hh = *reinterpret_cast<const __half2*>(&w);
+                  r0 += __low2float(hh); r1 += __high2float(hh);
+                  if (--left == 0 || r == nvalid - 1) {
+                    atomicAdd(job.aux_dst + ray * 128 + c, r0 * inv); atomicAdd(job.aux_dst + ray * 128 + c + 1, r1 * inv);
+                    r0 = r1 = 0.f; ++ray; left = p.S;
+                  }
+                }
+              }
             }
           }
         }
-        if (job.aux == 2) {                             // B half tile (h_{D-1}, 256 columns): columns 2 tid, 2 tid + 1
-          const uint32_t base = sb + s * WG2_STAGE + ybase + coff;
-          const float* ds = s_dsig + s * 64;
-#pragma unroll 8
-          for (int r = 0; r < 64; ++r) {
-            uint32_t w;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((cc ^ (uint32_t)(r & 7)) << 4)));
-            const __half2 hh = *reinterpret_cast<const __half2*>(&w);
-            const float d = ds[r];
-            a0 = fmaf(d, __low2float(hh), a0); a1 = fmaf(d, __high2float(hh), a1);
-          }
-        }
+#undef NB_LDPAIR
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
         if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
@@ -656,7 +672,7 @@ __global__ void __launch_bounds__(256) head_grads_kernel(const HeadGradParams p)
 __global__ void __launch_bounds__(128) views_enc_wgrad_kernel(const float* __restrict__ dsum, const float* __restrict__ encv, long long N, int ICV,
                                                             float* __restrict__ views_w, int ld, int col0) {
   const int e = blockIdx.x, c = threadIdx.x;
-  const long long n0 = (long long)blockIdx.y * 512, n1 = (n0 + 512 < N) ? n0 + 512 : N;
+  const long long n0 = (long long)blockIdx.y * 64, n1 = (n0 + 64 < N) ? n0 + 64 : N;
   float s = 0.f;
   for (long long n = n0; n < n1; ++n) s = fmaf(dsum[n * 128 + c], encv[n * ICV + e], s);
   atomicAdd(views_w + (size_t)c * ld + col0 + e, s);

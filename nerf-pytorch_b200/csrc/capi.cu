@@ -734,6 +734,9 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
   BwdTcJobs J = make_bwd_jobs(*net, grads, sms);
   J.w[0].aux = 1;                                   // views job: per-ray row sums of d_hv (aux_dst set below)
   J.w[1].aux = 2; J.w[1].aux_dst = grads->alpha_w; J.w[1].aux_b = grads->alpha_b;   // feature job: alpha_linear gradients
+  { static int noaux = -1; if (noaux < 0) { const char* e = getenv("NERF_B200_DBG_NOAUX"); noaux = e ? atoi(e) : 0; }
+    if (noaux & 1) J.w[0].aux = 0;
+    if (noaux & 2) J.w[1].aux = 0; }
   const BwdTcLayout LY = make_bwd_layout(N, S, *net, plan, J.part_floats);
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   NB_CHECK_ARG(workspace && workspace_bytes >= LY.total + (size_t)(ws - static_cast<uint8_t*>(workspace)), "march_bwd_tc workspace too small (%zu < %zu)", workspace_bytes, LY.total + 1024);
@@ -830,7 +833,7 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     hp.rgb_w = grads->rgb_w; hp.rgb_b = grads->rgb_b;
     head_grads_kernel<<<(int)(plan.n_tiles < 2 * sms ? plan.n_tiles : 2 * sms), 256, 0, st>>>(hp);
     NB_LAUNCH_OK("head_grads_kernel");
-    dim3 vg(ICV, cdiv(N, 512));
+    dim3 vg(ICV, cdiv(N, 64));
     views_enc_wgrad_kernel<<<vg, 128, 0, st>>>(dsum, encv, N, ICV, grads->views_w, net->W + ICV, net->W);
     NB_LAUNCH_OK("views_enc_wgrad_kernel");
   }

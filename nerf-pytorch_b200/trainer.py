@@ -29,7 +29,7 @@ from ._lib import NerfPassOut, NerfTrainSave, check
 
 class FusedTrainStep:
     def __init__(self, H, W, K, n_rays, render_kwargs, lrate=5e-4, lrate_decay=250, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, use_graph=True):
+                 process_group=None, use_graph=True, data_parallel=True):
         """render_kwargs: the `render_kwargs_train` dict of create_nerf() plus near / far (run_nerf.py:643-648).
         lrate_decay is in units of 1000 steps like the reference's --lrate_decay (run_nerf.py:779-780)."""
         import torch.distributed as dist
@@ -48,13 +48,13 @@ class FusedTrainStep:
         q = kw.get("network_query_fn")
         self.cfgd = dict(N_samples=self.Sc, N_importance=self.Ni, multires=int(getattr(q, "multires", 10)),
                          multires_views=int(getattr(q, "multires_views", 4)), lindisp=bool(kw.get("lindisp", False)),
-                         perturb=float(kw.get("perturb", 0.)), white_bkgd=bool(kw.get("white_bkgd", False)), retraw=True)
+                         perturb=float(kw.get("perturb", 0.)), white_bkgd=bool(kw.get("white_bkgd", False)), retraw=True, want_grad=True)
         self.noise_std = float(kw.get("raw_noise_std", 0.))
         self.ndc, self.near, self.far = int(bool(kw.get("ndc", True))), float(kw.get("near", 0.)), float(kw.get("far", 1.))
         self.lr0, self.decay_rate, self.decay_steps = float(lrate), 0.1, float(lrate_decay) * 1000.0
         self.b1, self.b2, self.eps = float(betas[0]), float(betas[1]), float(eps)
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dist.get_world_size(process_group) if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         # ---- one flat buffer for parameters, gradients and moments; the Parameters become views of it ----
         nets = [self.net_c] + ([self.net_f] if (self.net_f is not None and self.net_f is not self.net_c) else [])
         self.params = [p for n in nets for p in n.parameters()]

@@ -131,6 +131,32 @@ def test_training_forward_records(G, N, S):
     _record(f"records_N{N}_S{S}", stats)
 
 
+def test_inference_render_stays_on_the_inference_kernel(G):
+    """render() under torch.no_grad() with parameters that require grad must not run the training-mode pass (no tile
+    records: 1.2 MB per 128 rows would be allocated and written) -- ctx.needs_input_grad is not a usable signal there."""
+    sb = G.synth.ray_batch("lego", 1024, seed=3)
+    nets = [G.make_net(G.synth.nerf_state(0)), G.make_net(G.synth.nerf_state(1))]
+    assert all(p.requires_grad for n in nets for p in n.parameters())
+    kw = dict(ndc=False, near=2., far=6., use_viewdirs=True, network_fn=nets[0], network_fine=nets[1], network_query_fn=G.query_fn(),
+              N_samples=64, N_importance=128, perturb=0., white_bkgd=True, raw_noise_std=0.)
+    rays = G.dev(sb["rays"])
+    with torch.no_grad():
+        G.nb.render(400, 400, sb["K"], rays=rays, **kw)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        out = G.nb.render(400, 400, sb["K"], rays=rays, **kw)
+    torch.cuda.synchronize()
+    assert torch.cuda.max_memory_allocated() - base < 64 << 20           # records of 1024 rays would be > 2 GB
+    base = torch.cuda.memory_allocated()
+    torch.cuda.reset_peak_memory_stats()
+    out = G.nb.render(400, 400, sb["K"], rays=rays, **kw)                # grad mode on: the training-mode pass
+    torch.cuda.synchronize()
+    assert torch.cuda.max_memory_allocated() - base > 1 << 30
+    assert out[0].requires_grad
+
+
 def _bwd_tc(G, net, rays11, zd, raw, act, mask, g_rgb):
     """nerf_b200_march_bwd_tc through the C ABI -> (grads dict name -> np, workspace bytes np)"""
     lib = G._lib.load()
