@@ -79,4 +79,5 @@ def test_two_gpu_render_and_dp_gradients():
         p.join(timeout=120)
     for rank, ok_render, worst in res:
         assert ok_render, f"rank {rank}: sharded render differs from the single-GPU render"
-        assert worst < 2e-4, f"rank {rank}: all-reduced gradients differ ({worst})"      # fp32 atomics / reduction order
+        # tensor-core backward: each shard has its own loss scale and tile plan (fp16 rounding of the activation gradients differs)
+        assert worst < 3e-3, f"rank {rank}: all-reduced gradients differ ({worst})"
