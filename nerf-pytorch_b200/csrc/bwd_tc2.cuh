@@ -385,7 +385,7 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
 // 192 threads: warps 0-3 column sums (bias gradient) while streaming, then the TMEM epilogue; warp 4 producer; warp 5 issuer.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int WG2_THREADS = 192, WG2_NSTAGE = 3, WG2_MAX_JOBS = 16;
-constexpr uint32_t WG2_STAGE = 65536, WG2_BARS = WG2_NSTAGE * WG2_STAGE, WG2_DSIG = WG2_BARS + 128, WG2_TOTAL = WG2_DSIG + WG2_NSTAGE * 256;
+constexpr uint32_t WG2_STAGE = 65536, WG2_BARS = WG2_NSTAGE * WG2_STAGE, WG2_DSIG = WG2_BARS + 128, WG2_TOTAL = WG2_DSIG + 1024;
 
 struct WgradJob {
   uint32_t a_off, b_off;        // image offsets inside the gradient / activation record
@@ -488,21 +488,35 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
     const float inv = 1.0f / loss_scale_from_absmax(__uint_as_float(*p.amax));
     float* s_dsig = reinterpret_cast<float*>(smem + WG2_DSIG);
     float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, bsum = 0.f;
+    // aux == 2: d_sigma of a tile's 128 rows sits in shared memory (two slots); the NEXT tile's values are fetched while the
+    // current tile is processed, so the global-load latency never sits between two stages
+    auto load_dsig = [&](long long t_) -> float {
+      const int cta_ = (int)(t_ / (2 * p.nst_plan)), st_ = (int)((t_ >> 1) % p.nst_plan), X_ = (int)(t_ & 1);
+      const int lr_ = st_ * 256 + X_ * 128 + tid;
+      return (lr_ < plan_cta_rows(p.N, p.S, p.rays_per_cta, cta_)) ? p.d_raw[((long long)cta_ * p.rays_per_cta * p.S + lr_) * 4 + 3] : 0.f;
+    };
+    auto next_valid = [&](long long t_) -> long long {
+      for (t_ += G; t_ < p.n_tiles; t_ += G) if (plan_tile_valid(p, t_)) return t_;
+      return -1;
+    };
+    int dslot = 0;
+    if (job.aux == 2) {
+      long long t0 = g - G;
+      t0 = next_valid(t0);
+      const float v = (t0 >= 0) ? load_dsig(t0) : 0.f;
+      s_dsig[tid] = v;
+      bsum += v;
+      ptx::named_bar_sync(1, 128);
+    }
     for (long long t = g; t < p.n_tiles; t += G) {
       if (!plan_tile_valid(p, t)) continue;
       const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
       const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
       const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
+      float v_next = 0.f;
+      if (job.aux == 2) { const long long tn = next_valid(t); v_next = (tn >= 0) ? load_dsig(tn) : 0.f; }
       for (int h = 0; h < 2; ++h) {
         const int lr0 = st * 256 + X * 128 + h * 64;
-        if (job.aux == 2) {                             // d_sigma of this half tile's rows -> shared memory
-          if (tid < 64) {
-            const float v = (lr0 + tid < nrows) ? p.d_raw[(row_begin + lr0 + tid) * 4 + 3] : 0.f;
-            s_dsig[s * 64 + tid] = v;
-            bsum += v;
-          }
-          ptx::named_bar_sync(1, 128);
-        }
         ptx::mbar_wait(bar_full + 8 * s, ph);
         // one row of this thread's column pair in a half-tile image that starts at shared-memory address `b_`
 #define NB_LDPAIR(b_, r_, w_) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w_) : "r"((b_) + (uint32_t)(((r_) >> 3) * 1024 + ((r_) & 7) * 128) + ((cc ^ (uint32_t)((r_) & 7)) << 4)))
@@ -511,7 +525,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
           float h0 = 0.f, h1 = 0.f;                     // column sums of this half tile of A
           if (job.aux == 2) {
             // A = d_feat (bias gradient) and B = h_{D-1} (x d_sigma -> alpha_linear.weight) in one sweep
-            const float* ds = s_dsig + s * 64;
+            const float* ds = s_dsig + dslot * 128 + h * 64;
 #pragma unroll 8
             for (int r = 0; r < 64; ++r) {
               uint32_t wa, wb;
@@ -537,8 +551,8 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
             // rows of this half tile belong to ONE ray (always for S % 64 == 0) its sum is the half-tile column sum
             const int nvalid = (nrows - lr0 < 64) ? nrows - lr0 : 64;
             if (nvalid > 0) {
-              const long long m0 = row_begin + lr0;
-              const long long ray_a = m0 / p.S, ray_b = (m0 + nvalid - 1) / p.S;
+              const long long m0 = row_begin + lr0;                     // row_begin is a multiple of S: rays are whole per CTA
+              const long long ray_a = (long long)cta * p.rays_per_cta + lr0 / p.S, ray_b = (long long)cta * p.rays_per_cta + (lr0 + nvalid - 1) / p.S;
               if (ray_a == ray_b) {
                 atomicAdd(job.aux_dst + ray_a * 128 + c, h0 * inv); atomicAdd(job.aux_dst + ray_a * 128 + c + 1, h1 * inv);
               } else {                                  // general S: walk the rows, flush at every ray boundary
@@ -564,10 +578,17 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
         if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
         if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
       }
+      if (job.aux == 2) {                               // the prefetched d_sigma of the next tile -> the other slot
+        s_dsig[(dslot ^ 1) * 128 + tid] = v_next;
+        bsum += v_next;
+        dslot ^= 1;
+        ptx::named_bar_sync(1, 128);
+      }
     }
     if (job.aux == 2 && my_halves > 0) {
       atomicAdd(job.aux_dst + c, a0); atomicAdd(job.aux_dst + c + 1, a1);
-      if (tid < 64) { bsum = warp_sum(bsum); if (lane == 0) atomicAdd(job.aux_b, bsum); }
+      bsum = warp_sum(bsum);
+      if (lane == 0) atomicAdd(job.aux_b, bsum);
     }
     if (do_sum && my_halves > 0) { atomicAdd(job.db + c, s0 * inv); atomicAdd(job.db + c + 1, s1 * inv); }
     float* part = p.partial + job.part_off + (size_t)g * job.Mc * job.Nc;

@@ -54,8 +54,12 @@ def _worker(rank, world, port, n, q):
     (tot / world).backward()
     ok = ok and torch.allclose(w.grad, w2.grad, atol=1e-6) and torch.allclose(b.grad, b2.grad, atol=1e-6)
     p = torch.nn.Parameter(torch.full((4,), float(rank)))
+    v0 = p._version
     nd.broadcast_params([p], src=0)
     ok = ok and bool((p == 0).all())
+    # the broadcast writes through the Parameter itself (not .data): the version counter that NeRF.packed() keys its
+    # fp16 weight cache on must move, otherwise non-zero ranks would keep rendering with stale tensor-core weights
+    ok = ok and p._version > v0
     q.put((rank, ok))
     dist.destroy_process_group()
 
