@@ -448,7 +448,7 @@ def main():
             r_h = rays_host[:, lo:lo + n_local].contiguous().pin_memory() if n_local != N_RAYS else rays_host
             t_h = tgt_host[lo:lo + n_local].contiguous().pin_memory() if n_local != N_RAYS else tgt_host
             tr.rays.copy_(r_h); tr.target.copy_(t_h)
-            l0_ = nb.launch_count(); tr._fwd_bwd(); tr._adam(); launches = nb.launch_count() - l0_     # one eager step to count launches
+            l0_ = nb.launch_count(); tr._pack_rays(); tr._fwd_bwd(); tr._adam(); launches = nb.launch_count() - l0_     # one eager step to count launches
             torch.cuda.synchronize()
             lib.nerf_b200_timing_enable(0)
             ms_dev, ms_dev_mean = timed(tr.step_device, args.steps, args.warmup)
@@ -456,7 +456,7 @@ def main():
             # kernel split of the step: an eager (un-graphed) pass with the library's event bracketing on
             lib.nerf_b200_timing_enable(1)
             for _ in range(3):
-                tr._fwd_bwd(); tr._adam()
+                tr._pack_rays(); tr._fwd_bwd(); tr._adam()
             torch.cuda.synchronize()
             kms_t, kn_t, kfl_t, kinds = read_timing()
             lib.nerf_b200_timing_enable(0)
@@ -493,7 +493,7 @@ def main():
             rays0 = torch.from_numpy(synth.ray_batch("lego", N_RAYS, seed=0)["rays"]).to(dev)       # the same batch on every rank
             t_full.rays.copy_(rays0); t_full.target.copy_(tgt_host.to(dev))
             t_dp.rays.copy_(rays0[:, rank * n_local:(rank + 1) * n_local]); t_dp.target.copy_(tgt_host.to(dev)[rank * n_local:(rank + 1) * n_local])
-            t_full._fwd_bwd(); t_dp._fwd_bwd()
+            t_full._pack_rays(); t_dp._pack_rays(); t_full._fwd_bwd(); t_dp._fwd_bwd()
             dist.all_reduce(t_dp.flat_g, op=dist.ReduceOp.SUM)
             torch.cuda.synchronize()
             gd, gf = t_dp.flat_g.double(), t_full.flat_g.double()

@@ -126,6 +126,14 @@ typedef struct NerfCamera {
 int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam,
                         int64_t N, int64_t pixel0, int ndc, float near, float far, int use_viewdirs,
                         float* out, void* stream);
+/* same, for an arbitrary device list of pixel ids (row-major j * W + i) of the camera's image: the per-image random
+ * pixel choice of train() (run_nerf.py:728-757: get_rays for the whole image, meshgrid, np.random.choice, gather)
+ * without the [H,W,3] ray tensors */
+int nerf_b200_pack_rays_pixels(const NerfCamera* cam, const int64_t* pixel_index, int64_t N, int ndc, float near,
+                               float far, int use_viewdirs, float* out, void* stream);
+/* to8b (run_nerf_helpers.py:11) on the device: out[i] = uint8(255 * clip(x[i], 0, 1)) -- image output of render_path
+ * (run_nerf.py:160-169) without a float32 round trip through the host */
+int nerf_b200_to8b(const float* x, int64_t n, uint8_t* out, void* stream);
 
 /* ---- hierarchical resampling of render_rays (run_nerf.py:392-396, :412): z_mid, sample_pdf on
  *      weights[...,1:-1], sort(cat) and z_std in one kernel.

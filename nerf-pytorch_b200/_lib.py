@@ -67,6 +67,8 @@ SIGNATURES = {
     "nerf_b200_raw2outputs_bwd": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, c_fp, C.c_int64, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
     "nerf_b200_pack_rays": (C.c_int, [c_fp, c_fp, c_fp, C.POINTER(NerfCamera), C.c_int64, C.c_int64, C.c_int, C.c_float,
                                       C.c_float, C.c_int, c_fp, c_fp]),
+    "nerf_b200_pack_rays_pixels": (C.c_int, [C.POINTER(NerfCamera), c_fp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, c_fp, c_fp]),
+    "nerf_b200_to8b": (C.c_int, [c_fp, C.c_int64, c_fp, c_fp]),
     "nerf_b200_sample_pdf": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int64, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_coarse_z": (C.c_int, [c_fp, C.c_int, c_fp, c_fp, C.c_int64, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_fine_z": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int64, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp]),

@@ -29,7 +29,7 @@ from ._lib import (NerfCamera, NerfNetGrads, NerfNetParams, NerfPassOut, NerfRen
 __all__ = ["NeRF", "Embedder", "get_embedder", "sample_pdf", "raw2outputs", "run_network", "batchify",
            "batchify_rays", "render_rays", "render", "create_nerf",
            "img2mse", "mse2psnr", "to8b", "set_precision", "get_precision", "set_backward", "get_backward",
-           "launch_count", "DEBUG", "GraphedRender"]
+           "launch_count", "DEBUG", "GraphedRender", "render_to8b", "DeviceRayBatcher"]
 
 DEBUG = False
 _PRECISION = {"mode": PREC_TC_FP16}
@@ -212,6 +212,20 @@ class NeRF(nn.Module):
         else:
             g.output_w, g.output_b = grads["output_linear.weight"].data_ptr(), grads["output_linear.bias"].data_ptr()
         return g
+
+    def load_weights_from_keras(self, weights):
+        """Import the original TF/Keras NeRF's weight list (same contract as run_nerf_helpers.py:121-148): kernels arrive as
+        [in, out] arrays in the order pts_linears (D), feature, views, rgb, alpha, each followed by its bias.  The layers
+        keep their Parameters (copy_ under no_grad, on whatever device they live), so the optimizer and the packed
+        tensor-core copy stay valid; the reference re-binds `.data` to CPU tensors instead."""
+        if not self.use_viewdirs:
+            raise AssertionError("Not implemented if use_viewdirs=False")
+        order = list(self.pts_linears) + [self.feature_linear, self.views_linears[0], self.rgb_linear, self.alpha_linear]
+        with torch.no_grad():
+            for i, lin in enumerate(order):
+                lin.weight.copy_(torch.as_tensor(np.ascontiguousarray(np.asarray(weights[2 * i]).T), dtype=lin.weight.dtype))
+                lin.bias.copy_(torch.as_tensor(np.asarray(weights[2 * i + 1]).reshape(-1), dtype=lin.bias.dtype))
+        self.invalidate_pack()
 
     def invalidate_pack(self):
         """Force the next packed() to re-pack.  Needed after writes that autograd's version counter does not see
@@ -694,6 +708,75 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
     k_extract = ["rgb_map", "disp_map", "acc_map"]
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+def render_to8b(H, W, K, c2w, chunk=1024 * 32, out=None, **kwargs):
+    """One frame of render_path (run_nerf.py:151-169) with the image output on the device: rays are generated per chunk from
+    the camera (pixel offset, no [H,W,3] ray tensors), rendered, converted with to8b (run_nerf_helpers.py:11) by a kernel and
+    copied to pinned host memory asynchronously.  Returns (rgb8 [H,W,3] uint8 pinned host tensor, disp [H,W] float32 CUDA
+    tensor); synchronise the stream (or call .numpy() after torch.cuda.synchronize()) before reading rgb8.  No reference
+    counterpart in signature; `kwargs` are render()'s (render_kwargs_test + near/far + ndc/use_viewdirs)."""
+    lib = _lib.load()
+    dev = _render_device(kwargs)
+    kw = dict(kwargs)
+    ndc, use_viewdirs = int(bool(kw.pop("ndc", True))), bool(kw.pop("use_viewdirs", False))
+    near, far = float(kw.pop("near", 0.)), float(kw.pop("far", 1.))
+    n_pix = int(H) * int(W)
+    cam = _camera(H, W, K, c2w)
+    rgb8_dev = torch.empty((n_pix, 3), dtype=torch.uint8, device=dev)
+    disp = torch.empty((n_pix,), dtype=torch.float32, device=dev)
+    host = out if out is not None else torch.empty((int(H), int(W), 3), dtype=torch.uint8, device="cpu").pin_memory()
+    with torch.no_grad(), _on(rgb8_dev):
+        for p0 in range(0, n_pix, chunk):
+            n = min(chunk, n_pix - p0)
+            packed = torch.empty((n, 11 if use_viewdirs else 8), device=dev, dtype=torch.float32)
+            check(lib.nerf_b200_pack_rays(None, None, None, C.byref(cam), n, p0, ndc, near, far, int(use_viewdirs), _ptr(packed), _stream(packed)), "pack_rays")
+            ret = render_rays(packed, **kw)
+            rgb = ret["rgb_map"].contiguous()
+            check(lib.nerf_b200_to8b(_ptr(rgb), n * 3, _ptr(rgb8_dev[p0:p0 + n]), _stream(rgb)), "to8b")
+            disp[p0:p0 + n] = ret["disp_map"]
+        host.view(-1, 3).copy_(rgb8_dev, non_blocking=True)
+    return host, disp.view(int(H), int(W))
+
+
+class DeviceRayBatcher:
+    """The two ray-batching modes of train() (run_nerf.py:677-757) with the data resident on the device.
+
+    use_batching=True : `rays_rgb` [(N_img*H*W), 3, 3] (ro, rd, rgb) lives on the device, is shuffled with torch.randperm at every
+                        epoch end (:746-750) and sliced; next() -> (batch_rays [2,B,3], target [B,3]).
+    use_batching=False: per step one random training image; pixel ids are drawn on the device (inside the centre crop while
+                        i < precrop_iters, :731-744) and the targets gathered there; next() -> (c2w [3,4], pixel_index [B] int64,
+                        target [B,3]) for FusedTrainStep.step_device(c2w, pixel_index) / nerf_b200_pack_rays_pixels."""
+
+    def __init__(self, images, poses, H, W, N_rand, i_train=None, rays_rgb=None, precrop_iters=0, precrop_frac=0.5, device="cuda"):
+        self.dev = torch.device(device)
+        self.H, self.W, self.B = int(H), int(W), int(N_rand)
+        self.images = torch.as_tensor(images, dtype=torch.float32, device=self.dev)
+        self.poses = torch.as_tensor(poses, dtype=torch.float32)                        # host: one [3,4] pose per step goes into kernel arguments
+        self.i_train = list(range(self.images.shape[0])) if i_train is None else [int(i) for i in i_train]
+        self.rays_rgb = None if rays_rgb is None else torch.as_tensor(rays_rgb, dtype=torch.float32, device=self.dev)
+        self.i_batch, self.step = 0, 0
+        self.precrop_iters, self.precrop_frac = int(precrop_iters), float(precrop_frac)
+
+    def next(self):
+        self.step += 1
+        if self.rays_rgb is not None:
+            b = self.rays_rgb[self.i_batch:self.i_batch + self.B].transpose(0, 1)
+            self.i_batch += self.B
+            if self.i_batch >= self.rays_rgb.shape[0]:
+                self.rays_rgb = self.rays_rgb[torch.randperm(self.rays_rgb.shape[0], device=self.dev)]
+                self.i_batch = 0
+            return b[:2].contiguous(), b[2].contiguous()
+        img_i = self.i_train[int(torch.randint(len(self.i_train), (1,)).item())]
+        if self.step <= self.precrop_iters:
+            dH, dW = int(self.H // 2 * self.precrop_frac), int(self.W // 2 * self.precrop_frac)
+            j = torch.randint(self.H // 2 - dH, self.H // 2 + dH, (self.B,), device=self.dev)
+            i = torch.randint(self.W // 2 - dW, self.W // 2 + dW, (self.B,), device=self.dev)
+            pix = j * self.W + i
+        else:
+            pix = torch.randperm(self.H * self.W, device=self.dev)[:self.B]             # np.random.choice(..., replace=False), :741
+        target = self.images[img_i].reshape(-1, self.images.shape[-1])[pix][:, :3].contiguous()
+        return self.poses[img_i][:3, :4], pix, target
 
 
 # ------------------------------------------------------------------------------------------------

@@ -348,8 +348,8 @@ int nerf_b200_raw2outputs_bwd(const float* raw, const float* z_vals, const float
   return 0;
 }
 
-int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam, int64_t N,
-                        int64_t pixel0, int ndc, float near, float far, int use_viewdirs, float* out, void* stream) {
+static int pack_rays_impl(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam, int64_t N,
+                          int64_t pixel0, const int64_t* pixel_index, int ndc, float near, float far, int use_viewdirs, float* out, void* stream) {
   NB_CHECK_ARG(out != nullptr, "NULL output");
   NB_CHECK_ARG((rays_o && rays_d) || (cam && !rays_o && !rays_d), "give rays_o and rays_d, or a camera to generate them");
   NB_CHECK_ARG(!ndc || cam, "ndc needs the camera (H, W, focal)");
@@ -357,6 +357,7 @@ int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* v
   PackRaysArgs a;
   memset(&a, 0, sizeof(a));
   a.rays_o = rays_o; a.rays_d = rays_d; a.view_src = view_src; a.N = N; a.pixel0 = pixel0;
+  a.pixel_index = reinterpret_cast<const long long*>(pixel_index);
   a.ndc = ndc; a.use_viewdirs = use_viewdirs; a.stride = use_viewdirs ? 11 : 8; a.near = near; a.far = far;
   if (cam) {
     a.H = cam->H; a.W = cam->W; a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy;
@@ -366,6 +367,27 @@ int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* v
   }
   pack_rays_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(a, out);
   NB_LAUNCH_OK("pack_rays_kernel");
+  return 0;
+}
+
+int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam, int64_t N,
+                        int64_t pixel0, int ndc, float near, float far, int use_viewdirs, float* out, void* stream) {
+  return pack_rays_impl(rays_o, rays_d, view_src, cam, N, pixel0, nullptr, ndc, near, far, use_viewdirs, out, stream);
+}
+
+// the same for an arbitrary list of pixels of the camera's image (the per-image random pixel choice of run_nerf.py:728-757,
+// without materialising get_rays' [H, W, 3] tensors or gathering from them)
+int nerf_b200_pack_rays_pixels(const NerfCamera* cam, const int64_t* pixel_index, int64_t N, int ndc, float near, float far,
+                               int use_viewdirs, float* out, void* stream) {
+  NB_CHECK_ARG(cam && pixel_index, "camera and pixel_index are required");
+  return pack_rays_impl(nullptr, nullptr, nullptr, cam, N, 0, pixel_index, ndc, near, far, use_viewdirs, out, stream);
+}
+
+int nerf_b200_to8b(const float* x, int64_t n, uint8_t* out, void* stream) {
+  NB_CHECK_ARG(x && out, "NULL pointer");
+  if (n == 0) return 0;
+  to8b_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  NB_LAUNCH_OK("to8b_kernel");
   return 0;
 }
 

@@ -68,6 +68,7 @@ struct PackRaysArgs {
   const float* view_src;                        // [N,3] directions for viewdirs, or NULL -> rays_d
   int H, W; float fx, fy, cx, cy; float c2w[12];
   long long N, pixel0;
+  const long long* pixel_index;                 // [N] pixel ids (row-major j * W + i) or NULL -> pixel0 + n
   int ndc, use_viewdirs, stride;
   float near, far, ndc_cw, ndc_ch;              // ndc_cw = -1/(W/(2 focal)), ndc_ch = -1/(H/(2 focal)) (host double -> float)
 };
@@ -80,7 +81,7 @@ __global__ void pack_rays_kernel(PackRaysArgs a, float* __restrict__ out) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) { o[k] = a.rays_o[n * 3 + k]; d[k] = a.rays_d[n * 3 + k]; }
   } else {
-    const long long pix = a.pixel0 + n;
+    const long long pix = a.pixel_index ? a.pixel_index[n] : a.pixel0 + n;
     const float i = (float)(pix % a.W), j = (float)(pix / a.W);                       // :154-156 (i along W, j along H)
     const float dir[3] = {__fdiv_rn(__fsub_rn(i, a.cx), a.fx), -__fdiv_rn(__fsub_rn(j, a.cy), a.fy), -1.0f};   // :157
 #pragma unroll
@@ -109,6 +110,14 @@ __global__ void pack_rays_kernel(PackRaysArgs a, float* __restrict__ out) {
     o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
   }
   r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = d[0]; r[4] = d[1]; r[5] = d[2]; r[6] = a.near; r[7] = a.far;
+}
+
+// to8b (run_nerf_helpers.py:11: (255 * clip(x, 0, 1)).astype(uint8)) on the device, for render_path-style image output
+__global__ void to8b_kernel(const float* __restrict__ x, long long n, uint8_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  out[i] = (uint8_t)(255.0f * fminf(fmaxf(v, 0.0f), 1.0f));      // NaN -> fmaxf gives 0, like np.clip + astype on most platforms
 }
 
 // pts = rays_o + rays_d * z  (run_nerf.py:381), exact-mode helper

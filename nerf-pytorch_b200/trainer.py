@@ -120,7 +120,7 @@ class FusedTrainStep:
             snap = (self.flat_p.clone(), self.m.clone(), self.v.clone(), self.state.clone())
             with torch.cuda.stream(side):
                 for _ in range(2):                      # opt-ins, caches, lazy initialisations outside the capture
-                    self._fwd_bwd(); self._adam()
+                    self._pack_rays(); self._fwd_bwd(); self._adam()
             torch.cuda.current_stream(self.dev).wait_stream(side)
             torch.cuda.synchronize(self.dev)
             with torch.no_grad():                       # the warm-up steps must not count: restore parameters and moments
@@ -136,6 +136,18 @@ class FusedTrainStep:
                     self._adam()
 
     # ---- the step, as library calls on the current stream ----
+    def _pack_rays(self, c2w=None, pixel_index=None):
+        """The ray batch -> packed [N,11] rows.  Outside the graph (one launch): the camera travels in the kernel arguments, so a
+        per-step pose could not be replayed.  Given rays (self.rays) or -- SURVEY 8f rank 3 -- pixels of one posed image."""
+        with api._on(self.rays):
+            if pixel_index is None:
+                check(self.lib.nerf_b200_pack_rays(api._ptr(self.rays[0]), api._ptr(self.rays[1]), None, C.byref(self._cam), self.N, 0, self.ndc, self.near,
+                                                   self.far, 1, api._ptr(self.packed_rays), api._stream(self.rays)), "pack_rays")
+            else:
+                cam = api._camera(self.H, self.W, self.K, c2w)
+                check(self.lib.nerf_b200_pack_rays_pixels(C.byref(cam), api._ptr(pixel_index), self.N, self.ndc, self.near, self.far, 1,
+                                                          api._ptr(self.packed_rays), api._stream(self.rays)), "pack_rays_pixels")
+
     def _fwd_bwd(self):
         lib, N, cfg = self.lib, self.N, self._cfg
         st = api._stream(self.rays)
@@ -143,8 +155,6 @@ class FusedTrainStep:
             check(lib.nerf_b200_pack_weights(C.byref(self._np_c), api._ptr(self._pk_c), self._pk_c.numel(), st), "pack_weights")
             if self._pk_f is not self._pk_c:
                 check(lib.nerf_b200_pack_weights(C.byref(self._np_f), api._ptr(self._pk_f), self._pk_f.numel(), st), "pack_weights")
-            check(lib.nerf_b200_pack_rays(api._ptr(self.rays[0]), api._ptr(self.rays[1]), None, C.byref(self._cam), N, 0, self.ndc, self.near, self.far, 1,
-                                          api._ptr(self.packed_rays), st), "pack_rays")
             if self.t_rand is not None:
                 self.t_rand.uniform_()                                  # run_nerf.py:371
             if self.u_rand is not None:
@@ -185,9 +195,12 @@ class FusedTrainStep:
                                                api._stream(self.rays)), "adam_step")
 
     # ---- public ----
-    def step_device(self):
-        """One step on the rays / target already in `self.rays` ([2,N,3]) and `self.target` ([N,3]); no host sync."""
+    def step_device(self, c2w=None, pixel_index=None):
+        """One step on the rays / target already in `self.rays` ([2,N,3]) and `self.target` ([N,3]); no host sync.
+        With `c2w` [3,4] and `pixel_index` (int64 CUDA tensor [N] of row-major pixel ids) the rays are generated on the device
+        for those pixels of that pose instead (run_nerf.py:728-757 without get_rays' [H,W,3] tensors)."""
         import torch.distributed as dist
+        self._pack_rays(c2w, pixel_index)
         if self.graph is not None:
             self.graph.replay()
         else:

@@ -116,6 +116,26 @@ def test_create_nerf_structure(nb, tmp_path):
     assert "ndc" not in tr3 and "lindisp" not in tr3                                          # :250-253
 
 
+def test_keras_weight_import_matches_the_reference(nb):
+    """NeRF.load_weights_from_keras vs the reference's own (run_nerf_helpers.py:121-148) on a synthetic Keras-style weight list;
+    needs /root/reference (build container), otherwise checks the documented layout only."""
+    rng = np.random.default_rng(0)
+    shapes = [(63, 256)] + [(256, 256)] * 4 + [(319, 256)] + [(256, 256)] * 2 + [(256, 256), (283, 128), (128, 3), (256, 1)]
+    weights = []
+    for (i, o) in shapes:
+        weights += [rng.standard_normal((i, o)).astype(np.float32), rng.standard_normal((o,)).astype(np.float32)]
+    m = nb.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    m.load_weights_from_keras(weights)
+    assert torch.equal(m.pts_linears[5].weight, torch.from_numpy(weights[10].T)) and torch.equal(m.alpha_linear.bias, torch.from_numpy(weights[23]))
+    from oracle import ref_import
+    if ref_import.available():
+        _, rh = ref_import.load()
+        r = rh.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        r.load_weights_from_keras(weights)
+        for (ka, a), (kb, b) in zip(m.state_dict().items(), r.state_dict().items()):
+            assert ka == kb and torch.equal(a, b), ka
+
+
 def test_dropin_patch_list_covers_the_seam(nb):
     from nerf_pytorch_b200 import dropin
     for name in ("render", "render_rays", "batchify_rays", "raw2outputs", "create_nerf", "sample_pdf", "NeRF", "get_embedder"):
