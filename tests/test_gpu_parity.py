@@ -151,6 +151,32 @@ def test_config3_fern_ndc_4096_rays(G, prec):
 
 
 @needs_trained
+def test_psnr_on_the_analytic_scene_matches_the_reference(G):
+    """PSNR of the trained networks against the analytic ground truth they were trained on (oracle/gen_trained.py: a shaded unit
+    sphere on white) -- the reference's rendering (golden rgb_map) and ours must score the same (BASELINE config 5 asks for
+    PSNR; no dataset exists in the container, so the scene is analytic)."""
+    from oracle.gen_trained import sphere_targets
+    fx = load_golden("trained_lego_1024")
+    sb = G.synth.ray_batch("lego", int(fx["N"]), seed=int(fx["ray_seed"]))
+    gt = sphere_targets(sb["rays"][0], sb["rays"][1])
+    nets = _trained_nets(G)
+    st = {"psnr_reference_fp32_cpu": float(-10.0 * np.log10(np.mean((fx["rgb_map"] - gt) ** 2)))}
+    for prec in ("fp32", "tc_fp16"):
+        G.nb.set_precision(prec)
+        try:
+            with torch.no_grad():
+                rgb = G.nb.render(sb["H"], sb["W"], sb["K"], chunk=32768, rays=G.dev(sb["rays"]), ndc=False, near=2., far=6., use_viewdirs=True,
+                                  network_fn=nets[0], network_fine=nets[1], network_query_fn=G.query_fn(), N_samples=64, N_importance=128,
+                                  perturb=0., white_bkgd=True, raw_noise_std=0.)[0]
+        finally:
+            G.nb.set_precision("tc_fp16")
+        st[f"psnr_{prec}"] = float(G.nb.mse2psnr(G.nb.img2mse(rgb, G.dev(gt))).item())
+    _record("psnr_analytic_scene_trained_lego_1024", st)
+    print(st)
+    assert abs(st["psnr_fp32"] - st["psnr_reference_fp32_cpu"]) < 1e-3 and abs(st["psnr_tc_fp16"] - st["psnr_reference_fp32_cpu"]) < 2e-2, st
+
+
+@needs_trained
 def test_reference_tf32_deviates_as_much(G):
     """Context for the tensor-core gates: the UNMODIFIED reference on this GPU with TF32 matmuls (the default of its pinned torch
     1.11; same 10-bit mantissa as our fp16 operands) against its own fp32 run on the same GPU, next to our tc_fp16 path against
