@@ -21,6 +21,7 @@
 //   head_grads_kernel    rgb_linear gradients (CUDA cores, tiny); alpha_linear's and the per-ray row sums of d_hv are computed
 //                        by the wgrad kernel's spare warps from the tiles it streams anyway
 //   views_enc_wgrad_kernel  views_linears[0].weight[:, W:] from the per-ray sums and gamma(viewdir)
+//   views_feat_wgrad_kernel views_linears[0].weight[:, :W] = (d_hv^T h_{D-1}) W_feat^T + db_v b_feat^T (feature_linear's output is never stored)
 //
 // TMEM capacity is what shapes this: one layer's dW fills an SM's tensor memory, so the weight gradient cannot share
 // a kernel with a tile-major dgrad chain (ten layers would need ten SMs' worth); hence dgrad is tile-major (on-chip
@@ -78,7 +79,7 @@ struct SeedParams {
   uint32_t rec_mask, rec_grad; long long n_tiles;
 };
 
-__global__ void __launch_bounds__(256) dhv_seed_kernel(const SeedParams p) {
+__global__ void __launch_bounds__(256, 4) dhv_seed_kernel(const SeedParams p) {
   __shared__ float s_w[3 * 128];
   for (int i = threadIdx.x; i < 384; i += 256) s_w[i] = p.rgb_w[i];
   __syncthreads();
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) dhv_seed_kernel(const SeedParams p) {
       mk = *reinterpret_cast<const uint2*>(p.mask + (size_t)t * p.rec_mask + (uint32_t)p.D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u);
     }
     uint8_t* const g = p.grad + (size_t)t * p.rec_grad;
-#pragma unroll
+#pragma unroll 2
     for (int c8 = 0; c8 < 8; ++c8) {
       const int col = ch * 64 + c8 * 8;
       const uint32_t word = (c8 < 4) ? mk.x : mk.y;
@@ -647,7 +648,7 @@ struct HeadGradParams {
   float* rgb_w; float* rgb_b;
 };
 
-__global__ void __launch_bounds__(256) head_grads_kernel(const HeadGradParams p) {
+__global__ void __launch_bounds__(256, 4) head_grads_kernel(const HeadGradParams p) {
   __shared__ float s_acc[8][12 * 32 + 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane * 4;
@@ -663,8 +664,8 @@ __global__ void __launch_bounds__(256) head_grads_kernel(const HeadGradParams p)
     const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
     const int nv = (nrows - lr0 < 128) ? nrows - lr0 : 128;
     const uint8_t* hv = p.act + (size_t)t * p.rec_act + rec_act_hv(p.D);
-#pragma unroll 4
-    for (int r = warp; r < nv; r += 8) {
+#pragma unroll 8
+    for (int r = warp; r < nv; r += 8) {                  // 8 independent 256-byte row loads in flight per warp (the kernel is load-latency bound)
       const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + r];
       const uint2 w = *reinterpret_cast<const uint2*>(hv + img_off(r, c));
       const __half2 h01 = *reinterpret_cast<const __half2*>(&w.x), h23 = *reinterpret_cast<const __half2*>(&w.y);
@@ -689,14 +690,40 @@ __global__ void __launch_bounds__(256) head_grads_kernel(const HeadGradParams p)
   }
 }
 
-// views_linears[0].weight[c][W + e] += sum_rays dsum[ray][c] * gamma(viewdir_ray)[e]      (run_nerf_helpers.py:108-110)
+// views_linears[0].weight[c][W + e] += sum_rays dsum[ray][c] * gamma(viewdir_ray)[e]      (run_nerf_helpers.py:108-110);
+// block e == ICV: dbv[c] += sum_rays dsum[ray][c]  (this pass's bias gradient of views_linears[0], for the kernel below)
 __global__ void __launch_bounds__(128) views_enc_wgrad_kernel(const float* __restrict__ dsum, const float* __restrict__ encv, long long N, int ICV,
-                                                            float* __restrict__ views_w, int ld, int col0) {
+                                                            float* __restrict__ views_w, int ld, int col0, float* __restrict__ dbv) {
   const int e = blockIdx.x, c = threadIdx.x;
   const long long n0 = (long long)blockIdx.y * 64, n1 = (n0 + 64 < N) ? n0 + 64 : N;
   float s = 0.f;
-  for (long long n = n0; n < n1; ++n) s = fmaf(dsum[n * 128 + c], encv[n * ICV + e], s);
-  atomicAdd(views_w + (size_t)c * ld + col0 + e, s);
+  if (e < ICV) {
+    for (long long n = n0; n < n1; ++n) s = fmaf(dsum[n * 128 + c], encv[n * ICV + e], s);
+    atomicAdd(views_w + (size_t)c * ld + col0 + e, s);
+  } else {
+    for (long long n = n0; n < n1; ++n) s += dsum[n * 128 + c];
+    atomicAdd(dbv + c, s);
+  }
+}
+
+// views_linears[0].weight[v][f] (f < W) += sum_k G[v][k] W_feat[f][k] + dbv[v] b_feat[f], with G = d_hv^T h_{D-1} (the views job of
+// the wgrad kernel, already reduced and un-scaled): the feature layer has no activation, so
+//   d_hv^T feat = d_hv^T (h_{D-1} W_feat^T + 1 b_feat^T) = G W_feat^T + (sum_rows d_hv) b_feat^T
+// and feature_linear's output never has to be stored (run_nerf_helpers.py:107-110).  grid = 128 (v), block = 256 (f).
+__global__ void __launch_bounds__(256) views_feat_wgrad_kernel(const float* __restrict__ G, const float* __restrict__ dbv, const float* __restrict__ feat_w,
+                                                             const float* __restrict__ feat_b, float* __restrict__ views_w, int ld) {
+  __shared__ float s_g[256];
+  const int v = blockIdx.x, f = threadIdx.x;
+  s_g[f] = G[v * 256 + f];
+  __syncthreads();
+  const float4* w4 = reinterpret_cast<const float4*>(feat_w + (size_t)f * 256);
+  float acc = dbv[v] * feat_b[f];
+#pragma unroll 8
+  for (int k4 = 0; k4 < 64; ++k4) {
+    const float4 w = w4[k4];
+    acc = fmaf(s_g[4 * k4], w.x, acc); acc = fmaf(s_g[4 * k4 + 1], w.y, acc); acc = fmaf(s_g[4 * k4 + 2], w.z, acc); acc = fmaf(s_g[4 * k4 + 3], w.w, acc);
+  }
+  views_w[(size_t)v * ld + f] += acc;
 }
 
 }  // namespace nb

@@ -656,7 +656,7 @@ int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noi
 
 // ---- tensor-core backward of one pass (bwd_tc2.cuh) ------------------------------------------------
 namespace {
-struct BwdTcLayout { size_t off_amax, off_draw, off_encv, off_dsum, off_partial, off_grad, total; long long part_floats; };
+struct BwdTcLayout { size_t off_amax, off_draw, off_encv, off_dsum, off_gv, off_partial, off_grad, total; long long part_floats; };
 struct BwdTcJobs { int n; WgradJob w[WG2_MAX_JOBS]; ReduceJob r[WG2_MAX_JOBS]; int total_ctas; long long part_floats; };
 
 // jobs of the weight gradient and their CTA ranges (proportional to the bytes each job streams per tile)
@@ -671,8 +671,9 @@ BwdTcJobs make_bwd_jobs(const NerfNetParams& n, const NerfNetGrads* g, int sms) 
     r.Mc = Mc; r.Nc = Nc; r.n_valid = n_valid; r.ldw = ldw; r.dst = dst;
     ++J.n;
   };
-  // views_linears[0].weight[:, :W] = d_hv^T feat;  feature_linear = d_feat^T h_{D-1}
-  add(0, 128, rec_act_h(D), 256, g ? g->views_w : nullptr, W + ICV, W, g ? g->views_b : nullptr);
+  // job 0: G = d_hv^T h_{D-1} (-> views_linears[0].weight[:, :W] through views_feat_wgrad_kernel; its reduce target is a scratch
+  // block set by the caller);  job 1: feature_linear = d_feat^T h_{D-1}
+  add(0, 128, rec_act_h(D - 1), 256, nullptr, 256, 256, g ? g->views_b : nullptr);
   add(rec_grad_step(0), 256, rec_act_h(D - 1), 256, g ? g->feature_w : nullptr, W, W, g ? g->feature_b : nullptr);
   for (int l = D - 1; l >= 1; --l) {
     const bool sk = (n.skip >= 0 && l == n.skip + 1);
@@ -710,6 +711,7 @@ BwdTcLayout make_bwd_layout(long long N, int S, const NerfNetParams& n, const Ti
   L.off_draw = o;    o = up(o + (size_t)N * S * 16);
   L.off_encv = o;    o = up(o + (size_t)N * (n.input_ch_views > 0 ? n.input_ch_views : 1) * 4);
   L.off_dsum = o;    o = up(o + (size_t)N * 128 * 4);
+  L.off_gv = o;      o = up(o + (size_t)(128 * 256 + 128) * 4);      // G = d_hv^T h_{D-1} (reduced) and this pass's db_v
   L.off_partial = o; o = up(o + (size_t)part_floats * 4);
   L.off_grad = o;    o = up(o + (size_t)plan.n_tiles * rec_grad_bytes(n.D));
   L.total = o; L.part_floats = part_floats;
@@ -770,6 +772,8 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
   float* d_raw = reinterpret_cast<float*>(ws + LY.off_draw);
   float* encv = reinterpret_cast<float*>(ws + LY.off_encv);
   float* dsum = reinterpret_cast<float*>(ws + LY.off_dsum);
+  float* gv = reinterpret_cast<float*>(ws + LY.off_gv);
+  float* dbv = gv + 128 * 256;
   float* partial = reinterpret_cast<float*>(ws + LY.off_partial);
   uint8_t* grec = ws + LY.off_grad;
   const uint8_t* act = static_cast<const uint8_t*>(save->act);
@@ -782,6 +786,7 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
   // 1. loss scale from max |dL/drgb_map|; compositing adjoint -> dL/draw
   NB_CUDA(cudaMemsetAsync(amax, 0, 256, st));
   NB_CUDA(cudaMemsetAsync(dsum, 0, (size_t)N * 128 * 4, st));
+  NB_CUDA(cudaMemsetAsync(gv, 0, (size_t)(128 * 256 + 128) * 4, st));
   absmax_kernel<<<cdiv(N * 3, 1024) < 64 ? cdiv(N * 3, 1024) : 64, 256, 0, st>>>(g_rgb, N * 3, amax);
   NB_LAUNCH_OK("absmax_kernel");
   NB_TRY(nerf_b200_raw2outputs_bwd(raw, z_vals, rays + 3, rs, noise, N, S, cfg->white_bkgd, g_rgb, d_raw, stream));
@@ -790,7 +795,7 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
   sp.d_raw = d_raw; sp.mask = mask; sp.grad = grec; sp.rgb_w = net->rgb_w; sp.amax = amax;
   sp.N = N; sp.S = S; sp.rays_per_cta = plan.rays_per_cta; sp.nst_plan = plan.nst; sp.D = D;
   sp.rec_mask = rec_mask_bytes(D); sp.rec_grad = rec_grad_bytes(D); sp.n_tiles = plan.n_tiles;
-  dhv_seed_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(sp);
+  dhv_seed_kernel<<<(int)(plan.n_tiles < 8 * sms ? plan.n_tiles : 8 * sms), 256, 0, st>>>(sp);
   NB_LAUNCH_OK("dhv_seed_kernel");
   // 3. dgrad chain (CTA pairs, the forward's tile order)
   const long long rows = N * (long long)S;
@@ -838,6 +843,7 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     ReduceParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.partial = partial; rp.amax = amax; rp.njobs = J.n;
+    J.r[0].dst = gv;                                  // job 0 reduces into the scratch block G
     for (int i = 0; i < J.n; ++i) rp.jobs[i] = J.r[i];
     dim3 rg(256, J.n);
     wgrad_reduce_kernel<<<rg, 256, 0, st>>>(rp);
@@ -853,11 +859,13 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     hp.N = N; hp.S = S; hp.rays_per_cta = plan.rays_per_cta; hp.nst_plan = plan.nst; hp.D = D;
     hp.rec_act = rec_act_bytes(D); hp.n_tiles = plan.n_tiles;
     hp.rgb_w = grads->rgb_w; hp.rgb_b = grads->rgb_b;
-    head_grads_kernel<<<(int)(plan.n_tiles < 2 * sms ? plan.n_tiles : 2 * sms), 256, 0, st>>>(hp);
+    head_grads_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(hp);
     NB_LAUNCH_OK("head_grads_kernel");
-    dim3 vg(ICV, cdiv(N, 64));
-    views_enc_wgrad_kernel<<<vg, 128, 0, st>>>(dsum, encv, N, ICV, grads->views_w, net->W + ICV, net->W);
+    dim3 vg(ICV + 1, cdiv(N, 64));
+    views_enc_wgrad_kernel<<<vg, 128, 0, st>>>(dsum, encv, N, ICV, grads->views_w, net->W + ICV, net->W, dbv);
     NB_LAUNCH_OK("views_enc_wgrad_kernel");
+    views_feat_wgrad_kernel<<<128, 256, 0, st>>>(gv, dbv, net->feature_w, net->feature_b, grads->views_w, net->W + ICV);
+    NB_LAUNCH_OK("views_feat_wgrad_kernel");
   }
   return 0;
 }

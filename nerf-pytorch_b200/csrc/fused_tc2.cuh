@@ -15,7 +15,7 @@
 //   d_full[2]  both    : multicast commit -> both CTAs' epilogue warps of that slot
 //   act[2]     leader  : 16 arrivals = one per epilogue warp of the slot, 8 local + 8 remote (accumulator drained, A tile written)
 //   enc_full   leader  : 2 arrivals (both sampler warps);  enc_free both: multicast commit after the last encoding chunk
-// Training mode (template parameter EMIT, train_common.cuh): every A tile the epilogue writes (h_l, feat), the
+// Training mode (template parameter EMIT, train_common.cuh): every post-ReLU A tile the epilogue writes (h_l), the
 // encodings and the view layer's post-ReLU output are also copied to a per-tile record in global memory with
 // cp.async.bulk shared -> global, plus the sign bits of the pre-activations; two CTA-local barriers per slot:
 //   st_full[2] local   : 8 arrivals = the slot's epilogue warps wrote the tile (warp e == 0 then issues the bulk store)
@@ -301,6 +301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         if (e == 0 && lane == 0) { ptx::bulk_wait_read0(); ptx::mbar_arrive(bar_stdone + 8 * X); }
         ptx::mbar_wait(bar_stdone + 8 * X, sdph);
         sdph ^= 1;
+        st_pending = false;
       }
     };
     // all 8 warps of the slot have written (and proxy-fenced) their part of the tile: warp e == 0 copies `bytes` from
@@ -406,7 +407,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           arrive_leader(bar_act + 8 * X);
           if (EMIT) {
             if (l < D) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-            emit_store(arec + rec_act_h(l), act_base, 65536u);     // h_l (l < D) or feat (l == D)
+            if (l < D) emit_store(arec + rec_act_h(l), act_base, 65536u);     // h_l; feature_linear's output (l == D) is not recorded
           }
           if (tr) trp[2] = clock64();
           if (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) { p.trace[2500 + blockIdx.x * 32 + (warp - 4) * 2] = t_f; p.trace[2501 + blockIdx.x * 32 + (warp - 4) * 2] = clock64(); }

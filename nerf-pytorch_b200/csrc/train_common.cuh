@@ -10,8 +10,9 @@
 //   activation record (forward -> backward), rec_act_bytes(D):
 //     [0, 16 KB)                       enc    : gamma(p), 64 columns (63 + zero pad)
 //     [16 KB + l * 64 KB), l < D       h_l    : post-ReLU output of pts_linears[l]        (run_nerf_helpers.py:99-101)
-//     [16 KB + D * 64 KB)              feat   : feature_linear output (no activation)      (:107)
-//     [16 KB + (D+1) * 64 KB), 32 KB   hv     : post-ReLU output of views_linears[0]       (:110-112)
+//     [16 KB + D * 64 KB), 32 KB       hv     : post-ReLU output of views_linears[0]       (:110-112)
+//   (feature_linear's output is NOT recorded: its only consumer, the weight gradient of views_linears[0], is rewritten as
+//    dW_v[:, :W] = (d_hv^T h_{D-1}) W_feat^T + db_v b_feat^T, which reads h_{D-1} -- already recorded -- instead)
 //   mask record, rec_mask_bytes(D): sign bits of the pre-activations (1 = not positive = ReLU gradient 0)
 //     layer l < D : l * 4096 + ch * 2048 + r * 16  : uint4 = columns [ch*128, ch*128+128), word b = columns b*32..
 //     hv          : D * 4096 + ch * 1024 + r * 8   : uint2 = columns [ch*64, ch*64+64)
@@ -49,9 +50,9 @@ static inline TilePlan make_tile_plan(long long N, int S, int sms) {
   return t;
 }
 
-__host__ __device__ __forceinline__ uint32_t rec_act_bytes(int D) { return 16384u + (uint32_t)(D + 1) * 65536u + 32768u; }
-__host__ __device__ __forceinline__ uint32_t rec_act_h(int l) { return 16384u + (uint32_t)l * 65536u; }              // l == D: feat
-__host__ __device__ __forceinline__ uint32_t rec_act_hv(int D) { return 16384u + (uint32_t)(D + 1) * 65536u; }
+__host__ __device__ __forceinline__ uint32_t rec_act_bytes(int D) { return 16384u + (uint32_t)D * 65536u + 32768u; }
+__host__ __device__ __forceinline__ uint32_t rec_act_h(int l) { return 16384u + (uint32_t)l * 65536u; }              // l < D
+__host__ __device__ __forceinline__ uint32_t rec_act_hv(int D) { return 16384u + (uint32_t)D * 65536u; }
 __host__ __device__ __forceinline__ uint32_t rec_mask_bytes(int D) { return (uint32_t)D * 4096u + 2048u; }
 __host__ __device__ __forceinline__ uint32_t rec_grad_bytes(int D) { return 32768u + (uint32_t)(D + 1) * 65536u; }
 __host__ __device__ __forceinline__ uint32_t rec_grad_step(int j) { return 32768u + (uint32_t)j * 65536u; }         // output of dgrad step j

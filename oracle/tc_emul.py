@@ -105,7 +105,8 @@ def backward(sd: dict, acts: dict, masks: dict, d_raw: torch.Tensor, scale: floa
     g["alpha_linear.weight"] = d_sig.t() @ acts["h16"][D - 1]
     g["alpha_linear.bias"] = d_sig.sum(0)
     gv = torch.zeros_like(sd["views_linears.0.weight"])
-    gv[:, :256] = d_hv16.t() @ acts["feat16"] * inv
+    # feature_linear's output is not recorded: d_hv^T feat = (d_hv^T h_{D-1}) W_feat^T + (sum_rows d_hv) b_feat^T  (csrc/bwd_tc2.cuh)
+    gv[:, :256] = (d_hv16.t() @ acts["h16"][D - 1] * inv) @ sd["feature_linear.weight"].t() + torch.outer(d_hv16.sum(0) * inv, sd["feature_linear.bias"])
     dsum = torch.zeros((n_rays, 128), dtype=torch.float64).index_add_(0, ray_of_row, d_hv16 * inv)
     encv_ray = torch.zeros((n_rays, acts["encv"].shape[1]), dtype=torch.float64)
     encv_ray[ray_of_row] = acts["encv"]

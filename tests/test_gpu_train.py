@@ -110,9 +110,9 @@ def test_training_forward_records(G, N, S):
     assert not np.isnan(enc).any()
     stats["enc_close"] = _close_frac(enc, ref_enc, 2e-3, 1e-4)
     assert stats["enc_close"] > 0.995, stats
-    for l in range(D + 1):
+    for l in range(D):
         h = R.gather_image(A, plan, plan.rec_act, 16384 + l * 65536, 256)
-        ref = (em["h16"][l] if l < D else em["feat16"]).numpy()
+        ref = em["h16"][l].numpy()
         assert not np.isnan(h).any(), l
         stats[f"h{l}_rel"] = rel_l2(h, ref)
         assert stats[f"h{l}_rel"] < 2e-3, (l, stats)
@@ -120,7 +120,7 @@ def test_training_forward_records(G, N, S):
             m = R.gather_mask(Mk, plan, l, D)
             stats[f"mask{l}_mismatch"] = float(np.mean(m != (h > 0)))
             assert stats[f"mask{l}_mismatch"] < 2e-4, (l, stats)          # fp16 underflow of a positive pre-activation only
-    hv = R.gather_image(A, plan, plan.rec_act, 16384 + (D + 1) * 65536, 128)
+    hv = R.gather_image(A, plan, plan.rec_act, 16384 + D * 65536, 128)
     stats["hv_rel"] = rel_l2(hv, em["hv16"].numpy())
     assert stats["hv_rel"] < 2e-3, stats
     mv = R.gather_mask(Mk, plan, 0, D, hv=True)
@@ -203,8 +203,7 @@ def test_backward_stages_match_emulation(G, N, S, sharpen):
     # --- saved tensors decoded from the CUDA records ---
     acts = {"enc16": torch.from_numpy(R.gather_image(A, plan, plan.rec_act, 0, 64)).double(),
             "h16": [torch.from_numpy(R.gather_image(A, plan, plan.rec_act, 16384 + l * 65536, 256)).double() for l in range(D)],
-            "feat16": torch.from_numpy(R.gather_image(A, plan, plan.rec_act, 16384 + D * 65536, 256)).double(),
-            "hv16": torch.from_numpy(R.gather_image(A, plan, plan.rec_act, 16384 + (D + 1) * 65536, 128)).double()}
+            "hv16": torch.from_numpy(R.gather_image(A, plan, plan.rec_act, 16384 + D * 65536, 128)).double()}
     vd = np.repeat(packed[:, 8:11], S, 0)
     acts["encv"] = E.T.embed(torch.from_numpy(vd), 4).double()
     masks = {"h": [torch.from_numpy(R.gather_mask(Mk, plan, l, D)).double() for l in range(D)],
