@@ -214,6 +214,26 @@ size_t nerf_b200_march_bwd_tc_workspace_bytes(int64_t N, int S, const NerfNetPar
  * out[12] = off_d_raw, off_grad_records, rec_act_bytes, rec_mask_bytes, rec_grad_bytes, grid, rays_per_cta, nst,
  * n_tiles, off_amax, off_dsum, off_partial */
 int nerf_b200_march_bwd_tc_layout(int64_t N, int S, const NerfNetParams* net, int64_t* out);
+/* Backward of BOTH passes of one render_rays call -- what loss.backward() triggers for loss = img2mse(rgb) + img2mse(rgb0)
+ * (run_nerf.py:765-772; z_samples is detached at :394, so the two passes are independent).  Same kernels as
+ * nerf_b200_march_bwd_tc per pass, but scheduled together: the data-gradient chain of one pass (HBM-write-bound) runs on
+ * part of the SMs next to the weight gradient of the other pass / previous chunk (HBM-read-bound) on a side stream that forks
+ * from and joins `stream` (CUDA-graph capturable).  `fine` may be NULL (N_importance == 0). */
+typedef struct {
+  const float* z_vals;      /* [N,S] */
+  const float* noise;       /* [N,S] or NULL */
+  int S;
+  const NerfNetParams* net;
+  const void* packed;
+  const float* raw;         /* [N,S,4] of the training-mode pass */
+  const NerfTrainSave* save;
+  const float* g_rgb;       /* dL/drgb_map [N,3] */
+  const NerfNetGrads* grads;
+} NerfBwdPass;
+int nerf_b200_render_rays_bwd_tc(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfBwdPass* coarse,
+                                 const NerfBwdPass* fine, void* workspace, size_t workspace_bytes, void* stream);
+size_t nerf_b200_render_rays_bwd_tc_workspace_bytes(int64_t N, int S_coarse, const NerfNetParams* net_coarse, int S_fine,
+                                                    const NerfNetParams* net_fine);
 /* exact mode (csrc/bwd_simt.cuh): fp32 recompute with saved activations + fp32 CUDA-core GEMMs; any network
  * the exact forward supports (with or without view directions). */
 int nerf_b200_march_bwd(const float* rays, const float* z_vals, const float* noise, int64_t N, int S,

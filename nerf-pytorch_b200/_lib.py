@@ -52,6 +52,11 @@ class NerfTrainSave(C.Structure):
     _fields_ = [("act", c_fp), ("act_bytes", C.c_size_t), ("mask", c_fp), ("mask_bytes", C.c_size_t)]
 
 
+class NerfBwdPass(C.Structure):
+    _fields_ = [("z_vals", c_fp), ("noise", c_fp), ("S", C.c_int), ("net", C.POINTER(NerfNetParams)), ("packed", c_fp), ("raw", c_fp),
+                ("save", C.POINTER(NerfTrainSave)), ("g_rgb", c_fp), ("grads", C.POINTER(NerfNetGrads))]
+
+
 # name -> (restype, argtypes); mirrors include/nerf_b200.h one to one
 SIGNATURES = {
     "nerf_b200_abi_version": (C.c_int, []),
@@ -94,6 +99,9 @@ SIGNATURES = {
                                          C.POINTER(NerfNetGrads), c_fp, C.c_size_t, c_fp]),
     "nerf_b200_march_bwd_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.POINTER(NerfNetParams)]),
     "nerf_b200_march_bwd_tc_layout": (C.c_int, [C.c_int64, C.c_int, C.POINTER(NerfNetParams), C.POINTER(C.c_int64)]),
+    "nerf_b200_render_rays_bwd_tc": (C.c_int, [c_fp, C.c_int64, C.POINTER(NerfRenderCfg), C.POINTER(NerfBwdPass), C.POINTER(NerfBwdPass),
+                                               c_fp, C.c_size_t, c_fp]),
+    "nerf_b200_render_rays_bwd_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.POINTER(NerfNetParams), C.c_int, C.POINTER(NerfNetParams)]),
     "nerf_b200_march_bwd": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, C.POINTER(NerfNetParams), c_fp,
                                       C.POINTER(NerfRenderCfg), c_fp, C.POINTER(NerfNetGrads), c_fp, C.c_size_t, c_fp]),
     "nerf_b200_march_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.POINTER(NerfNetParams)]),
@@ -114,6 +122,8 @@ DEV_SIGNATURES = {
     "nerf_b200_debug_ldtm_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_debug_issue_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "nerf_b200_debug_l2_stream": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
+    "nerf_b200_debug_dram_stream": (C.c_int, [c_fp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
+    "nerf_b200_debug_hbm_stream": (C.c_int, [c_fp, c_fp, C.c_size_t, C.c_int, C.c_int, c_fp]),
     "nerf_b200_selftest_gemm": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, C.c_size_t, c_fp]),
     "nerf_b200_selftest_gemm_tn": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp]),
 }

@@ -533,6 +533,21 @@ class _RenderRays(torch.autograd.Function):
         if fine:
             passes.append((g_fine, z_f, noise1, net_c if same_net else net_f, grads_f, rec[3:6]))
         with _on(ray_batch):
+            if ctx.train_tc and fine and g_fine is not None and g_coarse is not None:
+                # both passes in one call: the chain of one pass runs next to the weight gradient of the other (capi.cu)
+                keep, bp = [], []
+                for g_rgb, z, noise, net, gbuf, rc in passes:
+                    raw, act, mask = rc
+                    n, gs, g_rgb = net.net_params(), net.grad_struct(gbuf), g_rgb.contiguous().float()
+                    sv = NerfTrainSave(_ptr(act), act.numel(), _ptr(mask), mask.numel())
+                    keep += [n, gs, g_rgb, sv]
+                    bp.append(_lib.NerfBwdPass(_ptr(z), _ptr(noise if noise.numel() else None), z.shape[1], C.pointer(n), _ptr(net.packed()),
+                                               _ptr(raw), C.pointer(sv), _ptr(g_rgb), C.pointer(gs)))
+                ws_bytes = lib.nerf_b200_render_rays_bwd_tc_workspace_bytes(N, bp[0].S, bp[0].net, bp[1].S, bp[1].net)
+                ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=ray_batch.device)
+                check(lib.nerf_b200_render_rays_bwd_tc(_ptr(ray_batch), N, C.byref(cfg), C.byref(bp[0]), C.byref(bp[1]), _ptr(ws), ws_bytes,
+                                                       _stream(ray_batch)), "render_rays_bwd_tc")
+                passes = []
             for g_rgb, z, noise, net, gbuf, rc in passes:
                 if g_rgb is None:
                     continue

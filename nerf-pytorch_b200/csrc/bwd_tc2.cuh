@@ -11,7 +11,7 @@
 //   dgrad_tc2_kernel     the chain  d_hv -> d_feat -> dA_{D-1} -> ... -> dA_0  as tcgen05 cta_group::2 passes with
 //                        TRANSPOSED weight chunks streamed through the forward's 7 x 8 KB TMA ring; the epilogue applies
 //                        the ReLU mask (and the alpha_linear rank-1 term), writes the next A tile in place and the same
-//                        tile goes to the gradient record with one bulk store.  Same warp roles / barriers as the
+//                        tile goes to the gradient record, one 16 KB K-block per bulk store.  Same warp roles / barriers as the
 //                        forward pair kernel (fused_tc2.cuh); activation gradients never leave the SM between layers.
 //   wgrad_tc_kernel      dW_l += dA_l^T H_{l-1}: both operands MN-major straight from the images (no re-layout), the
 //                        CTAs are partitioned over the layers so that each holds ONE layer's dW in TMEM across all of
@@ -122,6 +122,7 @@ struct DgradParams {
   long long N; int S, rays_per_cta, nst_plan, D;
   uint32_t rec_mask, rec_grad;
   unsigned long long pair_half_bytes;       // bytes of one rank's half of the backward chunk stream
+  int vc0, vc1;                             // forward CTAs [vc0, vc1) (both even): this launch's CTA b serves vc0 + b, vc0 + b + gridDim, ...
 };
 
 constexpr uint32_t DG2_SEED = SM_ENC;                                        // 131072: 32 KB, d_hv of ONE slot
@@ -161,8 +162,6 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
   const uint32_t bar_act = sb + DG2_BARS + 128;        // [2] (leader) 16 epilogue warps
   const uint32_t bar_seedfull = sb + DG2_BARS + 144;   //     (leader) TMA bytes of both CTAs' seed tiles
   const uint32_t bar_seedfree = sb + DG2_BARS + 152;   //     multicast commit after the last step-0 MMA
-  const uint32_t bar_stfull = sb + DG2_BARS + 160;     // [2] local, 8 epilogue warps
-  const uint32_t bar_stdone = sb + DG2_BARS + 176;     // [2] local
   auto arrive_leader = [&](uint32_t bar) {
     __syncwarp();
     if (lane == 0) {
@@ -171,10 +170,9 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     }
   };
 
-  // this CTA's rows: exactly the forward's split (same blockIdx -> same rays -> same tile records)
-  const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, (int)blockIdx.x);
-  const int nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, (int)blockIdx.x);
-  const long long row_begin = (long long)blockIdx.x * p.rays_per_cta * p.S;
+  // rows: exactly the forward's split (forward CTA vc -> same rays -> same tile records).  The launch may be narrower than the
+  // forward's (gridDim even, so a pair keeps its ranks): each pair then walks the forward pairs b/2, b/2 + gridDim/2, ... --
+  // this is what lets the chain share the GPU with the weight-gradient kernel of the other pass (capi.cu).
   const int D = p.D, NS = D + 1;
 
   for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_alpha[i] = p.alpha_w[i];
@@ -182,7 +180,6 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     for (int i = 0; i < TC2_NST; ++i) { ptx::mbar_init(bar_wfull + 8 * i, 1); ptx::mbar_init(bar_wempty + 8 * i, 1); }
     for (int x = 0; x < 2; ++x) {
       ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 16);
-      ptx::mbar_init(bar_stfull + 8 * x, 8); ptx::mbar_init(bar_stdone + 8 * x, 1);
     }
     ptx::mbar_init(bar_seedfull, 1);
     ptx::mbar_init(bar_seedfree, 1);
@@ -199,7 +196,8 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     // =========================== weight producer (both CTAs): this CTA's 8 KB half of every unit ===========
     uint32_t stage = 0, ph = 0;
     const int half_rows = (int)(p.pair_half_bytes >> 9);
-    for (int st = 0; st < nst; ++st) {
+    for (int vc = p.vc0 + (int)blockIdx.x; vc < p.vc1; vc += (int)gridDim.x)
+    for (int st = 0, nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, vc); st < nst; ++st) {
       int row = (int)rank * half_rows;
       for (int j = 0; j < NS; ++j) {
         const int nu = bwd_step_units(j);
@@ -226,7 +224,8 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     const uint64_t bdesc0 = ptx::umma_desc(sb, 512, ptx::UMMA_SW64);
     const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = ptx::umma_idesc_f16(256, 256);
-    for (int st = 0; st < nst; ++st) {
+    for (int vc = p.vc0 + (int)blockIdx.x; vc < p.vc1; vc += (int)gridDim.x)
+    for (int st = 0, nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, vc); st < nst; ++st) {
       for (int j = 0; j < NS; ++j) {
         const int nu = bwd_step_units(j);
         for (int X = 0; X < 2; ++X) {
@@ -234,7 +233,7 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
           // slot X's accumulator drained (and, for j >= 1, its A tile written) by both CTAs' epilogue warps
           if (X == 0) { ptx::mbar_wait_cluster(bar_act, actph0); actph0 ^= 1; }
           else { ptx::mbar_wait_cluster(bar_act + 8, actph1); actph1 ^= 1; }
-          if (j == 0) ptx::mbar_wait_cluster(bar_seedfull, (uint32_t)((st * 2 + X) & 1));
+          if (j == 0) ptx::mbar_wait_cluster(bar_seedfull, (uint32_t)X);        // one seed per (super-tile, slot): phase parity = X
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             uint32_t s_ = stage, ph_ = ph;
@@ -280,13 +279,13 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     // =========================== seed loader (both CTAs): d_hv tile of (super-tile, slot) -> SEED ===========
     // one 32 KB box of the gradient-record tensor map per (st, X); bytes of both CTAs are counted on the leader's barrier
     const int rec_rows = (int)(p.rec_grad >> 9);
-    for (int st = 0; st < nst; ++st) {
+    for (int vc = p.vc0 + (int)blockIdx.x; vc < p.vc1; vc += (int)gridDim.x)
+    for (int st = 0, nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, vc); st < nst; ++st) {
       for (int X = 0; X < 2; ++X) {
-        const int i = st * 2 + X;
-        ptx::mbar_wait(bar_seedfree, (uint32_t)((i & 1) ^ 1));
+        ptx::mbar_wait(bar_seedfree, (uint32_t)(X ^ 1));
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_arrive_expect_tx(bar_seedfull, 2u * 32768u);
-          const long long t = ((long long)blockIdx.x * p.nst_plan + st) * 2 + X;
+          const long long t = ((long long)vc * p.nst_plan + st) * 2 + X;
           ptx::tma2_load_2d(sb + DG2_SEED, (const void*)&gmap, 0, (int)(t * rec_rows), bar_seedfull);
         }
         __syncwarp();
@@ -300,15 +299,32 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     const uint32_t act_base = sb + SM_ACT + X * 65536;
     const float scale = loss_scale_from_absmax(__uint_as_float(*p.amax));
     arrive_leader(bar_act + 8 * X);                            // accumulator initially free
-    uint32_t dph = 0, sfph = 0, sdph = 0;
-    bool st_pending = false;
+    uint32_t dph = 0;
     uint32_t swk[8];
+    // gradient record: each 16 KB K-block of the A tile is bulk-copied out as soon as the four warps (q = 0..3) that share a
+    // column half have written it, and the next step waits per K-block for the copy that still reads it (as in the forward's
+    // training mode, fused_tc2.cuh).  Lane 0 of warp q == 0 issues and waits; named barrier 3 + 2 X + ch joins the four warps.
+    const int emit_bar = 3 + X * 2 + ch;
+    const bool emit_issuer = (q == 0) && lane == 0;
+    auto emit_gate = [&]() {
+      if (emit_issuer) ptx::bulk_wait_read1();
+      ptx::named_bar_sync(emit_bar, 128);
+    };
+    auto emit_kblock = [&](uint8_t* dst, uint32_t src) {
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(emit_bar, 128);
+      if (emit_issuer) { ptx::bulk_s2g(dst, src, 16384u); ptx::bulk_commit(); }
+    };
 #pragma unroll
     for (int c = 0; c < 8; ++c) swk[c] = act_base + (uint32_t)(ch * 2) * 16384u + act_row_off(r) + (uint32_t)((c ^ (r & 7)) << 4);
+    for (int vc = p.vc0 + (int)blockIdx.x; vc < p.vc1; vc += (int)gridDim.x) {
+    const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, vc);
+    const int nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, vc);
+    const long long row_begin = (long long)vc * p.rays_per_cta * p.S;
     for (int st = 0; st < nst; ++st) {
       const int lr = st * TC_ST + X * TC_TILE + r;
       const bool valid = lr < nrows;
-      const long long t = ((long long)blockIdx.x * p.nst_plan + st) * 2 + X;
+      const long long t = ((long long)vc * p.nst_plan + st) * 2 + X;
       const uint8_t* const mrec = p.mask + (size_t)t * p.rec_mask;
       uint8_t* const grec = p.grad + (size_t)t * p.rec_grad;
       const float dsig = valid ? p.d_raw[(row_begin + lr) * 4 + 3] * scale : 0.f;
@@ -319,11 +335,6 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
         ptx::mbar_wait(bar_dfull + 8 * X, dph);
         dph ^= 1;
         ptx::tc_fence_after();
-        if (st_pending) {                                       // the previous bulk store has finished reading the A tile
-          if (e == 0 && lane == 0) { ptx::bulk_wait_read0(); ptx::mbar_arrive(bar_stdone + 8 * X); }
-          ptx::mbar_wait(bar_stdone + 8 * X, sdph);
-          sdph ^= 1;
-        }
         const int colw = ch * 128;
         uint32_t va[32], vb[32];
         ptx::tmem_ld_x32(t_lane + colw, va);
@@ -349,28 +360,23 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = mask_apply(m, i, x[i]);
           }
+          // next step's A operand, in place; batches 0, 1 fill K-block 2 ch, batches 2, 3 K-block 2 ch + 1
+          if (b == 0) emit_gate();
+          if (b == 2) {
+            emit_kblock(grec + rec_grad_step(j) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
+            emit_gate();
+          }
           if (b == 0) store_grad32_pre<0>(x, swk); else if (b == 1) store_grad32_pre<32>(x, swk);
           else if (b == 2) store_grad32_pre<64>(x, swk); else store_grad32_pre<96>(x, swk);
         }
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         arrive_leader(bar_act + 8 * X);
-        // the tile (next step's A operand) also goes to the gradient record: wgrad reads it from there
-        if (lane == 0) ptx::mbar_arrive(bar_stfull + 8 * X);
-        if (e == 0) {
-          ptx::mbar_wait(bar_stfull + 8 * X, sfph);
-          sfph ^= 1;
-          if (lane == 0) {
-            uint8_t* dst = grec + rec_grad_step(j);
-            for (uint32_t o = 0; o < 65536u; o += 16384u) ptx::bulk_s2g(dst + o, act_base + o, 16384u);
-            ptx::bulk_commit();
-          }
-          __syncwarp();
-        }
-        st_pending = true;
+        emit_kblock(grec + rec_grad_step(j) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
       }
     }
-    if (e == 0 && lane == 0) ptx::bulk_wait_all();
+    }
+    if (emit_issuer) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before();
@@ -385,8 +391,9 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
 // serves a job, CTA g of G takes the job's tiles g, g + G, ...  Stage = one 64-row half tile of A and of B.
 // 192 threads: warps 0-3 column sums (bias gradient) while streaming, then the TMEM epilogue; warp 4 producer; warp 5 issuer.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int WG2_THREADS = 192, WG2_NSTAGE = 3, WG2_MAX_JOBS = 16;
-constexpr uint32_t WG2_STAGE = 65536, WG2_BARS = WG2_NSTAGE * WG2_STAGE, WG2_DSIG = WG2_BARS + 128, WG2_TOTAL = WG2_DSIG + 1024;
+constexpr int WG2_THREADS = 192, WG2_MAX_STAGES = 4, WG2_MAX_JOBS = 16;
+constexpr uint32_t WG2_BARS = 196608,                  // ring: 192 KB = 3 stages of a 256 + 256 column job
+                   WG2_DSIG = WG2_BARS + 128, WG2_TOTAL = WG2_DSIG + 1024;
 
 struct WgradJob {
   uint32_t a_off, b_off;        // image offsets inside the gradient / activation record
@@ -402,6 +409,9 @@ struct WgradParams {
   const uint8_t* act; const uint8_t* grad; uint32_t rec_act, rec_grad;
   long long N; int S, rays_per_cta, nst_plan; long long n_tiles;
   const unsigned int* amax; float* partial; const float* d_raw; int njobs;
+  long long t0, t1;             // tiles [t0, t1) of the plan (a launch may cover part of a pass; the reduction adds up)
+  int dbg;                      // experiments (NERF_B200_DBG_WGRAD): 1 = no MMA (stream only; results are garbage)
+  unsigned long long* prof;     // experiments (NERF_B200_DBG_WGRAD_PROF): [CTA][2] globaltimer at start / end, or NULL
   WgradJob jobs[WG2_MAX_JOBS];
 };
 
@@ -410,20 +420,22 @@ __device__ __forceinline__ bool plan_tile_valid(const WgradParams& p, long long 
   return st < plan_cta_nst(p.N, p.S, p.rays_per_cta, cta);
 }
 
-__global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradParams p) {
+// (launched as 2-CTA clusters only so that its CTAs fill whole TPCs: next to it the chain's CTA pairs need both SMs of a TPC)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradParams p) {
   uint8_t* smem = tc_smem;
   const uint32_t sb = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((sb & 1023u) != 0) __trap();
   int ji = -1;
   for (int i = 0; i < p.njobs; ++i) if ((int)blockIdx.x >= p.jobs[i].cta0 && (int)blockIdx.x < p.jobs[i].cta0 + p.jobs[i].ncta) ji = i;
+  if (p.prof && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[2 * blockIdx.x] = t_; }
   if (ji < 0) return;                                   // (uniform per CTA, before any barrier / allocation)
   const WgradJob job = p.jobs[ji];
   const int g = (int)blockIdx.x - job.cta0, G = job.ncta;
   const uint32_t bar_full = sb + WG2_BARS, bar_empty = sb + WG2_BARS + 32, bar_done = sb + WG2_BARS + 64;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + WG2_BARS + 96);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WG2_NSTAGE; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 5); }
+    for (int i = 0; i < WG2_MAX_STAGES; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 5); }
     ptx::mbar_init(bar_done, 1);
     ptx::fence_mbar_init();
   }
@@ -434,12 +446,15 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
   const uint32_t tmem = *s_tmem;
   const int xkb = job.Mc >> 6, ykb = job.Nc >> 6;
   const uint32_t ybase = (uint32_t)xkb * 8192u;
+  // ring: as many stages of this job's size as fit (narrow jobs get a 4th: the bytes in flight per SM set its share of the bus)
+  const uint32_t stride = (uint32_t)(xkb + ykb) * 8192u;
+  const uint32_t nstg = (WG2_BARS / stride < (uint32_t)WG2_MAX_STAGES) ? WG2_BARS / stride : (uint32_t)WG2_MAX_STAGES;
   long long my_halves = 0;
-  for (long long t = g; t < p.n_tiles; t += G) if (plan_tile_valid(p, t)) my_halves += 2;
+  for (long long t = p.t0 + g; t < p.t1; t += G) if (plan_tile_valid(p, t)) my_halves += 2;
 
   if (warp == 4) {
     uint32_t s = 0, ph = 0;
-    for (long long t = g; t < p.n_tiles; t += G) {
+    for (long long t = p.t0 + g; t < p.t1; t += G) {
       if (!plan_tile_valid(p, t)) continue;
       for (int h = 0; h < 2; ++h) {
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -447,11 +462,11 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
           ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(xkb + ykb) * 8192u);
           const uint8_t* xs = p.grad + (size_t)t * p.rec_grad + job.a_off + h * 8192;
           const uint8_t* ys = p.act + (size_t)t * p.rec_act + job.b_off + h * 8192;
-          for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s(sb + s * WG2_STAGE + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s);
-          for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s(sb + s * WG2_STAGE + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s);
+          for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s(sb + s * stride + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s);
+          for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s(sb + s * stride + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s);
         }
         __syncwarp();
-        if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
+        if (++s == nstg) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -461,8 +476,10 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
     for (long long i = 0; i < my_halves; ++i) {
       ptx::mbar_wait(bar_full + 8 * s, ph);
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t xb = sb + s * WG2_STAGE, yb = xb + ybase;
+      if (p.dbg & 1) {
+        if (ptx::elect_one()) { ptx::mbar_arrive(bar_empty + 8 * s); if (i == my_halves - 1) ptx::mbar_arrive(bar_done); }
+      } else if (ptx::elect_one()) {
+        const uint32_t xb = sb + s * stride, yb = xb + ybase;
         for (int mh = 0; mh < mhalves; ++mh)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -476,7 +493,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
         if (i == my_halves - 1) ptx::mma_commit(bar_done);
       }
       __syncwarp();
-      if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
+      if (++s == nstg) { s = 0; ph ^= 1; }
     }
   } else {
     // warps 0-3: while the tiles stream through shared memory -- bias gradient = column sums of the A half tiles; job
@@ -497,19 +514,19 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
       return (lr_ < plan_cta_rows(p.N, p.S, p.rays_per_cta, cta_)) ? p.d_raw[((long long)cta_ * p.rays_per_cta * p.S + lr_) * 4 + 3] : 0.f;
     };
     auto next_valid = [&](long long t_) -> long long {
-      for (t_ += G; t_ < p.n_tiles; t_ += G) if (plan_tile_valid(p, t_)) return t_;
+      for (t_ += G; t_ < p.t1; t_ += G) if (plan_tile_valid(p, t_)) return t_;
       return -1;
     };
     int dslot = 0;
     if (job.aux == 2) {
-      long long t0 = g - G;
+      long long t0 = p.t0 + g - G;
       t0 = next_valid(t0);
       const float v = (t0 >= 0) ? load_dsig(t0) : 0.f;
       s_dsig[tid] = v;
       bsum += v;
       ptx::named_bar_sync(1, 128);
     }
-    for (long long t = g; t < p.n_tiles; t += G) {
+    for (long long t = p.t0 + g; t < p.t1; t += G) {
       if (!plan_tile_valid(p, t)) continue;
       const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
       const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
@@ -521,30 +538,48 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
         ptx::mbar_wait(bar_full + 8 * s, ph);
         // one row of this thread's column pair in a half-tile image that starts at shared-memory address `b_`
 #define NB_LDPAIR(b_, r_, w_) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w_) : "r"((b_) + (uint32_t)(((r_) >> 3) * 1024 + ((r_) & 7) * 128) + ((cc ^ (uint32_t)((r_) & 7)) << 4)))
+        // The stage is held only while its rows are copied into registers (64 LDS back to back); the arithmetic runs after the
+        // release, while the producer already refills the stage (holding it through the sums cost 15 % of the kernel: measured)
+        bool released = false;
+        auto release = [&]() {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
+          released = true;
+        };
         if (do_sum || job.aux == 2) {
-          const uint32_t abase = sb + s * WG2_STAGE + coff, bbase = abase + ybase;
+          const uint32_t abase = sb + s * stride + coff, bbase = abase + ybase;
           float h0 = 0.f, h1 = 0.f;                     // column sums of this half tile of A
+          uint32_t wa[64];
+#pragma unroll
+          for (int r = 0; r < 64; ++r) NB_LDPAIR(abase, r, wa[r]);
           if (job.aux == 2) {
-            // A = d_feat (bias gradient) and B = h_{D-1} (x d_sigma -> alpha_linear.weight) in one sweep
+            // A = d_feat (bias gradient) and B = h_{D-1} (x d_sigma -> alpha_linear.weight)
+            uint32_t wb[64];
+#pragma unroll
+            for (int r = 0; r < 64; ++r) NB_LDPAIR(bbase, r, wb[r]);
+            release();
             const float* ds = s_dsig + dslot * 128 + h * 64;
-#pragma unroll 8
-            for (int r = 0; r < 64; ++r) {
-              uint32_t wa, wb;
-              NB_LDPAIR(abase, r, wa);
-              NB_LDPAIR(bbase, r, wb);
-              const __half2 ha = *reinterpret_cast<const __half2*>(&wa), hb = *reinterpret_cast<const __half2*>(&wb);
-              const float d = ds[r];
-              h0 += __low2float(ha); h1 += __high2float(ha);
-              a0 = fmaf(d, __low2float(hb), a0); a1 = fmaf(d, __high2float(hb), a1);
+            float a0b = 0.f, a1b = 0.f;
+#pragma unroll
+            for (int r = 0; r < 64; r += 2) {
+              const __half2 hb0 = *reinterpret_cast<const __half2*>(&wb[r]), hb1 = *reinterpret_cast<const __half2*>(&wb[r + 1]);
+              const float d0 = ds[r], d1 = ds[r + 1];
+              a0 = fmaf(d0, __low2float(hb0), a0); a1 = fmaf(d0, __high2float(hb0), a1);
+              a0b = fmaf(d1, __low2float(hb1), a0b); a1b = fmaf(d1, __high2float(hb1), a1b);
             }
-          } else {
-#pragma unroll 8
-            for (int r = 0; r < 64; ++r) {
-              uint32_t w;
-              NB_LDPAIR(abase, r, w);
-              const __half2 hh = *reinterpret_cast<const __half2*>(&w);
-              h0 += __low2float(hh); h1 += __high2float(hh);
+            a0 += a0b; a1 += a1b;
+          } else if (!(job.aux == 1 && p.S % 64 != 0)) {
+            release();                                  // (aux == 1 with S % 64 != 0 may have to walk the rows again: keeps the stage)
+          }
+          {
+            float e0 = 0.f, e1 = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 64; r += 2) {
+              const __half2 ha = *reinterpret_cast<const __half2*>(&wa[r]), hb = *reinterpret_cast<const __half2*>(&wa[r + 1]);
+              e0 += __low2float(ha); e1 += __high2float(ha);
+              o0 += __low2float(hb); o1 += __high2float(hb);
             }
+            h0 = e0 + o0; h1 = e1 + o1;
           }
           s0 += h0; s1 += h1;
           if (job.aux == 1 && do_sum) {
@@ -575,9 +610,8 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
           }
         }
 #undef NB_LDPAIR
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
-        if (++s == WG2_NSTAGE) { s = 0; ph ^= 1; }
+        if (!released) release();
+        if (++s == nstg) { s = 0; ph ^= 1; }
       }
       if (job.aux == 2) {                               // the prefetched d_sigma of the next tile -> the other slot
         s_dsig[(dslot ^ 1) * 128 + tid] = v_next;
@@ -617,6 +651,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad_tc_kernel(const WgradPar
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+  if (p.prof && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[2 * blockIdx.x + 1] = t_; }
 }
 
 // dst[o][i] += inv_scale * sum_g partial[g][o][i]   (i < n_valid; dst row stride ldw)

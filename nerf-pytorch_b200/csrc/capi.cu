@@ -55,7 +55,7 @@ static int smem_optin(const void* fn, size_t bytes) {
 
 // per-device facts (SM count; which kernels already have their > 48 KB shared-memory opt-in): the library may be used
 // on several devices of one process, and cudaFuncSetAttribute is per device
-struct DeviceState { int sms; bool optin_fwd, optin_bwd; };
+struct DeviceState { int sms; bool optin_fwd, optin_bwd; cudaStream_t side; cudaEvent_t ev[10]; };
 static DeviceState* device_state() {
   static DeviceState st[64];
   static bool init[64] = {false};
@@ -67,6 +67,7 @@ static DeviceState* device_state() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     st[dev].sms = n > 0 ? n : 148;
     st[dev].optin_fwd = st[dev].optin_bwd = false;
+    st[dev].side = nullptr;
     init[dev] = true;
   }
   return &st[dev];
@@ -101,7 +102,8 @@ static int make_row_map(CUtensorMap* map, const void* base, size_t bytes, int bo
 static int launch_march(const float* rays, int ray_stride, const float* z_vals, const float* pts,
                         const float* dirs, int dir_stride, const float* noise, long long N, int S,
                         const NerfNetParams* net, const void* packed, int L, int Lv, int white_bkgd, int do_composite,
-                        const NerfPassOut* out, void* workspace, size_t workspace_bytes, const NerfTrainSave* save, cudaStream_t st) {
+                        const NerfPassOut* out, void* workspace, size_t workspace_bytes, const NerfTrainSave* save, const float* vb_pre,
+                        cudaStream_t st) {
   if (int rc = check_tc_net(net)) return rc;
   NB_CHECK_ARG(packed != nullptr, "packed weights are NULL (call nerf_b200_pack_weights)");
   NB_CHECK_ARG(N > 0 && S > 0, "empty ray batch must be handled by the caller (N=%lld S=%d)", N, S);
@@ -119,7 +121,9 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
   p.D = net->D; p.skip = net->skip; p.use_viewdirs = net->use_viewdirs; p.L = L; p.IC = net->input_ch;
   p.white_bkgd = white_bkgd; p.do_composite = do_composite;
   if (out) p.out = *out;
-  if (net->use_viewdirs) {
+  if (net->use_viewdirs && vb_pre != nullptr) {
+    p.vb = vb_pre;                                     // the per-ray view-bias table was prepared by ray_setup_kernel
+  } else if (net->use_viewdirs) {
     NB_CHECK_ARG(dirs != nullptr, "viewdirs required by a use_viewdirs network");
     NB_CHECK_ARG(workspace != nullptr && workspace_bytes >= (size_t)N * 128 * 4, "workspace too small: need %zu bytes", (size_t)N * 128 * 4);
     NB_CHECK_ARG(3 + 6 * Lv == net->input_ch_views || (Lv == 0 && net->input_ch_views == 3), "multires_views mismatch");
@@ -322,7 +326,7 @@ int nerf_b200_run_network(const float* pts, const float* viewdirs, int64_t N, in
   memset(&out, 0, sizeof(out));
   out.raw = raw;
   return launch_march(nullptr, 0, nullptr, pts, viewdirs, 3, nullptr, N, S, net, packed, multires, multires_views, 0, 0,
-                      &out, workspace, workspace_bytes, nullptr, st);
+                      &out, workspace, workspace_bytes, nullptr, nullptr, st);
 }
 
 int nerf_b200_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int d_stride, const float* noise,
@@ -430,13 +434,13 @@ int nerf_b200_fine_z(const float* z_vals, const float* weights, const float* u, 
 }
 
 size_t nerf_b200_march_workspace_bytes(int64_t N, int S) {
-  size_t tc = (size_t)N * 128 * 4, exact = (size_t)N * S * 28;   // view-bias table | pts + raw scratch
+  size_t tc = (size_t)N * 128 * 4 * 2, exact = (size_t)N * S * 28;   // view-bias tables of both nets | pts + raw scratch
   return (tc > exact ? tc : exact) + 256;
 }
 
 static int march_impl(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
                       const void* packed, const NerfRenderCfg* cfg, const NerfPassOut* out, void* workspace,
-                      size_t workspace_bytes, const NerfTrainSave* save, void* stream) {
+                      size_t workspace_bytes, const NerfTrainSave* save, void* stream, const float* vb_pre = nullptr) {
   NB_CHECK_ARG(rays && z_vals && net && cfg && out, "NULL pointer");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -461,7 +465,7 @@ static int march_impl(const float* rays, const float* z_vals, const float* noise
     return 0;
   }
   return launch_march(rays, cfg->ray_stride, z_vals, nullptr, rays + 8, cfg->ray_stride, noise, N, S, net, packed,
-                      cfg->multires, cfg->multires_views, cfg->white_bkgd, 1, out, workspace, workspace_bytes, save, st);
+                      cfg->multires, cfg->multires_views, cfg->white_bkgd, 1, out, workspace, workspace_bytes, save, vb_pre, st);
 }
 
 int nerf_b200_march(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
@@ -497,10 +501,41 @@ static int render_rays_fwd_impl(const float* rays, int64_t N, const NerfRenderCf
   const int Sc = cfg->N_samples, Ni = cfg->N_importance;
   NB_CHECK_ARG(Sc >= 1 && Ni >= 0, "bad sample counts");
   NB_CHECK_ARG(!cfg->perturb || t_rand, "perturb > 0 needs t_rand");
-  // z sampling (run_nerf.py:357-379)
-  if (int rc = nerf_b200_coarse_z(rays, cfg->ray_stride, t_vals, cfg->perturb ? t_rand : nullptr, N, Sc, cfg->lindisp, z_coarse, stream)) return rc;
+  // per-ray prologue: z sampling (run_nerf.py:357-379) and, on the tensor-core path, the view-bias tables of both networks
+  // -- one launch (ray_setup_kernel); the exact path keeps the stand-alone z kernel
+  const NerfNetParams* nf = net_fine ? net_fine : net_coarse;
+  const void* pf = net_fine ? packed_fine : packed_coarse;
+  const float* vb_c = nullptr;
+  const float* vb_f = nullptr;
+  if (cfg->precision == NERF_B200_PREC_TC_FP16 && net_coarse->use_viewdirs && packed_coarse && (Ni == 0 || (nf->use_viewdirs && pf))) {
+    if (int rc = check_tc_net(net_coarse)) return rc;
+    NB_CHECK_ARG(workspace != nullptr && workspace_bytes >= (size_t)N * 128 * 4 * 2, "workspace too small: need %zu bytes", (size_t)N * 128 * 4 * 2);
+    NB_CHECK_ARG(cfg->ray_stride >= 11, "ray_stride %d too small for view directions", cfg->ray_stride);
+    NB_CHECK_ARG(3 + 6 * cfg->multires_views == net_coarse->input_ch_views || (cfg->multires_views == 0 && net_coarse->input_ch_views == 3), "multires_views mismatch");
+    const PackLayout PLc = make_pack_layout(*net_coarse);
+    RaySetupArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rays = rays; a.ray_stride = cfg->ray_stride; a.N = N; a.Lv = cfg->multires_views; a.ICV = net_coarse->input_ch_views;
+    float* vb = static_cast<float*>(workspace);
+    a.vdir_a = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed_coarse) + PLc.off_vdir); a.vb_a = vb;
+    vb_c = vb;
+    if (Ni > 0) {
+      if (nf == net_coarse || pf == packed_coarse) vb_f = vb_c;
+      else {
+        NB_CHECK_ARG(nf->input_ch_views == net_coarse->input_ch_views, "coarse and fine networks must encode view directions alike");
+        const PackLayout PLf = make_pack_layout(*nf);
+        a.vdir_b = reinterpret_cast<const float*>(static_cast<const uint8_t*>(pf) + PLf.off_vdir); a.vb_b = vb + (size_t)N * 128;
+        vb_f = a.vb_b;
+      }
+    }
+    a.t_vals = t_vals; a.t_rand = cfg->perturb ? t_rand : nullptr; a.S = Sc; a.lindisp = cfg->lindisp; a.z_out = z_coarse;
+    ray_setup_kernel<<<cdiv(N, VB_RAYS), 256, 0, (cudaStream_t)stream>>>(a);
+    NB_LAUNCH_OK("ray_setup_kernel");
+  } else {
+    if (int rc = nerf_b200_coarse_z(rays, cfg->ray_stride, t_vals, cfg->perturb ? t_rand : nullptr, N, Sc, cfg->lindisp, z_coarse, stream)) return rc;
+  }
   // coarse pass (:381-386)
-  if (int rc = march_impl(rays, z_coarse, noise0, N, Sc, net_coarse, packed_coarse, cfg, coarse, workspace, workspace_bytes, save_coarse, stream)) return rc;
+  if (int rc = march_impl(rays, z_coarse, noise0, N, Sc, net_coarse, packed_coarse, cfg, coarse, workspace, workspace_bytes, save_coarse, stream, vb_c)) return rc;
   if (Ni == 0) return 0;
   NB_CHECK_ARG(coarse->weights && z_fine && fine, "N_importance > 0 needs coarse->weights, z_fine and fine outputs");
   // hierarchical sampling (:392-396, :412); det <=> perturb == 0 (:393)
@@ -508,9 +543,7 @@ static int render_rays_fwd_impl(const float* rays, int64_t N, const NerfRenderCf
   NB_CHECK_ARG(u != nullptr, "missing u (u_det for perturb==0, u_rand otherwise)");
   if (int rc = nerf_b200_fine_z(z_coarse, coarse->weights, u, cfg->perturb ? Ni : 0, N, Sc, Ni, z_fine, nullptr, z_std, stream)) return rc;
   // fine pass on all S_c + N_importance samples (:397-403); network_fine None -> coarse net (:399)
-  const NerfNetParams* nf = net_fine ? net_fine : net_coarse;
-  const void* pf = net_fine ? packed_fine : packed_coarse;
-  return march_impl(rays, z_fine, noise1, N, Sc + Ni, nf, pf, cfg, fine, workspace, workspace_bytes, save_fine, stream);
+  return march_impl(rays, z_fine, noise1, N, Sc + Ni, nf, pf, cfg, fine, workspace, workspace_bytes, save_fine, stream, vb_f);
 }
 
 int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfNetParams* net_coarse,
@@ -681,17 +714,38 @@ BwdTcJobs make_bwd_jobs(const NerfNetParams& n, const NerfNetGrads* g, int sms) 
     if (sk) add(rec_grad_dA(l, D), 256, 0, 64, g ? g->pts_w[l] : nullptr, W + IC, IC, nullptr);        // the [input_pts] columns
   }
   add(rec_grad_dA(0, D), 256, 0, 64, g ? g->pts_w[0] : nullptr, IC, IC, g ? g->pts_b[0] : nullptr);
+  // CTAs per job ~ its measured cost (profiles/r02_wgrad_job_balance.txt: per-job finish times of a byte-proportional split):
+  // bytes streamed per tile (Mc + Nc columns), x 1.27 for the feature job (its spare warps also sweep B for alpha_linear),
+  // x 1.06 for the views job (per-ray atomics), x 1.16 for a 64-wide B with a bias gradient (short stages, same column sums)
+  auto cost = [&](int i) {
+    double c = (double)(J.w[i].Mc + J.w[i].Nc);
+    if (i == 0) c *= 1.06;
+    if (i == 1) c *= 1.27;
+    if (J.w[i].Nc == 64 && J.w[i].db) c *= 1.16;
+    return c;
+  };
   double tot = 0;
-  for (int i = 0; i < J.n; ++i) tot += J.w[i].Mc + J.w[i].Nc;
-  int used = 0, big = 0;
+  for (int i = 0; i < J.n; ++i) tot += cost(i);
+  int used = 0;
+  double frac[WG2_MAX_JOBS];
   for (int i = 0; i < J.n; ++i) {
-    int c = (int)((double)sms * (J.w[i].Mc + J.w[i].Nc) / tot);
+    const double x = (double)sms * cost(i) / tot;
+    int c = (int)x;
     if (c < 1) c = 1;
+    frac[i] = x - c;
     J.w[i].ncta = c;
     used += c;
-    if (J.w[i].Mc + J.w[i].Nc > J.w[big].Mc + J.w[big].Nc) big = i;
   }
-  for (int i = 0; used < sms; i = (i + 1) % J.n) if (J.w[i].Mc + J.w[i].Nc == J.w[big].Mc + J.w[big].Nc) { ++J.w[i].ncta; ++used; }
+  while (used < sms) {                               // leftovers: largest remainder first
+    int b = 0;
+    for (int i = 1; i < J.n; ++i) if (frac[i] > frac[b]) b = i;
+    ++J.w[b].ncta; ++used; frac[b] -= 1.0;
+  }
+  while (used > sms) {                               // (tiny launches: more jobs than CTAs is rejected by the caller's minimum)
+    int b = 0;
+    for (int i = 1; i < J.n; ++i) if (J.w[i].ncta > J.w[b].ncta) b = i;
+    --J.w[b].ncta; --used;
+  }
   int cta = 0;
   long long pf = 0;
   for (int i = 0; i < J.n; ++i) {
@@ -719,12 +773,15 @@ BwdTcLayout make_bwd_layout(long long N, int S, const NerfNetParams& n, const Ti
 }
 }  // namespace
 
-size_t nerf_b200_march_bwd_tc_workspace_bytes(int64_t N, int S, const NerfNetParams* net) {
-  if (!net || check_tc_net(net) || !net->use_viewdirs || N <= 0 || S <= 0) return 0;
+static size_t bwd_pass_bytes(int64_t N, int S, const NerfNetParams* net) {
   const int sms = num_sms();
   const TilePlan plan = make_tile_plan(N, S, sms);
-  const BwdTcJobs J = make_bwd_jobs(*net, nullptr, sms);
-  return make_bwd_layout(N, S, *net, plan, J.part_floats).total + 1024;
+  return make_bwd_layout(N, S, *net, plan, (long long)sms * 256 * 256).total + 1024;
+}
+
+size_t nerf_b200_march_bwd_tc_workspace_bytes(int64_t N, int S, const NerfNetParams* net) {
+  if (!net || check_tc_net(net) || !net->use_viewdirs || N <= 0 || S <= 0) return 0;
+  return bwd_pass_bytes(N, S, net);
 }
 
 // introspection for tests and tools: where nerf_b200_march_bwd_tc keeps its intermediates inside the (1 KB-aligned)
@@ -735,76 +792,84 @@ int nerf_b200_march_bwd_tc_layout(int64_t N, int S, const NerfNetParams* net, in
   NB_CHECK_ARG(out && N > 0 && S > 0 && net->use_viewdirs, "bad arguments");
   const int sms = num_sms();
   const TilePlan plan = make_tile_plan(N, S, sms);
-  const BwdTcJobs J = make_bwd_jobs(*net, nullptr, sms);
-  const BwdTcLayout LY = make_bwd_layout(N, S, *net, plan, J.part_floats);
+  const BwdTcLayout LY = make_bwd_layout(N, S, *net, plan, (long long)sms * 256 * 256);
   out[0] = (int64_t)LY.off_draw; out[1] = (int64_t)LY.off_grad; out[2] = rec_act_bytes(net->D); out[3] = rec_mask_bytes(net->D);
   out[4] = rec_grad_bytes(net->D); out[5] = plan.grid; out[6] = plan.rays_per_cta; out[7] = plan.nst; out[8] = plan.n_tiles;
   out[9] = (int64_t)LY.off_amax; out[10] = (int64_t)LY.off_dsum; out[11] = (int64_t)LY.off_partial;
   return 0;
 }
 
-int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
-                           const void* packed, const NerfRenderCfg* cfg, const float* raw, const NerfTrainSave* save,
-                           const float* g_rgb, const NerfNetGrads* grads, void* workspace, size_t workspace_bytes, void* stream) {
-  NB_CHECK_ARG(rays && z_vals && net && packed && cfg && raw && save && g_rgb && grads, "NULL pointer");
-  if (int rc = check_tc_net(net)) return rc;
-  NB_CHECK_ARG(net->use_viewdirs, "the tensor-core backward serves use_viewdirs networks (exact mode serves the others)");
-  NB_CHECK_ARG(net->W == 256, "the tensor-core backward supports netwidth == 256");
-  if (N == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  DeviceState* ds = device_state();
-  const int sms = ds->sms, D = net->D, rs = cfg->ray_stride;
-  const TilePlan plan = make_tile_plan(N, S, sms);
-  BwdTcJobs J = make_bwd_jobs(*net, grads, sms);
-  J.w[0].aux = 1;                                   // views job: per-ray row sums of d_hv (aux_dst set below)
-  J.w[1].aux = 2; J.w[1].aux_dst = grads->alpha_w; J.w[1].aux_b = grads->alpha_b;   // feature job: alpha_linear gradients
-  { static int noaux = -1; if (noaux < 0) { const char* e = getenv("NERF_B200_DBG_NOAUX"); noaux = e ? atoi(e) : 0; }
-    if (noaux & 1) J.w[0].aux = 0;
-    if (noaux & 2) J.w[1].aux = 0; }
-  const BwdTcLayout LY = make_bwd_layout(N, S, *net, plan, J.part_floats);
-  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-  NB_CHECK_ARG(workspace && workspace_bytes >= LY.total + (size_t)(ws - static_cast<uint8_t*>(workspace)), "march_bwd_tc workspace too small (%zu < %zu)", workspace_bytes, LY.total + 1024);
-  NB_CHECK_ARG(save->act && save->mask && save->act_bytes >= (size_t)plan.n_tiles * rec_act_bytes(D) && save->mask_bytes >= (size_t)plan.n_tiles * rec_mask_bytes(D),
-               "training-mode records missing or too small");
-  const PackLayout PL = make_pack_layout(*net);
-  const uint8_t* pk = static_cast<const uint8_t*>(packed);
-  unsigned int* amax = reinterpret_cast<unsigned int*>(ws + LY.off_amax);
-  float* d_raw = reinterpret_cast<float*>(ws + LY.off_draw);
-  float* encv = reinterpret_cast<float*>(ws + LY.off_encv);
-  float* dsum = reinterpret_cast<float*>(ws + LY.off_dsum);
-  float* gv = reinterpret_cast<float*>(ws + LY.off_gv);
-  float* dbv = gv + 128 * 256;
-  float* partial = reinterpret_cast<float*>(ws + LY.off_partial);
-  uint8_t* grec = ws + LY.off_grad;
-  const uint8_t* act = static_cast<const uint8_t*>(save->act);
-  const uint8_t* mask = static_cast<const uint8_t*>(save->mask);
-  if (!ds->optin_bwd) {
-    NB_TRY(smem_optin((const void*)dgrad_tc2_kernel, SM_ALLOC));
-    NB_TRY(smem_optin((const void*)wgrad_tc_kernel, WG2_TOTAL));
-    ds->optin_bwd = true;
+namespace {
+constexpr int BWD_OVERLAP_SMS = 0, BWD_OVERLAP_CHUNKS = 1;     // defaults of NERF_B200_BWD_OVERLAP: off -- measured slower than one pass after the other
+                                                               // in every split (profiles/r02_bwd_overlap_sweep.jsonl)
+// One pass of the tensor-core backward, split into its phases so that the two passes of render_rays can interleave: the data-
+// gradient chain is bound by HBM WRITES (3.9 TB/s ceiling), the weight gradient by HBM READS; side by side on disjoint SMs they
+// share a bus that carries 6.6 TB/s of mixed traffic (profiles/r02_hbm_probe.json).
+struct BwdTcPass {
+  const float* rays; const float* z; const float* noise; int64_t N; int S; const NerfNetParams* net; const void* packed;
+  const NerfRenderCfg* cfg; const float* raw; const NerfTrainSave* save; const float* g_rgb; const NerfNetGrads* grads;
+  DeviceState* ds; TilePlan plan; BwdTcLayout LY; PackLayout PL;
+  unsigned int* amax; float *d_raw, *encv, *dsum, *gv, *dbv, *partial; uint8_t* grec; const uint8_t *act, *mask;
+
+  int init(void* workspace, size_t workspace_bytes) {
+    ds = device_state();
+    plan = make_tile_plan(N, S, ds->sms);
+    LY = make_bwd_layout(N, S, *net, plan, (long long)ds->sms * 256 * 256);
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    NB_CHECK_ARG(workspace && workspace_bytes >= LY.total + (size_t)(ws - static_cast<uint8_t*>(workspace)), "march_bwd_tc workspace too small (%zu < %zu)", workspace_bytes, LY.total + 1024);
+    NB_CHECK_ARG(save->act && save->mask && save->act_bytes >= (size_t)plan.n_tiles * rec_act_bytes(net->D) && save->mask_bytes >= (size_t)plan.n_tiles * rec_mask_bytes(net->D),
+                 "training-mode records missing or too small");
+    PL = make_pack_layout(*net);
+    amax = reinterpret_cast<unsigned int*>(ws + LY.off_amax);
+    d_raw = reinterpret_cast<float*>(ws + LY.off_draw);
+    encv = reinterpret_cast<float*>(ws + LY.off_encv);
+    dsum = reinterpret_cast<float*>(ws + LY.off_dsum);
+    gv = reinterpret_cast<float*>(ws + LY.off_gv);
+    dbv = gv + 128 * 256;
+    partial = reinterpret_cast<float*>(ws + LY.off_partial);
+    grec = ws + LY.off_grad;
+    act = static_cast<const uint8_t*>(save->act);
+    mask = static_cast<const uint8_t*>(save->mask);
+    if (!ds->optin_bwd) {
+      NB_TRY(smem_optin((const void*)dgrad_tc2_kernel, SM_ALLOC));
+      NB_TRY(smem_optin((const void*)wgrad_tc_kernel, WG2_TOTAL));
+      ds->optin_bwd = true;
+    }
+    return 0;
   }
-  // 1. loss scale from max |dL/drgb_map|; compositing adjoint -> dL/draw
-  NB_CUDA(cudaMemsetAsync(amax, 0, 256, st));
-  NB_CUDA(cudaMemsetAsync(dsum, 0, (size_t)N * 128 * 4, st));
-  NB_CUDA(cudaMemsetAsync(gv, 0, (size_t)(128 * 256 + 128) * 4, st));
-  absmax_kernel<<<cdiv(N * 3, 1024) < 64 ? cdiv(N * 3, 1024) : 64, 256, 0, st>>>(g_rgb, N * 3, amax);
-  NB_LAUNCH_OK("absmax_kernel");
-  NB_TRY(nerf_b200_raw2outputs_bwd(raw, z_vals, rays + 3, rs, noise, N, S, cfg->white_bkgd, g_rgb, d_raw, stream));
-  // 2. seed of the chain: d_hv tiles
-  SeedParams sp;
-  sp.d_raw = d_raw; sp.mask = mask; sp.grad = grec; sp.rgb_w = net->rgb_w; sp.amax = amax;
-  sp.N = N; sp.S = S; sp.rays_per_cta = plan.rays_per_cta; sp.nst_plan = plan.nst; sp.D = D;
-  sp.rec_mask = rec_mask_bytes(D); sp.rec_grad = rec_grad_bytes(D); sp.n_tiles = plan.n_tiles;
-  dhv_seed_kernel<<<(int)(plan.n_tiles < 8 * sms ? plan.n_tiles : 8 * sms), 256, 0, st>>>(sp);
-  NB_LAUNCH_OK("dhv_seed_kernel");
-  // 3. dgrad chain (CTA pairs, the forward's tile order)
-  const long long rows = N * (long long)S;
-  {
+
+  // 1. loss scale from max |dL/drgb_map|; compositing adjoint -> dL/draw;  2. seed of the chain: d_hv tiles
+  int prologue(cudaStream_t st) {
+    const int sms = ds->sms, D = net->D;
+    NB_CUDA(cudaMemsetAsync(amax, 0, 256, st));
+    NB_CUDA(cudaMemsetAsync(dsum, 0, (size_t)N * 128 * 4, st));
+    NB_CUDA(cudaMemsetAsync(gv, 0, (size_t)(128 * 256 + 128) * 4, st));
+    absmax_kernel<<<cdiv(N * 3, 1024) < 64 ? cdiv(N * 3, 1024) : 64, 256, 0, st>>>(g_rgb, N * 3, amax);
+    NB_LAUNCH_OK("absmax_kernel");
+    NB_TRY(nerf_b200_raw2outputs_bwd(raw, z, rays + 3, cfg->ray_stride, noise, N, S, cfg->white_bkgd, g_rgb, d_raw, (void*)st));
+    SeedParams sp;
+    sp.d_raw = d_raw; sp.mask = mask; sp.grad = grec; sp.rgb_w = net->rgb_w; sp.amax = amax;
+    sp.N = N; sp.S = S; sp.rays_per_cta = plan.rays_per_cta; sp.nst_plan = plan.nst; sp.D = D;
+    sp.rec_mask = rec_mask_bytes(D); sp.rec_grad = rec_grad_bytes(D); sp.n_tiles = plan.n_tiles;
+    dhv_seed_kernel<<<(int)(plan.n_tiles < 8 * sms ? plan.n_tiles : 8 * sms), 256, 0, st>>>(sp);
+    NB_LAUNCH_OK("dhv_seed_kernel");
+    return 0;
+  }
+
+  // 3. dgrad chain of the forward's CTAs [vc0, vc1) on at most `ctas` CTAs (CTA pairs, the forward's tile order)
+  int dgrad(cudaStream_t st, int ctas, int vc0, int vc1) {
+    const int D = net->D;
+    const uint8_t* pk = static_cast<const uint8_t*>(packed);
     DgradParams dp;
     dp.mask = mask; dp.grad = grec; dp.d_raw = d_raw; dp.amax = amax; dp.alpha_w = net->alpha_w;
     dp.N = N; dp.S = S; dp.rays_per_cta = plan.rays_per_cta; dp.nst_plan = plan.nst; dp.D = D;
     dp.rec_mask = rec_mask_bytes(D); dp.rec_grad = rec_grad_bytes(D);
     dp.pair_half_bytes = PL.bwd_bytes / 2;
+    dp.vc0 = vc0; dp.vc1 = vc1;
+    int grid = vc1 - vc0;
+    if (grid > ctas) grid = ctas;
+    grid &= ~1;
+    if (grid < 2) grid = 2;
     CUtensorMap wmap, gmap;
     NB_TRY(make_row_map(&wmap, pk + PL.off_bwd_pair, PL.bwd_bytes, 16));
     NB_TRY(make_row_map(&gmap, grec, (size_t)plan.n_tiles * rec_grad_bytes(D), 64));
@@ -812,34 +877,65 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     if (g_timing && g_ntimed < 4096) {
       tl = &g_timed[g_ntimed++];
       cudaEventCreate(&tl->a); cudaEventCreate(&tl->b);
-      tl->flops = 2.0 * ((double)(net->W / 2) * net->W + (double)D * net->W * net->W) * (double)rows;
+      tl->flops = 2.0 * ((double)(net->W / 2) * net->W + (double)D * net->W * net->W) * (double)(N * (long long)S) * (double)(vc1 - vc0) / (double)plan.grid;
       tl->kind = 1;
       cudaEventRecord(tl->a, st);
     }
-    dgrad_tc2_kernel<<<plan.grid, TC_THREADS, SM_ALLOC, st>>>(dp, wmap, gmap);
+    dgrad_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(dp, wmap, gmap);
     if (tl) cudaEventRecord(tl->b, st);
     NB_LAUNCH_OK("dgrad_tc2_kernel");
+    return 0;
   }
-  // 4. weight gradients (layer-major) + bias gradients, then the reduction of the per-CTA partial blocks
-  {
+
+  // 4. weight gradients (layer-major) + bias gradients of the forward's CTAs [vc0, vc1) on `ctas` CTAs, then the reduction of
+  // the per-CTA partial blocks (adds into the gradient tensors, so a pass may be covered by several launches)
+  int wgrad(cudaStream_t st, int ctas, int vc0, int vc1) {
+    const int D = net->D;
+    BwdTcJobs J = make_bwd_jobs(*net, grads, ctas & ~1);           // whole CTA pairs: the kernel launches as 2-CTA clusters
+    J.w[0].aux = 1; J.w[0].aux_dst = dsum;            // views job: per-ray row sums of d_hv
+    J.w[1].aux = 2; J.w[1].aux_dst = grads->alpha_w; J.w[1].aux_b = grads->alpha_b;   // feature job: alpha_linear gradients
+    { static int noaux = -1; if (noaux < 0) { const char* e = getenv("NERF_B200_DBG_NOAUX"); noaux = e ? atoi(e) : 0; }
+      if (noaux & 1) J.w[0].aux = 0;
+      if (noaux & 2) J.w[1].aux = 0;
+      if (noaux & 4) for (int i = 0; i < J.n; ++i) J.w[i].db = nullptr; }
     WgradParams wp;
     memset(&wp, 0, sizeof(wp));
     wp.act = act; wp.grad = grec; wp.rec_act = rec_act_bytes(D); wp.rec_grad = rec_grad_bytes(D);
     wp.N = N; wp.S = S; wp.rays_per_cta = plan.rays_per_cta; wp.nst_plan = plan.nst; wp.n_tiles = plan.n_tiles;
+    wp.t0 = (long long)vc0 * plan.nst * 2; wp.t1 = (long long)vc1 * plan.nst * 2;
     wp.amax = amax; wp.partial = partial; wp.d_raw = d_raw; wp.njobs = J.n;
-    J.w[0].aux_dst = dsum;
+    { static int wd = -1; if (wd < 0) { const char* e = getenv("NERF_B200_DBG_WGRAD"); wd = e ? atoi(e) : 0; } wp.dbg = wd; }
     for (int i = 0; i < J.n; ++i) wp.jobs[i] = J.w[i];
     TimedLaunch* tl = nullptr;
     if (g_timing && g_ntimed < 4096) {
       tl = &g_timed[g_ntimed++];
       cudaEventCreate(&tl->a); cudaEventCreate(&tl->b);
-      tl->flops = 2.0 * (net_macs_per_row(*net) - (double)net->W - 3.0 * (net->W / 2) - (double)net->input_ch_views * (net->W / 2)) * (double)rows;
+      tl->flops = 2.0 * (net_macs_per_row(*net) - (double)net->W - 3.0 * (net->W / 2) - (double)net->input_ch_views * (net->W / 2)) * (double)(N * (long long)S) * (double)(vc1 - vc0) / (double)plan.grid;
       tl->kind = 2;
       cudaEventRecord(tl->a, st);
     }
+    static const char* prof_path = getenv("NERF_B200_DBG_WGRAD_PROF");     // experiments: per-CTA start / end times appended to a file
+    static unsigned long long* prof_dev = nullptr;
+    if (prof_path) { if (!prof_dev) NB_CUDA(cudaMalloc(&prof_dev, 1024 * 16)); wp.prof = prof_dev; }
     wgrad_tc_kernel<<<J.total_ctas, WG2_THREADS, WG2_TOTAL, st>>>(wp);
     if (tl) cudaEventRecord(tl->b, st);
     NB_LAUNCH_OK("wgrad_tc_kernel");
+    if (prof_path) {
+      unsigned long long h[2048];
+      NB_CUDA(cudaStreamSynchronize(st));
+      NB_CUDA(cudaMemcpy(h, prof_dev, (size_t)J.total_ctas * 16, cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(prof_path, "a")) {
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < J.total_ctas; ++i) if (h[2 * i] < t0) t0 = h[2 * i];
+        fprintf(f, "launch S=%d ctas=%d\n", S, J.total_ctas);
+        for (int j = 0; j < J.n; ++j) {
+          unsigned long long lo = ~0ull, hi = 0;
+          for (int i = J.w[j].cta0; i < J.w[j].cta0 + J.w[j].ncta; ++i) { if (h[2 * i + 1] - t0 < lo) lo = h[2 * i + 1] - t0; if (h[2 * i + 1] - t0 > hi) hi = h[2 * i + 1] - t0; }
+          fprintf(f, "  job %2d Mc=%3d Nc=%3d aux=%d db=%d ctas=%2d end_us min %.1f max %.1f\n", j, J.w[j].Mc, J.w[j].Nc, J.w[j].aux, J.w[j].db != nullptr, J.w[j].ncta, lo * 1e-3, hi * 1e-3);
+        }
+        fclose(f);
+      }
+    }
     ReduceParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.partial = partial; rp.amax = amax; rp.njobs = J.n;
@@ -848,11 +944,13 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     dim3 rg(256, J.n);
     wgrad_reduce_kernel<<<rg, 256, 0, st>>>(rp);
     NB_LAUNCH_OK("wgrad_reduce_kernel");
+    return 0;
   }
-  // 5. the small heads: rgb_linear, alpha_linear, the view columns of views_linears[0]
-  {
-    const int ICV = net->input_ch_views;
-    encv_kernel<<<cdiv(N * ICV, 256), 256, 0, st>>>(rays + 8, rs, N, ICV, encv);
+
+  // 5. the small heads: rgb_linear, the view columns of views_linears[0] (after ALL of the pass's weight-gradient launches)
+  int heads(cudaStream_t st) {
+    const int sms = ds->sms, D = net->D, ICV = net->input_ch_views;
+    encv_kernel<<<cdiv(N * ICV, 256), 256, 0, st>>>(rays + 8, cfg->ray_stride, N, ICV, encv);
     NB_LAUNCH_OK("encv_kernel");
     HeadGradParams hp;
     hp.act = act; hp.d_raw = d_raw;
@@ -866,7 +964,128 @@ int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* 
     NB_LAUNCH_OK("views_enc_wgrad_kernel");
     views_feat_wgrad_kernel<<<128, 256, 0, st>>>(gv, dbv, net->feature_w, net->feature_b, grads->views_w, net->W + ICV);
     NB_LAUNCH_OK("views_feat_wgrad_kernel");
+    return 0;
   }
+};
+
+int check_bwd_pass(const float* rays, const NerfBwdPass* q, const NerfRenderCfg* cfg) {
+  NB_CHECK_ARG(rays && q && q->z_vals && q->net && q->packed && cfg && q->raw && q->save && q->g_rgb && q->grads, "NULL pointer");
+  if (int rc = check_tc_net(q->net)) return rc;
+  NB_CHECK_ARG(q->net->use_viewdirs, "the tensor-core backward serves use_viewdirs networks (exact mode serves the others)");
+  NB_CHECK_ARG(q->net->W == 256, "the tensor-core backward supports netwidth == 256");
+  NB_CHECK_ARG(q->S > 0, "S must be positive");
+  return 0;
+}
+BwdTcPass bind_pass(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfBwdPass* q) {
+  BwdTcPass b;
+  memset(&b, 0, sizeof(b));
+  b.rays = rays; b.z = q->z_vals; b.noise = q->noise; b.N = N; b.S = q->S; b.net = q->net; b.packed = q->packed; b.cfg = cfg;
+  b.raw = q->raw; b.save = q->save; b.g_rgb = q->g_rgb; b.grads = q->grads;
+  return b;
+}
+}  // namespace
+
+int nerf_b200_march_bwd_tc(const float* rays, const float* z_vals, const float* noise, int64_t N, int S, const NerfNetParams* net,
+                           const void* packed, const NerfRenderCfg* cfg, const float* raw, const NerfTrainSave* save,
+                           const float* g_rgb, const NerfNetGrads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  NerfBwdPass q;
+  q.z_vals = z_vals; q.noise = noise; q.S = S; q.net = net; q.packed = packed; q.raw = raw; q.save = save; q.g_rgb = g_rgb; q.grads = grads;
+  if (int rc = check_bwd_pass(rays, &q, cfg)) return rc;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdTcPass b = bind_pass(rays, N, cfg, &q);
+  NB_TRY(b.init(workspace, workspace_bytes));
+  NB_TRY(b.prologue(st));
+  NB_TRY(b.dgrad(st, b.plan.grid, 0, b.plan.grid));
+  NB_TRY(b.wgrad(st, b.ds->sms, 0, b.plan.grid));
+  NB_TRY(b.heads(st));
+  return 0;
+}
+
+size_t nerf_b200_render_rays_bwd_tc_workspace_bytes(int64_t N, int S_coarse, const NerfNetParams* net_coarse, int S_fine, const NerfNetParams* net_fine) {
+  if (!net_coarse || check_tc_net(net_coarse) || !net_coarse->use_viewdirs || N <= 0 || S_coarse <= 0) return 0;
+  size_t b = bwd_pass_bytes(N, S_coarse, net_coarse);
+  if (net_fine && S_fine > 0) {
+    if (check_tc_net(net_fine) || !net_fine->use_viewdirs) return 0;
+    b += bwd_pass_bytes(N, S_fine, net_fine);
+  }
+  return b;
+}
+
+// Backward of both passes of render_rays (run_nerf.py:765-772: loss = img2mse(rgb) + img2mse(rgb0); z_samples is detached, :394,
+// so the passes are independent).  Schedule on two streams (graph-capturable: the side stream forks from and joins `stream`):
+//   main: prologue(c) prologue(f) dgrad(c) | dgrad(f, chunk 1) | dgrad(f, chunk 2) ... |         wgrad(f, last chunk) heads(f)
+//   side:                                  | wgrad(c) heads(c) | wgrad(f, chunk 1)     ... | join
+// between the bars the chain (HBM writes) runs on `sms - w` SMs next to a weight gradient (HBM reads) on `w` SMs.
+// NERF_B200_BWD_OVERLAP = "w[,chunks]" overrides the split (0 = one pass after the other on one stream).
+int nerf_b200_render_rays_bwd_tc(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfBwdPass* coarse, const NerfBwdPass* fine,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_bwd_pass(rays, coarse, cfg)) return rc;
+  if (fine) if (int rc = check_bwd_pass(rays, fine, cfg)) return rc;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdTcPass c = bind_pass(rays, N, cfg, coarse);
+  const size_t cb = bwd_pass_bytes(N, coarse->S, coarse->net);
+  NB_CHECK_ARG(workspace && workspace_bytes >= cb, "render_rays_bwd_tc workspace too small");
+  NB_TRY(c.init(workspace, cb));
+  DeviceState* ds = c.ds;
+  const int sms = ds->sms;
+  static int env_w = -2, env_chunks = 0;
+  if (env_w == -2) {
+    const char* e = getenv("NERF_B200_BWD_OVERLAP");
+    env_w = -1;
+    if (e) { int a = -1, k = 0; const int n = sscanf(e, "%d,%d", &a, &k); if (n >= 1) env_w = a; if (n >= 2) env_chunks = k; }
+  }
+  if (!fine) {
+    NB_TRY(c.prologue(st)); NB_TRY(c.dgrad(st, c.plan.grid, 0, c.plan.grid)); NB_TRY(c.wgrad(st, sms, 0, c.plan.grid)); NB_TRY(c.heads(st));
+    return 0;
+  }
+  BwdTcPass f = bind_pass(rays, N, cfg, fine);
+  NB_TRY(f.init(static_cast<uint8_t*>(workspace) + cb, workspace_bytes - cb));
+  int w = (env_w >= 0) ? env_w : BWD_OVERLAP_SMS;
+  int chunks = (env_chunks > 0) ? env_chunks : BWD_OVERLAP_CHUNKS;
+  const bool shared_grads = (coarse->grads->pts_w[0] == fine->grads->pts_w[0]);       // one network serving both passes: += races
+  if (w > sms - 16) w = sms - 16;
+  w &= ~1;
+  if (w < 16 || shared_grads || f.plan.grid < 4) {
+    static int dc = -1, wc = -1;                       // NERF_B200_DBG_BWD_CTAS="d,w": CTA caps of the two kernels (scaling experiments)
+    if (dc < 0) { dc = 1 << 20; wc = sms; const char* e = getenv("NERF_B200_DBG_BWD_CTAS"); if (e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 2 && b >= 16 && b <= sms) { dc = a; wc = b; } } }
+    NB_TRY(c.prologue(st)); NB_TRY(c.dgrad(st, dc, 0, c.plan.grid)); NB_TRY(c.wgrad(st, wc, 0, c.plan.grid)); NB_TRY(c.heads(st));
+    NB_TRY(f.prologue(st)); NB_TRY(f.dgrad(st, dc, 0, f.plan.grid)); NB_TRY(f.wgrad(st, wc, 0, f.plan.grid)); NB_TRY(f.heads(st));
+    return 0;
+  }
+  if (!ds->side) {
+    NB_CUDA(cudaStreamCreateWithFlags(&ds->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 10; ++i) NB_CUDA(cudaEventCreateWithFlags(&ds->ev[i], cudaEventDisableTiming));
+  }
+  cudaStream_t sd = ds->side;
+  if (chunks > 8) chunks = 8;
+  if (chunks > f.plan.grid / 2) chunks = f.plan.grid / 2;
+  if (chunks < 1) chunks = 1;
+  NB_TRY(c.prologue(st));
+  NB_TRY(f.prologue(st));
+  NB_TRY(c.dgrad(st, c.plan.grid, 0, c.plan.grid));
+  NB_CUDA(cudaEventRecord(ds->ev[0], st));
+  NB_CUDA(cudaStreamWaitEvent(sd, ds->ev[0], 0));
+  NB_TRY(c.wgrad(sd, w, 0, c.plan.grid));
+  NB_TRY(c.heads(sd));
+  // fine pass: `chunks` ranges of the forward's CTA pairs; chunk k's weight gradient runs on the side stream next to chunk
+  // k + 1's chain, the last chunk's on the main stream with all SMs
+  const int pairs = f.plan.grid / 2;
+  int v0 = 0, v1 = 0;
+  for (int k = 0; k < chunks; ++k) {
+    v0 = 2 * (int)((long long)pairs * k / chunks); v1 = 2 * (int)((long long)pairs * (k + 1) / chunks);
+    NB_TRY(f.dgrad(st, sms - w, v0, v1));
+    if (k + 1 < chunks) {
+      NB_CUDA(cudaEventRecord(ds->ev[k + 1], st));
+      NB_CUDA(cudaStreamWaitEvent(sd, ds->ev[k + 1], 0));
+      NB_TRY(f.wgrad(sd, w, v0, v1));
+    }
+  }
+  NB_CUDA(cudaEventRecord(ds->ev[9], sd));
+  NB_CUDA(cudaStreamWaitEvent(st, ds->ev[9], 0));
+  NB_TRY(f.wgrad(st, sms, v0, v1));
+  NB_TRY(f.heads(st));
   return 0;
 }
 

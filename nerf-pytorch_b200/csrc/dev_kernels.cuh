@@ -457,4 +457,132 @@ __global__ void __launch_bounds__(384, 1) ldtm_rate_kernel(int reps, int shape, 
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
+
+// ---- HBM stream probes: what a pure read / pure write / mixed stream reaches on this GPU (context for the training kernels,
+// which are bound by record writes (forward, dgrad) or record reads (wgrad)) -----------------------------------------------
+// mode 0: read n 16-byte words (xor-reduced, result kept alive); 1: write; 2: read `src`, write `dst` (copy)
+__global__ void __launch_bounds__(512) hbm_stream_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n, int mode, uint4* sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  if (mode == 0) {
+    for (; i + 7 * stride < n; i += 8 * stride) {
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcs(src + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc.x ^= v[k].x; acc.y ^= v[k].y; acc.z ^= v[k].z; acc.w ^= v[k].w; }
+    }
+    for (; i < n; i += stride) { const uint4 v = __ldcs(src + i); acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w; }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = acc;
+  } else if (mode == 1) {
+    const uint4 v = make_uint4((uint32_t)i, 1u, 2u, 3u);
+    for (; i < n; i += stride) __stcs(dst + i, v);
+  } else {
+    for (; i + 3 * stride < n; i += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldcs(src + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) __stcs(dst + i + k * stride, v[k]);
+    }
+    for (; i < n; i += stride) __stcs(dst + i, __ldcs(src + i));
+  }
+}
+
+
+// ---- per-SM DRAM streaming probe: what ONE CTA per SM moves between HBM and shared memory / registers with each mechanism ----
+// Every CTA streams its own disjoint `bytes_per_cta` region (no L2 reuse when the buffer is much larger than L2).
+//   mode 0: cp.async.bulk global->shared through a ring of `stages` x `chunk` bytes (one producer lane, one consumer warp)
+//   mode 1: cp.async 16-byte copies (LDGSTS) by 128 producer threads into the same ring, completion through
+//           cp.async.mbarrier.arrive.noinc
+//   mode 2: cp.async.bulk shared->global of `chunk` bytes, at most `stages` bulk groups pending (wait_group.read)
+//   mode 3: st.global.v4 by 512 threads          mode 4: ld.global.v4 by 512 threads (8 loads in flight per thread)
+// out[blockIdx.x] = clock cycles of the CTA's stream.
+constexpr int DSP_THREADS = 512;
+__global__ void __launch_bounds__(DSP_THREADS, 1) dram_stream_probe_kernel(uint8_t* __restrict__ buf, unsigned long long bytes_per_cta, int chunk, int stages,
+                                                                           int mode, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const uint32_t BAR = (uint32_t)stages * (uint32_t)chunk;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* base = buf + (size_t)blockIdx.x * bytes_per_cta;
+  const int n = (int)(bytes_per_cta / (unsigned)chunk);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { ptx::mbar_init(sb + BAR + 8 * i, mode == 1 ? 128 : 1); ptx::mbar_init(sb + BAR + 128 + 8 * i, 1); }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  if (mode == 0 || mode == 1) {
+    if (mode == 0 && warp == 0) {
+      uint32_t stage = 0, ph = 0;
+      for (int i = 0; i < n; ++i) {
+        ptx::mbar_wait(sb + BAR + 128 + 8 * stage, ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(sb + BAR + 8 * stage, chunk);
+          for (int o = 0; o < chunk; o += 8192) ptx::bulk_g2s(sb + stage * chunk + o, base + (size_t)i * chunk + o, (chunk - o) < 8192 ? (chunk - o) : 8192, sb + BAR + 8 * stage);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+      }
+    } else if (mode == 1 && warp < 4) {
+      uint32_t stage = 0, ph = 0;
+      for (int i = 0; i < n; ++i) {
+        ptx::mbar_wait(sb + BAR + 128 + 8 * stage, ph ^ 1);
+        const uint8_t* src = base + (size_t)i * chunk;
+        for (int o = threadIdx.x * 16; o < chunk; o += 128 * 16)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sb + stage * chunk + o), "l"(src + o) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(sb + BAR + 8 * stage) : "memory");
+        if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+      }
+    } else if (warp == 4) {
+      uint32_t stage = 0, ph = 0;
+      for (int i = 0; i < n; ++i) {
+        ptx::mbar_wait(sb + BAR + 8 * stage, ph);
+        if (ptx::elect_one()) ptx::mbar_arrive(sb + BAR + 128 + 8 * stage);
+        __syncwarp();
+        if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else if (mode == 2) {
+    if (threadIdx.x == 0) {
+      ptx::fence_proxy_async_smem();
+      for (int i = 0; i < n; ++i) {
+        for (int o = 0; o < chunk; o += 16384) ptx::bulk_s2g(base + (size_t)i * chunk + o, sb + (uint32_t)(i % stages) * chunk + o, (chunk - o) < 16384 ? (chunk - o) : 16384);
+        ptx::bulk_commit();
+        switch (stages) {
+          case 1: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+          case 2: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+          case 3: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+          case 4: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+          default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
+        }
+      }
+      ptx::bulk_wait_all();
+    }
+  } else if (mode == 3) {
+    uint4* d = reinterpret_cast<uint4*>(base);
+    const size_t nw = bytes_per_cta / 16;
+    const uint4 v = make_uint4(threadIdx.x, 1u, 2u, 3u);
+    for (size_t i = threadIdx.x; i < nw; i += DSP_THREADS) __stcs(d + i, v);
+  } else {
+    const uint4* d = reinterpret_cast<const uint4*>(base);
+    const size_t nw = bytes_per_cta / 16;
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    size_t i = threadIdx.x;
+    for (; i + 7 * DSP_THREADS < nw; i += 8 * DSP_THREADS) {
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcs(d + i + k * DSP_THREADS);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc.x ^= v[k].x; acc.y ^= v[k].y; acc.z ^= v[k].z; acc.w ^= v[k].w; }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) out[gridDim.x] = acc.x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+}
+
 }  // namespace nb

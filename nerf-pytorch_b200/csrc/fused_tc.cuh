@@ -209,6 +209,76 @@ __global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict_
   }
 }
 
+// One launch per ray chunk for everything the two fused passes need per RAY (render_rays' prologue, run_nerf.py:351-379 and
+// the per-ray part of run_network, :44-46): the coarse z row (as coarse_z_kernel) and the view-bias rows of BOTH networks
+// (as view_bias_kernel) -- three launches of round 1 folded into one, and the fine net's table is off the critical path
+// between the resampling and the fine pass.  256 threads: threads 0-127 serve net A's 128 view units, 128-255 net B's.
+struct RaySetupArgs {
+  const float* rays; int ray_stride; long long N; int Lv, ICV;
+  const float* vdir_a; float* vb_a;               // net A side table (128 x ICV weights + 128 biases) -> vb_a [N,128]
+  const float* vdir_b; float* vb_b;               // net B or NULL
+  const float* t_vals; const float* t_rand; int S, lindisp; float* z_out;   // z_out NULL: no z sampling
+};
+__device__ __forceinline__ float setup_z_at(float near, float far, float t, int lindisp) {
+  const float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));                    // run_nerf.py:359
+  const float a = __fmul_rn(__fdiv_rn(1.0f, near), omt), b = __fmul_rn(__fdiv_rn(1.0f, far), t);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));                                                     // :361
+}
+__global__ void __launch_bounds__(256) ray_setup_kernel(const RaySetupArgs a) {
+  __shared__ float s_enc[VB_RAYS][64];
+  const long long n0 = (long long)blockIdx.x * VB_RAYS;
+  const int j = threadIdx.x & 127, net = threadIdx.x >> 7;
+  const int ICV = a.ICV;
+  if (a.vb_a != nullptr) {
+    for (int i = threadIdx.x; i < VB_RAYS * ICV; i += 256) {
+      const int r = i / ICV, c = i - r * ICV;
+      float v = 0.0f;
+      if (n0 + r < a.N) {
+        const float* d = a.rays + (n0 + r) * a.ray_stride + 8;
+        if (c < 3) v = d[c];
+        else { const int f = (c - 3) / 6, q = (c - 3) % 6; const float x = __fmul_rn(d[q % 3], exp2f((float)f)); v = (q < 3) ? sinf(x) : cosf(x); }
+      }
+      s_enc[r][c] = v;
+    }
+    const float* vdir = net ? a.vdir_b : a.vdir_a;
+    float* vb = net ? a.vb_b : a.vb_a;
+    float w[64];
+    float b = 0.f;
+    if (vdir != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 64; ++c) w[c] = (c < ICV) ? vdir[j * ICV + c] : 0.0f;
+      b = vdir[128 * ICV + j];
+    }
+    __syncthreads();
+    if (vdir != nullptr) {
+      for (int r = 0; r < VB_RAYS && n0 + r < a.N; ++r) {
+        float acc = b;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) if (c < ICV) acc = fmaf(w[c], s_enc[r][c], acc);
+        vb[(n0 + r) * 128 + j] = acc;
+      }
+    }
+  }
+  if (a.z_out != nullptr) {                          // z sampling of the block's rays (coarse_z_kernel's arithmetic)
+    for (int i = threadIdx.x; i < VB_RAYS * a.S; i += 256) {
+      const int r = i / a.S, s = i - r * a.S;
+      const long long n = n0 + r;
+      if (n >= a.N) break;
+      const float near = a.rays[n * a.ray_stride + 6], far = a.rays[n * a.ray_stride + 7];
+      float z = setup_z_at(near, far, a.t_vals[s], a.lindisp);
+      if (a.t_rand != nullptr) {
+        const float zl = (s > 0) ? setup_z_at(near, far, a.t_vals[s - 1], a.lindisp) : z;
+        const float zu = (s < a.S - 1) ? setup_z_at(near, far, a.t_vals[s + 1], a.lindisp) : z;
+        const float lower = (s > 0) ? __fmul_rn(0.5f, __fadd_rn(z, zl)) : z;                    // :367-369
+        const float upper = (s < a.S - 1) ? __fmul_rn(0.5f, __fadd_rn(zu, z)) : z;
+        z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.t_rand[n * a.S + s]));        // :379
+      }
+      a.z_out[n * a.S + s] = z;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fused march kernel
 // ---------------------------------------------------------------------------------------------
@@ -294,6 +364,40 @@ __device__ __forceinline__ void store_act32_pre(const float (&x)[32], const uint
     }
     ptx::st_shared_v4(sw[c16_0 + g] + kb, h0, h1, h2, h3);
   }
+}
+
+// Training mode: the same 32 columns also go straight from registers to the tile image in global memory (the record the
+// backward reads).  A row's eight 16-byte chunks sit at chunk positions c ^ (r & 7): chunks 2p and 2p + 1 share one aligned
+// 32-byte sector, in swapped order when r is odd, so a thread writes its 32 columns as two full-sector 32-byte stores.
+// gsec[p] = byte offset of the sector holding chunks 2p, 2p + 1 of this thread's row inside a K-block (see img_sector_offsets);
+// `field` = address of the K-block pair of this warp's column half in the record.
+__device__ __forceinline__ void img_sector_offsets(int r, uint32_t (&gsec)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) gsec[p] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + (uint32_t)(((2 * p) ^ (r & 6)) << 4);
+}
+template <int COL0>
+__device__ __forceinline__ void store_img32_global(const uint32_t (&h)[16], uint8_t* field, const uint32_t (&gsec)[4], bool odd) {
+  constexpr uint32_t kb = (uint32_t)(COL0 >> 6) * 16384u;
+  constexpr int p0 = ((COL0 & 63) >> 3) >> 1;
+#pragma unroll
+  for (int g2 = 0; g2 < 2; ++g2) {
+    const uint32_t* lo = &h[8 * g2];
+    const uint32_t* hi = &h[8 * g2 + 4];
+    ptx::st_global_v8(field + kb + gsec[p0 + g2], odd ? hi[0] : lo[0], odd ? hi[1] : lo[1], odd ? hi[2] : lo[2], odd ? hi[3] : lo[3],
+                      odd ? lo[0] : hi[0], odd ? lo[1] : hi[1], odd ? lo[2] : hi[2], odd ? lo[3] : hi[3]);
+  }
+}
+// store_act32_pre + the global copy
+template <bool RELU, int COL0>
+__device__ __forceinline__ void store_act32_emit(const float (&x)[32], const uint32_t (&sw)[8], uint8_t* field, const uint32_t (&gsec)[4], bool odd) {
+  constexpr uint32_t kb = (uint32_t)(COL0 >> 6) * 16384u;
+  constexpr int c16_0 = (COL0 & 63) >> 3;
+  uint32_t h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[i] = RELU ? ptx::cvt_relu_f16x2(x[2 * i], x[2 * i + 1]) : ptx::cvt_f16x2(x[2 * i], x[2 * i + 1]);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) ptx::st_shared_v4(sw[c16_0 + g] + kb, h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+  store_img32_global<COL0>(h, field, gsec, odd);
 }
 
 // segmented (per-ray) inclusive scans over one warp; `s` = lane of the segment start at or before

@@ -15,11 +15,12 @@
 //   d_full[2]  both    : multicast commit -> both CTAs' epilogue warps of that slot
 //   act[2]     leader  : 16 arrivals = one per epilogue warp of the slot, 8 local + 8 remote (accumulator drained, A tile written)
 //   enc_full   leader  : 2 arrivals (both sampler warps);  enc_free both: multicast commit after the last encoding chunk
-// Training mode (template parameter EMIT, train_common.cuh): every post-ReLU A tile the epilogue writes (h_l), the
-// encodings and the view layer's post-ReLU output are also copied to a per-tile record in global memory with
-// cp.async.bulk shared -> global, plus the sign bits of the pre-activations; two CTA-local barriers per slot:
-//   st_full[2] local   : 8 arrivals = the slot's epilogue warps wrote the tile (warp e == 0 then issues the bulk store)
-//   st_done[2] local   : the bulk store has finished reading the tile -> the next layer's epilogue may overwrite it
+// Training mode (template parameter EMIT, train_common.cuh): every post-ReLU A tile the epilogue writes (h_l) is also copied to
+// the tile's record in global memory with cp.async.bulk shared -> global, one 16 KB K-block at a time, each as soon as the four
+// warps that own it have written it; the next layer's epilogue waits per K-block (cp.async.bulk.wait_group.read) before it
+// overwrites the tile in place.  The view layer's output goes out straight from the registers as 32-byte sectors
+// (store_img32_global; for the 64 KB tiles that costs more LSU time than it saves: measured).  The sign bits of the
+// pre-activations go out as one 16-byte store per thread and layer; the encodings are bulk-copied by the sampler warp.
 #pragma once
 #include <cuda.h>
 #include "fused_tc.cuh"
@@ -76,8 +77,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
   const uint32_t bar_act = sb + P2_BARS + 128;        // [2] (leader)
   const uint32_t bar_encfull = sb + P2_BARS + 144;    //     (leader)
   const uint32_t bar_encfree = sb + P2_BARS + 152;
-  const uint32_t bar_stfull = sb + P2_BARS + 160;     // [2] (EMIT)
-  const uint32_t bar_stdone = sb + P2_BARS + 176;     // [2] (EMIT)
   // arrive on a barrier that lives in the leader CTA
   // debug heartbeat: trace[blockIdx.x * 32 + role] = last wait this role entered (trace may be mapped host memory)
   auto hb_ = [&](int role, long long code) { if (kTrace2 && p.trace && lane == 0 && blockIdx.x < 32) { volatile long long* t = p.trace; t[3000 + blockIdx.x * 32 + role] = code; } };
@@ -120,7 +119,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_dfull + 8 * x, 1); ptx::mbar_init(bar_act + 8 * x, 16); }
     ptx::mbar_init(bar_encfull, 2);
     ptx::mbar_init(bar_encfree, 2);
-    if (EMIT) for (int x = 0; x < 2; ++x) { ptx::mbar_init(bar_stfull + 8 * x, 8); ptx::mbar_init(bar_stdone + 8 * x, 1); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(s_tmem), 512); ptx::tmem_relinquish2(); }
@@ -292,35 +290,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       composite_rows(p, pend, valid_, lr_, rl_, nr_, row_begin, s, X, q, lane, a_carry);
     };
     const int defer_l = (NL > 1) ? 1 : 0;
-    // training mode: bulk-store bookkeeping of this slot (phases of st_full / st_done, "a store is in flight")
-    uint32_t sfph = 0, sdph = 0;
-    bool st_pending = false;
-    // the previous store of this slot has finished reading the A tile: it may be overwritten
-    auto emit_wait_prev = [&]() {
-      if (EMIT && st_pending) {
-        if (e == 0 && lane == 0) { ptx::bulk_wait_read0(); ptx::mbar_arrive(bar_stdone + 8 * X); }
-        ptx::mbar_wait(bar_stdone + 8 * X, sdph);
-        sdph ^= 1;
-        st_pending = false;
-      }
+    // training mode: this thread's row inside a K-block of the tile image in global memory (hv: store_img32_global)
+    uint32_t gsec[4];
+    img_sector_offsets(r, gsec);
+    const bool r_odd = (r & 1) != 0;
+    // training mode, h_l: the four warps (q = 0..3) that share a column half own two K-blocks (16 KB each) of the slot's A tile.
+    // Each K-block is bulk-copied to the record as soon as those four warps have written it (not when the whole tile is done), and
+    // the next layer's epilogue waits per K-block for the copy that still reads it -- the copies get most of a layer's time to
+    // drain instead of one MMA pass.  Lane 0 of warp q == 0 issues and waits; named barrier 3 + 2 X + ch joins the four warps.
+    const int emit_bar = 3 + X * 2 + ch;
+    const bool emit_issuer = EMIT && q == 0 && lane == 0;
+    auto emit_gate = [&](bool all) {                  // the K-block about to be overwritten is no longer being read
+      if (emit_issuer) { if (all) ptx::bulk_wait_read0(); else ptx::bulk_wait_read1(); }
+      ptx::named_bar_sync(emit_bar, 128);
     };
-    // all 8 warps of the slot have written (and proxy-fenced) their part of the tile: warp e == 0 copies `bytes` from
-    // shared-memory offset `src` to the record field at `dst`
-    auto emit_store = [&](uint8_t* dst, uint32_t src, uint32_t bytes) {
-      if (EMIT) {
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_stfull + 8 * X);
-        if (e == 0) {
-          ptx::mbar_wait(bar_stfull + 8 * X, sfph);
-          sfph ^= 1;
-          if (lane == 0) {
-            for (uint32_t o = 0; o < bytes; o += 16384u) ptx::bulk_s2g(dst + o, src + o, 16384u);
-            ptx::bulk_commit();
-          }
-          __syncwarp();
-        }
-        st_pending = true;
-      }
+    auto emit_kblock = [&](uint8_t* dst, uint32_t src) {   // K-block written by all four warps -> record
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(emit_bar, 128);
+      if (emit_issuer) { ptx::bulk_s2g(dst, src, 16384u); ptx::bulk_commit(); }
     };
     for (int st = 0; st < nst; ++st) {
       float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f, hp3 = 0.f;           // head partial sums of this thread's columns
@@ -340,7 +327,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
         dph ^= 1;
         ptx::tc_fence_after();
         if (tr) trp[1] = clock64();
-        emit_wait_prev();
         if (l <= D) {
           // pts layer (ReLU) or feature layer (no activation): 128 columns per warp in 4 batches,
           // the TMEM load of batch b+1 in flight while batch b is converted and stored
@@ -385,6 +371,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
               }
             }
             if (write_act) {
+              if (EMIT) {
+                // batches 0, 1 fill K-block 2 ch, batches 2, 3 K-block 2 ch + 1 (the previous layer's copies: one group each, in this order)
+                if (b == 0) emit_gate(false);
+                if (b == 2) {
+                  if (l < D) emit_kblock(arec + rec_act_h(l) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
+                  emit_gate(l == D);                            // (l == D: nothing was committed in between -> drain everything)
+                }
+              }
               // (b & 1) selects the K-block inside the column half; ch selects the half: the
               // immediate part of the address is compile-time, the row/swizzle part is in sw[]
               if (l < D) {
@@ -407,7 +401,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           arrive_leader(bar_act + 8 * X);
           if (EMIT) {
             if (l < D) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-            if (l < D) emit_store(arec + rec_act_h(l), act_base, 65536u);     // h_l; feature_linear's output (l == D) is not recorded
+            // second K-block of h_l (feature_linear's output, l == D, is not recorded)
+            if (l < D && write_act) emit_kblock(arec + rec_act_h(l) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
           }
           if (tr) trp[2] = clock64();
           if (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) { p.trace[2500 + blockIdx.x * 32 + (warp - 4) * 2] = t_f; p.trace[2501 + blockIdx.x * 32 + (warp - 4) * 2] = clock64(); }
@@ -423,15 +418,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           ptx::fence_proxy_async_smem();
           arrive_leader(bar_act + 8 * X);                      // accumulator drained: next super-tile may start
           uint32_t mkv[2] = {0u, 0u};                             // EMIT: sign bits of this thread's 64 pre-activations
-          // EMIT: post-ReLU fp16 copy of this thread's 64 columns into K-block (2 + ch) of the (dead) A tile
-          const uint32_t hvoff = ch ? 16384u : 32768u;            // relative to swk[] (which points at K-block 2 * ch)
+          // EMIT: post-ReLU fp16 copy of this thread's 64 columns = one row of K-block `ch` of the hv image, from registers
+          uint8_t* const hvfield = EMIT ? arec + rec_act_hv(D) + (uint32_t)ch * 16384u : nullptr;
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             const int col0 = ch * 64 + b * 32;
             const uint32_t (&v)[32] = b ? vb : va;
             const float4* vb4 = reinterpret_cast<const float4*>(vbrow + col0);
             const uint32_t w0 = a_heads + (uint32_t)(256 + col0) * 4u;
-            uint32_t hh[4];
+            uint32_t hh[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 bb = vb4[j];
@@ -440,20 +435,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
               const float h0 = fmaxf(a0, 0.f), h1 = fmaxf(a1, 0.f), h2 = fmaxf(a2, 0.f), h3 = fmaxf(a3, 0.f);
               if (EMIT) {
                 mkv[b] = mask_push(mask_push(mask_push(mask_push(mkv[b], a0), a1), a2), a3);
-                hh[(j & 1) * 2] = ptx::cvt_f16x2(h0, h1); hh[(j & 1) * 2 + 1] = ptx::cvt_f16x2(h2, h3);
-                if (j & 1) ptx::st_shared_v4(swk[b * 4 + (j >> 1)] + hvoff, hh[0], hh[1], hh[2], hh[3]);
+                hh[2 * j] = ptx::cvt_f16x2(h0, h1); hh[2 * j + 1] = ptx::cvt_f16x2(h2, h3);
               }
               const float4 wr = lds128(w0 + 16 * j), wg = lds128(w0 + 512 + 16 * j), wb = lds128(w0 + 1024 + 16 * j);
               hp0 = fmaf(h0, wr.x, hp0); hp0 = fmaf(h1, wr.y, hp0); hp0 = fmaf(h2, wr.z, hp0); hp0 = fmaf(h3, wr.w, hp0);
               hp1 = fmaf(h0, wg.x, hp1); hp1 = fmaf(h1, wg.y, hp1); hp1 = fmaf(h2, wg.z, hp1); hp1 = fmaf(h3, wg.w, hp1);
               hp2 = fmaf(h0, wb.x, hp2); hp2 = fmaf(h1, wb.y, hp2); hp2 = fmaf(h2, wb.z, hp2); hp2 = fmaf(h3, wb.w, hp2);
             }
+            if (EMIT) { if (b == 0) store_img32_global<0>(hh, hvfield, gsec, r_odd); else store_img32_global<32>(hh, hvfield, gsec, r_odd); }
           }
-          if (EMIT) {
-            *reinterpret_cast<uint2*>(mrec + (uint32_t)D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u) = make_uint2(mkv[0], mkv[1]);
-            ptx::fence_proxy_async_smem();
-            emit_store(arec + rec_act_hv(D), act_base + 32768u, 32768u);
-          }
+          if (EMIT) *reinterpret_cast<uint2*>(mrec + (uint32_t)D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u) = make_uint2(mkv[0], mkv[1]);
         }
         if (l == defer_l && st > 0 && ch == 0) composite_st(st - 1);
       }
@@ -474,7 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       }
     }
     if (ch == 0 && nst > 0) composite_st(nst - 1);                 // the last super-tile's rows
-    if (EMIT && e == 0 && lane == 0) ptx::bulk_wait_all();         // this thread's bulk stores (shared memory must outlive them)
+    if (emit_issuer) ptx::bulk_wait_all();
   } else {
     // =========================== sampler (warp 3) ===========================
     const int t = threadIdx.x - 96;                               // 0..31

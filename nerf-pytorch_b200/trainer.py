@@ -105,10 +105,14 @@ class FusedTrainStep:
             if self.Ni > 0:
                 self._sv_f, self._act_f, self._mask_f = api._train_save(lib, N, Sf, self._np_f, self.dev)
             self._ws = torch.empty(lib.nerf_b200_march_workspace_bytes(N, Sf), dtype=torch.uint8, device=self.dev)
-            bw = lib.nerf_b200_march_bwd_tc_workspace_bytes(N, Sc, C.byref(self._np_c))
-            if self.Ni > 0:
-                bw = max(bw, lib.nerf_b200_march_bwd_tc_workspace_bytes(N, Sf, C.byref(self._np_f)))
+            bw = lib.nerf_b200_render_rays_bwd_tc_workspace_bytes(N, Sc, C.byref(self._np_c), Sf if self.Ni > 0 else 0,
+                                                                  C.byref(self._np_f) if self.Ni > 0 else None)
             self._bws = torch.empty(bw + 1024, dtype=torch.uint8, device=self.dev)
+        o = self.out
+        self._bp_c = _lib.NerfBwdPass(api._ptr(self.z_c), api._ptr(self.noise0), Sc, C.pointer(self._np_c), api._ptr(self._pk_c), api._ptr(o["raw0"]),
+                                      C.pointer(self._sv_c), api._ptr(o["g_rgb0"]), C.pointer(self._gs[0]))
+        self._bp_f = _lib.NerfBwdPass(api._ptr(self.z_f), api._ptr(self.noise1), Sf, C.pointer(self._np_f), api._ptr(self._pk_f), api._ptr(o["raw"]),
+                                      C.pointer(self._sv_f), api._ptr(o["g_rgb"]), C.pointer(self._gs[-1])) if self.Ni > 0 else None
         self._cam = api._camera(self.H, self.W, self.K)
         self._cfg = api._cfg_struct(self.cfgd, 11)
         self.host_loss = torch.zeros(4, dtype=torch.float32, device="cpu").pin_memory()
@@ -179,14 +183,9 @@ class FusedTrainStep:
             if fine:
                 check(lib.nerf_b200_mse_seed(api._ptr(o["rgb"]), api._ptr(self.target), N, gscale, api._ptr(o["g_rgb"]), api._ptr(self.state), st), "mse_seed")
             check(lib.nerf_b200_mse_seed(api._ptr(o["rgb0"]), api._ptr(self.target), N, gscale, api._ptr(o["g_rgb0"]), api._ptr(self.state), st), "mse_seed")
-            # backward of both passes into the flat gradient buffer
-            check(lib.nerf_b200_march_bwd_tc(api._ptr(self.packed_rays), api._ptr(self.z_c), api._ptr(self.noise0), N, self.Sc, C.byref(self._np_c),
-                                             api._ptr(self._pk_c), C.byref(cfg), api._ptr(o["raw0"]), C.byref(self._sv_c), api._ptr(o["g_rgb0"]),
-                                             C.byref(self._gs[0]), api._ptr(self._bws), self._bws.numel(), st), "march_bwd_tc")
-            if fine:
-                check(lib.nerf_b200_march_bwd_tc(api._ptr(self.packed_rays), api._ptr(self.z_f), api._ptr(self.noise1), N, self.Sc + self.Ni, C.byref(self._np_f),
-                                                 api._ptr(self._pk_f), C.byref(cfg), api._ptr(o["raw"]), C.byref(self._sv_f), api._ptr(o["g_rgb"]),
-                                                 C.byref(self._gs[-1]), api._ptr(self._bws), self._bws.numel(), st), "march_bwd_tc")
+            # backward of both passes into the flat gradient buffer (one call: the passes are scheduled side by side)
+            check(lib.nerf_b200_render_rays_bwd_tc(api._ptr(self.packed_rays), N, C.byref(cfg), C.byref(self._bp_c),
+                                                   C.byref(self._bp_f) if fine else None, api._ptr(self._bws), self._bws.numel(), st), "render_rays_bwd_tc")
 
     def _adam(self):
         with api._on(self.rays):
