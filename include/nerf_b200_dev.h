@@ -24,8 +24,8 @@ int nerf_b200_debug_l2_stream(const void* buf, int buf_bytes, int chunk, int sta
 int nerf_b200_debug_epi_rate(int reps, int mode, int mma, void* out_2_i64, void* stream);
 /* stream `bytes` of HBM: mode 0 read src, 1 write dst, 2 copy src -> dst; plain 16-byte loads/stores, nblocks x 512 threads */
 /* one CTA per SM streams its own bytes_per_cta of `buf`: mode 0 cp.async.bulk g2s ring, 1 cp.async 16 B ring, 2 cp.async.bulk s2g,
- * 3 st.global.v4, 4 ld.global.v4; out[nblocks + 1] int64 = cycles per CTA */
-int nerf_b200_debug_dram_stream(void* buf, size_t bytes_per_cta, int chunk, int stages, int mode, int nblocks, void* out_i64, void* stream);
+ * 3 st.global.v4, 4 ld.global.v4; scatter != 0: the chunks of a region are visited in a strided order; out[nblocks + 1] int64 = cycles per CTA */
+int nerf_b200_debug_dram_stream(void* buf, size_t bytes_per_cta, int chunk, int stages, int mode, int nblocks, int scatter, void* out_i64, void* stream);
 int nerf_b200_debug_hbm_stream(const void* src, void* dst, size_t bytes, int mode, int nblocks, void* stream);
 #ifdef __cplusplus
 }

@@ -122,6 +122,7 @@ struct DgradParams {
   long long N; int S, rays_per_cta, nst_plan, D;
   uint32_t rec_mask, rec_grad;
   unsigned long long pair_half_bytes;       // bytes of one rank's half of the backward chunk stream
+  int dbg;                                  // NERF_B200_DBG_EMIT experiments (1: no record copies, 2: L2 evict_first hint)
   int vc0, vc1;                             // forward CTAs [vc0, vc1) (both even): this launch's CTA b serves vc0 + b, vc0 + b + gridDim, ...
 };
 
@@ -301,22 +302,25 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     arrive_leader(bar_act + 8 * X);                            // accumulator initially free
     uint32_t dph = 0;
     uint32_t swk[8];
-    // gradient record: each 16 KB K-block of the A tile is bulk-copied out as soon as the four warps (q = 0..3) that share a
-    // column half have written it, and the next step waits per K-block for the copy that still reads it (as in the forward's
-    // training mode, fused_tc2.cuh).  Lane 0 of warp q == 0 issues and waits; named barrier 3 + 2 X + ch joins the four warps.
-    const int emit_bar = 3 + X * 2 + ch;
-    const bool emit_issuer = (q == 0) && lane == 0;
-    auto emit_gate = [&]() {
-      if (emit_issuer) ptx::bulk_wait_read1();
-      ptx::named_bar_sync(emit_bar, 128);
-    };
-    auto emit_kblock = [&](uint8_t* dst, uint32_t src) {
-      ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(emit_bar, 128);
-      if (emit_issuer) { ptx::bulk_s2g(dst, src, 16384u); ptx::bulk_commit(); }
-    };
 #pragma unroll
     for (int c = 0; c < 8; ++c) swk[c] = act_base + (uint32_t)(ch * 2) * 16384u + act_row_off(r) + (uint32_t)((c ^ (r & 7)) << 4);
+    // gradient record: every warp copies ITS 32 rows of a K-block (4 KB, contiguous in the image) out as soon as it has written
+    // them and, before it overwrites a K-block in the next step, waits for its own older copy to finish reading -- warp-local,
+    // as in the forward's training mode (fused_tc2.cuh)
+    const uint32_t slice = (uint32_t)q * 4096u;
+    const uint64_t l2_first = ptx::l2_policy_evict_first();
+    auto emit_gate = [&]() {
+      if (lane == 0) ptx::bulk_wait_read1();
+      __syncwarp();
+    };
+    auto emit_slice = [&](uint8_t* dst_kblock, uint32_t src_kblock) {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (!(p.dbg & 1)) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
+        ptx::bulk_commit();
+      }
+    };
     for (int vc = p.vc0 + (int)blockIdx.x; vc < p.vc1; vc += (int)gridDim.x) {
     const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, vc);
     const int nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, vc);
@@ -363,7 +367,7 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
           // next step's A operand, in place; batches 0, 1 fill K-block 2 ch, batches 2, 3 K-block 2 ch + 1
           if (b == 0) emit_gate();
           if (b == 2) {
-            emit_kblock(grec + rec_grad_step(j) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
+            emit_slice(grec + rec_grad_step(j) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
             emit_gate();
           }
           if (b == 0) store_grad32_pre<0>(x, swk); else if (b == 1) store_grad32_pre<32>(x, swk);
@@ -372,11 +376,11 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         arrive_leader(bar_act + 8 * X);
-        emit_kblock(grec + rec_grad_step(j) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
+        emit_slice(grec + rec_grad_step(j) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
       }
     }
     }
-    if (emit_issuer) ptx::bulk_wait_all();
+    if (lane == 0) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before();
@@ -462,8 +466,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1) wgra
           ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(xkb + ykb) * 8192u);
           const uint8_t* xs = p.grad + (size_t)t * p.rec_grad + job.a_off + h * 8192;
           const uint8_t* ys = p.act + (size_t)t * p.rec_act + job.b_off + h * 8192;
+          if (p.dbg & 2) {
+            const uint64_t pol = ptx::l2_policy_evict_first();
+            for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s_hint(sb + s * stride + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s, pol);
+            for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s_hint(sb + s * stride + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s, pol);
+          } else {
           for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s(sb + s * stride + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s);
           for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s(sb + s * stride + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s);
+          }
         }
         __syncwarp();
         if (++s == nstg) { s = 0; ph ^= 1; }

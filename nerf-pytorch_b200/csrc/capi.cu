@@ -55,6 +55,7 @@ static int smem_optin(const void* fn, size_t bytes) {
 
 // per-device facts (SM count; which kernels already have their > 48 KB shared-memory opt-in): the library may be used
 // on several devices of one process, and cudaFuncSetAttribute is per device
+static int dbg_emit() { static int v = -1; if (v < 0) { const char* e = getenv("NERF_B200_DBG_EMIT"); v = e ? atoi(e) : 0; } return v; }
 struct DeviceState { int sms; bool optin_fwd, optin_bwd; cudaStream_t side; cudaEvent_t ev[10]; };
 static DeviceState* device_state() {
   static DeviceState st[64];
@@ -154,6 +155,7 @@ static int launch_march(const float* rays, int ray_stride, const float* z_vals, 
     NB_CHECK_ARG((reinterpret_cast<uintptr_t>(save->act) & 15) == 0 && (reinterpret_cast<uintptr_t>(save->mask) & 15) == 0, "save buffers must be 16-byte aligned");
     sv.act = static_cast<uint8_t*>(save->act); sv.mask = static_cast<uint8_t*>(save->mask);
     sv.nst_plan = plan.nst; sv.rec_act = rec_act_bytes(net->D); sv.rec_mask = rec_mask_bytes(net->D);
+    sv.dbg = dbg_emit();
   }
   TimedLaunch* tl = nullptr;
   if (g_timing && g_ntimed < 4096) {
@@ -865,7 +867,7 @@ struct BwdTcPass {
     dp.N = N; dp.S = S; dp.rays_per_cta = plan.rays_per_cta; dp.nst_plan = plan.nst; dp.D = D;
     dp.rec_mask = rec_mask_bytes(D); dp.rec_grad = rec_grad_bytes(D);
     dp.pair_half_bytes = PL.bwd_bytes / 2;
-    dp.vc0 = vc0; dp.vc1 = vc1;
+    dp.vc0 = vc0; dp.vc1 = vc1; dp.dbg = dbg_emit();
     int grid = vc1 - vc0;
     if (grid > ctas) grid = ctas;
     grid &= ~1;

@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(512) hbm_stream_kernel(const uint4* __restrict
 // out[blockIdx.x] = clock cycles of the CTA's stream.
 constexpr int DSP_THREADS = 512;
 __global__ void __launch_bounds__(DSP_THREADS, 1) dram_stream_probe_kernel(uint8_t* __restrict__ buf, unsigned long long bytes_per_cta, int chunk, int stages,
-                                                                           int mode, long long* out) {
+                                                                           int mode, long long* out, int scatter) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sb = ptx::smem_u32(smem);
@@ -509,6 +509,9 @@ __global__ void __launch_bounds__(DSP_THREADS, 1) dram_stream_probe_kernel(uint8
   const int warp = threadIdx.x >> 5;
   uint8_t* base = buf + (size_t)blockIdx.x * bytes_per_cta;
   const int n = (int)(bytes_per_cta / (unsigned)chunk);
+  // scatter: chunk i of the CTA's region is visited in a strided order (i * 37 mod n: successive chunks ~600 KB apart for 16 KB
+  // chunks), like the per-tile records of the training kernels, instead of front to back
+  auto at = [&](int i) -> size_t { return (size_t)(scatter ? (int)(((long long)i * 37) % n) : i) * (size_t)chunk; };
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(sb + BAR + 8 * i, mode == 1 ? 128 : 1); ptx::mbar_init(sb + BAR + 128 + 8 * i, 1); }
     ptx::fence_mbar_init();
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(DSP_THREADS, 1) dram_stream_probe_kernel(uint8
         ptx::mbar_wait(sb + BAR + 128 + 8 * stage, ph ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(sb + BAR + 8 * stage, chunk);
-          for (int o = 0; o < chunk; o += 8192) ptx::bulk_g2s(sb + stage * chunk + o, base + (size_t)i * chunk + o, (chunk - o) < 8192 ? (chunk - o) : 8192, sb + BAR + 8 * stage);
+          for (int o = 0; o < chunk; o += 8192) ptx::bulk_g2s(sb + stage * chunk + o, base + at(i) + o, (chunk - o) < 8192 ? (chunk - o) : 8192, sb + BAR + 8 * stage);
         }
         __syncwarp();
         if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(DSP_THREADS, 1) dram_stream_probe_kernel(uint8
     if (threadIdx.x == 0) {
       ptx::fence_proxy_async_smem();
       for (int i = 0; i < n; ++i) {
-        for (int o = 0; o < chunk; o += 16384) ptx::bulk_s2g(base + (size_t)i * chunk + o, sb + (uint32_t)(i % stages) * chunk + o, (chunk - o) < 16384 ? (chunk - o) : 16384);
+        for (int o = 0; o < chunk; o += 16384) ptx::bulk_s2g(base + at(i) + o, sb + (uint32_t)(i % stages) * chunk + o, (chunk - o) < 16384 ? (chunk - o) : 16384);
         ptx::bulk_commit();
         switch (stages) {
           case 1: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;

@@ -47,7 +47,7 @@ constexpr bool kTrace2 = false;
 #endif
 
 // training-mode save buffers of one pass (train_common.cuh)
-struct TrainSaveDev { uint8_t* act; uint8_t* mask; int nst_plan; uint32_t rec_act, rec_mask; };
+struct TrainSaveDev { uint8_t* act; uint8_t* mask; int nst_plan; uint32_t rec_act, rec_mask; int dbg; };   // dbg: NERF_B200_DBG_EMIT experiments
 static_assert(P2_TOTAL <= SM_ALLOC, "pair kernel shared-memory map exceeds the allocation");
 
 // ring units per pass of layer l (all even)
@@ -290,24 +290,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       composite_rows(p, pend, valid_, lr_, rl_, nr_, row_begin, s, X, q, lane, a_carry);
     };
     const int defer_l = (NL > 1) ? 1 : 0;
-    // training mode: this thread's row inside a K-block of the tile image in global memory (hv: store_img32_global)
-    uint32_t gsec[4];
-    img_sector_offsets(r, gsec);
-    const bool r_odd = (r & 1) != 0;
-    // training mode, h_l: the four warps (q = 0..3) that share a column half own two K-blocks (16 KB each) of the slot's A tile.
-    // Each K-block is bulk-copied to the record as soon as those four warps have written it (not when the whole tile is done), and
-    // the next layer's epilogue waits per K-block for the copy that still reads it -- the copies get most of a layer's time to
-    // drain instead of one MMA pass.  Lane 0 of warp q == 0 issues and waits; named barrier 3 + 2 X + ch joins the four warps.
-    const int emit_bar = 3 + X * 2 + ch;
-    const bool emit_issuer = EMIT && q == 0 && lane == 0;
-    auto emit_gate = [&](bool all) {                  // the K-block about to be overwritten is no longer being read
-      if (emit_issuer) { if (all) ptx::bulk_wait_read0(); else ptx::bulk_wait_read1(); }
-      ptx::named_bar_sync(emit_bar, 128);
+    // training mode: every warp copies ITS 32 rows of a K-block (4 KB, contiguous in the image) to the record as soon as it has
+    // written them -- cp.async.bulk shared -> global issued by lane 0, one bulk group per slice -- and before it overwrites a
+    // K-block in the next layer it waits for its own older copy to finish reading (wait_group.read 1: the newer group, the
+    // other K-block, may still be pending).  Nothing here crosses a warp: no barrier joins the epilogue warps.
+    const uint32_t slice = (uint32_t)q * 4096u;
+    const uint64_t l2_first = EMIT ? ptx::l2_policy_evict_first() : 0ull;      // records are written once, read once by the backward
+    auto emit_gate = [&](bool all) {
+      if (sv.dbg & 8) return;
+      if (lane == 0) { if (all) ptx::bulk_wait_read0(); else ptx::bulk_wait_read1(); }
+      __syncwarp();
     };
-    auto emit_kblock = [&](uint8_t* dst, uint32_t src) {   // K-block written by all four warps -> record
+    auto emit_slice = [&](uint8_t* dst_kblock, uint32_t src_kblock) {
+      if (sv.dbg & 8) return;
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(emit_bar, 128);
-      if (emit_issuer) { ptx::bulk_s2g(dst, src, 16384u); ptx::bulk_commit(); }
+      __syncwarp();
+      if (lane == 0) {
+        if (!(sv.dbg & 1)) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
+        ptx::bulk_commit();
+      }
     };
     for (int st = 0; st < nst; ++st) {
       float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f, hp3 = 0.f;           // head partial sums of this thread's columns
@@ -345,7 +346,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
             if (b < 3) ptx::tmem_ld_x32(t_lane + col0 + 32, vn);
             float x[32];
             as_float32(v, x);
-            if (EMIT && l < D) {
+            if (EMIT && l < D && !(sv.dbg & 4)) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) mk[b] = mask_push(mk[b], x[j]);
             }
@@ -375,7 +376,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
                 // batches 0, 1 fill K-block 2 ch, batches 2, 3 K-block 2 ch + 1 (the previous layer's copies: one group each, in this order)
                 if (b == 0) emit_gate(false);
                 if (b == 2) {
-                  if (l < D) emit_kblock(arec + rec_act_h(l) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
+                  if (l < D) emit_slice(arec + rec_act_h(l) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
                   emit_gate(l == D);                            // (l == D: nothing was committed in between -> drain everything)
                 }
               }
@@ -400,9 +401,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           const long long t_f = (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) ? clock64() : 0;
           arrive_leader(bar_act + 8 * X);
           if (EMIT) {
-            if (l < D) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+            if (l < D && !(sv.dbg & 4)) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
             // second K-block of h_l (feature_linear's output, l == D, is not recorded)
-            if (l < D && write_act) emit_kblock(arec + rec_act_h(l) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
+            if (l < D && write_act) emit_slice(arec + rec_act_h(l) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
           }
           if (tr) trp[2] = clock64();
           if (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) { p.trace[2500 + blockIdx.x * 32 + (warp - 4) * 2] = t_f; p.trace[2501 + blockIdx.x * 32 + (warp - 4) * 2] = clock64(); }
@@ -418,15 +419,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           ptx::fence_proxy_async_smem();
           arrive_leader(bar_act + 8 * X);                      // accumulator drained: next super-tile may start
           uint32_t mkv[2] = {0u, 0u};                             // EMIT: sign bits of this thread's 64 pre-activations
-          // EMIT: post-ReLU fp16 copy of this thread's 64 columns = one row of K-block `ch` of the hv image, from registers
-          uint8_t* const hvfield = EMIT ? arec + rec_act_hv(D) + (uint32_t)ch * 16384u : nullptr;
+          // EMIT: post-ReLU fp16 copy of this thread's 64 columns = one row of K-block `ch` of the hv image, parked in K-block
+          // 2 ch + 1 of the (dead) A tile -- this warp's own rows, drained by the l == D gate -- and copied out like the h_l slices
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             const int col0 = ch * 64 + b * 32;
             const uint32_t (&v)[32] = b ? vb : va;
             const float4* vb4 = reinterpret_cast<const float4*>(vbrow + col0);
             const uint32_t w0 = a_heads + (uint32_t)(256 + col0) * 4u;
-            uint32_t hh[16];
+            uint32_t hh[4];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 bb = vb4[j];
@@ -435,16 +436,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
               const float h0 = fmaxf(a0, 0.f), h1 = fmaxf(a1, 0.f), h2 = fmaxf(a2, 0.f), h3 = fmaxf(a3, 0.f);
               if (EMIT) {
                 mkv[b] = mask_push(mask_push(mask_push(mask_push(mkv[b], a0), a1), a2), a3);
-                hh[2 * j] = ptx::cvt_f16x2(h0, h1); hh[2 * j + 1] = ptx::cvt_f16x2(h2, h3);
+                hh[(j & 1) * 2] = ptx::cvt_f16x2(h0, h1); hh[(j & 1) * 2 + 1] = ptx::cvt_f16x2(h2, h3);
+                if (j & 1) ptx::st_shared_v4(swk[b * 4 + (j >> 1)] + 16384u, hh[0], hh[1], hh[2], hh[3]);
               }
               const float4 wr = lds128(w0 + 16 * j), wg = lds128(w0 + 512 + 16 * j), wb = lds128(w0 + 1024 + 16 * j);
               hp0 = fmaf(h0, wr.x, hp0); hp0 = fmaf(h1, wr.y, hp0); hp0 = fmaf(h2, wr.z, hp0); hp0 = fmaf(h3, wr.w, hp0);
               hp1 = fmaf(h0, wg.x, hp1); hp1 = fmaf(h1, wg.y, hp1); hp1 = fmaf(h2, wg.z, hp1); hp1 = fmaf(h3, wg.w, hp1);
               hp2 = fmaf(h0, wb.x, hp2); hp2 = fmaf(h1, wb.y, hp2); hp2 = fmaf(h2, wb.z, hp2); hp2 = fmaf(h3, wb.w, hp2);
             }
-            if (EMIT) { if (b == 0) store_img32_global<0>(hh, hvfield, gsec, r_odd); else store_img32_global<32>(hh, hvfield, gsec, r_odd); }
           }
-          if (EMIT) *reinterpret_cast<uint2*>(mrec + (uint32_t)D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u) = make_uint2(mkv[0], mkv[1]);
+          if (EMIT) {
+            *reinterpret_cast<uint2*>(mrec + (uint32_t)D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u) = make_uint2(mkv[0], mkv[1]);
+            emit_slice(arec + rec_act_hv(D) + (uint32_t)ch * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
+          }
         }
         if (l == defer_l && st > 0 && ch == 0) composite_st(st - 1);
       }
@@ -465,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       }
     }
     if (ch == 0 && nst > 0) composite_st(nst - 1);                 // the last super-tile's rows
-    if (emit_issuer) ptx::bulk_wait_all();
+    if (EMIT && lane == 0) ptx::bulk_wait_all();
   } else {
     // =========================== sampler (warp 3) ===========================
     const int t = threadIdx.x - 96;                               // 0..31

@@ -273,3 +273,31 @@ def test_tensor_core_gradients_end_to_end(G, fixture):
     med = float(np.median([v["vs_reference"] for v in stats.values()]))
     print(fixture, "tensor-core gradients vs reference autograd: median", med, "worst", worst)
     assert med < 3e-2 and worst < 1.5e-1, (med, worst, stats)
+
+
+def test_full_batch_tensor_core_gradients_are_stable_and_match_exact(G):
+    """BASELINE config 2 at full size (4096 rays x 64+128: every CTA walks many super-tiles, all 148 SMs stream records
+    concurrently) -- the sizes at which an ordering bug in the record copies would show: three evaluations of render() +
+    loss.backward() on the tensor-core path agree with each other (atomics reorder sums: 1e-4) and with the exact fp32
+    backward of the same library within the fp16 budget of the end-to-end test."""
+    fx = dict(load_golden("lego_grads"))
+    sb = G.synth.ray_batch("lego", 4096, seed=3)
+    fx["rays"], fx["H"], fx["W"], fx["K"] = sb["rays"], sb["H"], sb["W"], sb["K"]
+    fx["target"] = np.random.default_rng(5).random((4096, 3), dtype=np.float32)
+    runs = [_render_grads(G, fx, "tc_fp16", "tc") for _ in range(3)]
+    loss_ex, nets_ex = _render_grads(G, fx, "fp32", "exact")
+    devs, rep = [], []
+    for k in range(2):
+        ex = dict(nets_ex[k].named_parameters())
+        for name, p in runs[0][1][k].named_parameters():
+            g0 = p.grad.detach().double()
+            assert torch.isfinite(g0).all(), name
+            for other in runs[1:]:
+                g1 = dict(other[1][k].named_parameters())[name].grad.detach().double()
+                rep.append(float((g1 - g0).norm() / g0.norm().clamp_min(1e-30)))
+            devs.append(float((g0 - ex[name].grad.detach().double()).norm() / ex[name].grad.detach().double().norm().clamp_min(1e-30)))
+    _record("full_batch_4096", {"repeat_max": max(rep), "vs_exact_median": float(np.median(devs)), "vs_exact_max": max(devs),
+                                "loss_rel": abs(runs[0][0] - loss_ex) / loss_ex})
+    assert max(rep) < 1e-4, max(rep)
+    assert abs(runs[0][0] - loss_ex) / loss_ex < 5e-4
+    assert float(np.median(devs)) < 3e-2 and max(devs) < 1.5e-1, (float(np.median(devs)), max(devs))
