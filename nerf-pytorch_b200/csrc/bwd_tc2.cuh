@@ -7,7 +7,7 @@
 // saturating conversions) and fp32 accumulation in TMEM:
 //
 //   raw2outputs_bwd_kernel (small_kernels.cuh)  dL/draw per sample                       
-//   dhv_seed_kernel      d_hv = relu'(hv) * (d_rgb W_rgb) as tile images                 (rgb_linear backward, :114)
+//   dhv_seed_heads_kernel  d_hv = relu'(hv) * (d_rgb W_rgb) as tile images + rgb_linear's weight / bias gradient (:114)
 //   dgrad_tc2_kernel     the chain  d_hv -> d_feat -> dA_{D-1} -> ... -> dA_0  as tcgen05 cta_group::2 passes with
 //                        TRANSPOSED weight chunks streamed through the forward's 7 x 8 KB TMA ring; the epilogue applies
 //                        the ReLU mask (and the alpha_linear rank-1 term), writes the next A tile in place and the same
@@ -18,8 +18,8 @@
 //                        its tiles (256 x 256 fp32 = all 512 columns) and leaves the SM once; bias gradients are the
 //                        column sums of the dA tiles while they sit in shared memory.
 //   wgrad_reduce_kernel  sums the per-CTA partial dW, un-scales, adds into the gradient tensors
-//   head_grads_kernel    rgb_linear gradients (CUDA cores, tiny); alpha_linear's and the per-ray row sums of d_hv are computed
-//                        by the wgrad kernel's spare warps from the tiles it streams anyway
+//                        (alpha_linear's gradient and the per-ray row sums of d_hv are computed by the wgrad kernel's spare
+//                        warps from the tiles it streams anyway)
 //   views_enc_wgrad_kernel  views_linears[0].weight[:, W:] from the per-ray sums and gamma(viewdir)
 //   views_feat_wgrad_kernel views_linears[0].weight[:, :W] = (d_hv^T h_{D-1}) W_feat^T + db_v b_feat^T (feature_linear's output is never stored)
 //
@@ -70,47 +70,74 @@ __global__ void encv_kernel(const float* __restrict__ dirs, int stride, long lon
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// seed of the dgrad chain: d_hv[row][c] = scale * (hv[row][c] > 0) * sum_j d_rgb[row][j] W_rgb[j][c]   (c < 128)
-// as the first 32 KB of every tile's gradient record (rows beyond the CTA's range: zeros)
+// rgb_linear's backward (run_nerf_helpers.py:114), both halves in one sweep over the rows:
+//   seed of the dgrad chain: d_hv[row][c] = scale * (hv[row][c] > 0) * sum_j d_rgb[row][j] W_rgb[j][c]   (c < 128), written as the
+//     first 32 KB of every tile's gradient record (rows beyond the CTA's range: zeros -- dgrad and wgrad rely on that);
+//   weight / bias gradient: dW_rgb[j][c] += sum_rows d_rgb[row][j] hv[row][c],  db_rgb[j] += sum_rows d_rgb[row][j]   (fp32)
+// One warp per row, lane = four columns: a row is 256 contiguous bytes of hv in and of d_hv out (two 128-byte lines each).
 // ---------------------------------------------------------------------------------------------------------------
 struct SeedParams {
-  const float* d_raw; const uint8_t* mask; uint8_t* grad; const float* rgb_w; const unsigned int* amax;
+  const float* d_raw; const uint8_t* mask; const uint8_t* act; uint8_t* grad; const float* rgb_w; const unsigned int* amax;
   long long N; int S, rays_per_cta, nst_plan, D;
-  uint32_t rec_mask, rec_grad; long long n_tiles;
+  uint32_t rec_mask, rec_act, rec_grad; long long n_tiles;
+  float* g_rgb_w; float* g_rgb_b;
 };
 
-__global__ void __launch_bounds__(256, 4) dhv_seed_kernel(const SeedParams p) {
-  __shared__ float s_w[3 * 128];
-  for (int i = threadIdx.x; i < 384; i += 256) s_w[i] = p.rgb_w[i];
-  __syncthreads();
+__global__ void __launch_bounds__(256, 4) dhv_seed_heads_kernel(const SeedParams p) {
+  __shared__ float s_acc[8][12 * 32 + 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane * 4, ch = lane >> 4, wsel = (lane >> 3) & 1, bit0 = c & 31;
   const float scale = loss_scale_from_absmax(__uint_as_float(*p.amax));
-  const int r = threadIdx.x >> 1, ch = threadIdx.x & 1;
+  float wr[4], wg[4], wb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { wr[i] = p.rgb_w[c + i] * scale; wg[i] = p.rgb_w[128 + c + i] * scale; wb[i] = p.rgb_w[256 + c + i] * scale; }
+  float a[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) a[i] = 0.f;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f;
   for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
     const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
+    if (st >= plan_cta_nst(p.N, p.S, p.rays_per_cta, cta)) continue;          // never read (neither CTA of the pair has rows there)
     const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
+    const int lr0 = st * 256 + X * 128;
     const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
-    const int lr = st * 256 + X * 128 + r;
-    float dr = 0.f, dg = 0.f, db = 0.f;
-    uint2 mk = make_uint2(0xffffffffu, 0xffffffffu);
-    if (lr < nrows) {
-      const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr];
-      dr = d.x * scale; dg = d.y * scale; db = d.z * scale;
-      mk = *reinterpret_cast<const uint2*>(p.mask + (size_t)t * p.rec_mask + (uint32_t)p.D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u);
-    }
+    const int nv = (nrows - lr0 < 128) ? nrows - lr0 : 128;                   // (<= 0: the partner's rows only -> a tile of zeros)
+    const uint8_t* hv = p.act + (size_t)t * p.rec_act + rec_act_hv(p.D);
+    const uint8_t* mrec = p.mask + (size_t)t * p.rec_mask + (uint32_t)p.D * 4096u + (uint32_t)ch * 1024u + (uint32_t)wsel * 4u;
     uint8_t* const g = p.grad + (size_t)t * p.rec_grad;
-#pragma unroll 2
-    for (int c8 = 0; c8 < 8; ++c8) {
-      const int col = ch * 64 + c8 * 8;
-      const uint32_t word = (c8 < 4) ? mk.x : mk.y;
-      float v[8];
+#pragma unroll 8
+    for (int r = warp; r < 128; r += 8) {                 // 8 independent row loads in flight per warp (load-latency bound)
+      uint2 out = make_uint2(0u, 0u);
+      if (r < nv) {
+        const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + r];
+        const uint2 w = *reinterpret_cast<const uint2*>(hv + img_off(r, c));
+        const uint32_t m = *reinterpret_cast<const uint32_t*>(mrec + (uint32_t)r * 8u);
+        const __half2 h01 = *reinterpret_cast<const __half2*>(&w.x), h23 = *reinterpret_cast<const __half2*>(&w.y);
+        const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
+        float x[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x = fmaf(dr, s_w[col + i], fmaf(dg, s_w[128 + col + i], db * s_w[256 + col + i]));
-        v[i] = mask_apply(word, (c8 & 3) * 8 + i, x);
+        for (int i = 0; i < 4; ++i) {
+          a[i] = fmaf(d.x, h[i], a[i]); a[4 + i] = fmaf(d.y, h[i], a[4 + i]); a[8 + i] = fmaf(d.z, h[i], a[8 + i]);
+          x[i] = mask_apply(m, bit0 + i, fmaf(d.x, wr[i], fmaf(d.y, wg[i], d.z * wb[i])));
+        }
+        b0 += d.x; b1 += d.y; b2 += d.z;
+        out = make_uint2(ptx::cvt_sat_f16x2(x[0], x[1]), ptx::cvt_sat_f16x2(x[2], x[3]));
       }
-      *reinterpret_cast<uint4*>(g + img_off(r, col)) =
-          make_uint4(ptx::cvt_sat_f16x2(v[0], v[1]), ptx::cvt_sat_f16x2(v[2], v[3]), ptx::cvt_sat_f16x2(v[4], v[5]), ptx::cvt_sat_f16x2(v[6], v[7]));
+      *reinterpret_cast<uint2*>(g + img_off(r, c)) = out;
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) s_acc[warp][i * 32 + lane] = a[i];
+  if (lane == 0) { s_acc[warp][384] = b0; s_acc[warp][385] = b1; s_acc[warp][386] = b2; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 387; i += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_acc[w][i];
+    if (i < 384) {                                      // i = (j * 4 + k) * 32 + lane  ->  weight[j][lane * 4 + k]
+      const int j = i / 128, k = (i / 32) & 3, ln = i & 31;
+      atomicAdd(p.g_rgb_w + j * 128 + ln * 4 + k, v);
+    } else atomicAdd(p.g_rgb_b + (i - 384), v);
   }
 }
 
@@ -123,6 +150,7 @@ struct DgradParams {
   uint32_t rec_mask, rec_grad;
   unsigned long long pair_half_bytes;       // bytes of one rank's half of the backward chunk stream
   int dbg;                                  // NERF_B200_DBG_EMIT experiments (1: no record copies, 2: L2 evict_first hint)
+  unsigned long long* prof;                 // NERF_B200_DBG_DGRAD_PROF: per epilogue warp {total, waiting for d_full, waiting at the copy gates} cycles
   int vc0, vc1;                             // forward CTAs [vc0, vc1) (both even): this launch's CTA b serves vc0 + b, vc0 + b + gridDim, ...
 };
 
@@ -309,9 +337,13 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     // as in the forward's training mode (fused_tc2.cuh)
     const uint32_t slice = (uint32_t)q * 4096u;
     const uint64_t l2_first = ptx::l2_policy_evict_first();
+    long long pf_gate = 0, pf_dfull = 0;
+    const long long pf_t0 = p.prof ? clock64() : 0;
     auto emit_gate = [&]() {
+      const long long c0 = p.prof ? clock64() : 0;
       if (lane == 0) ptx::bulk_wait_read1();
       __syncwarp();
+      if (p.prof) pf_gate += clock64() - c0;
     };
     auto emit_slice = [&](uint8_t* dst_kblock, uint32_t src_kblock) {
       ptx::fence_proxy_async_smem();
@@ -336,7 +368,9 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
         // ReLU mask of this step's output (the pre-activation of pts layer D - j), fetched before the wait
         uint4 mk = make_uint4(0u, 0u, 0u, 0u);
         if (j >= 1) mk = *reinterpret_cast<const uint4*>(mrec + (uint32_t)(D - j) * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u);
-        ptx::mbar_wait(bar_dfull + 8 * X, dph);
+        { const long long c0 = p.prof ? clock64() : 0;
+          ptx::mbar_wait(bar_dfull + 8 * X, dph);
+          if (p.prof) pf_dfull += clock64() - c0; }
         dph ^= 1;
         ptx::tc_fence_after();
         const int colw = ch * 128;
@@ -381,6 +415,10 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     }
     }
     if (lane == 0) ptx::bulk_wait_all();
+    if (p.prof && lane == 0) {
+      unsigned long long* o = p.prof + ((size_t)blockIdx.x * 16 + (warp - 4)) * 3;
+      o[0] = (unsigned long long)(clock64() - pf_t0); o[1] = (unsigned long long)pf_dfull; o[2] = (unsigned long long)pf_gate;
+    }
   }
 
   ptx::tc_fence_before();
@@ -682,59 +720,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// rgb_linear gradients on CUDA cores (3 x 128 outputs: too small for the tensor pipe), tile by tile:
-//   rgb_linear.weight[j][c] += sum_rows d_rgb[row][j] hv[row][c],   rgb_linear.bias[j] += sum_rows d_rgb[row][j]
-// One warp per row (a 256-byte hv row = 32 lanes x 4 columns), 8 rows in flight per block; the other small heads
-// (alpha_linear, the view columns of views_linears[0]) ride along in the wgrad kernel, whose tiles already hold their operands.
+// the view columns of views_linears[0] (alpha_linear and the per-ray sums of d_hv ride along in the wgrad kernel, whose tiles
+// already hold their operands; rgb_linear's gradient comes from dhv_seed_heads_kernel)
 // ---------------------------------------------------------------------------------------------------------------
-struct HeadGradParams {
-  const uint8_t* act; const float* d_raw;
-  long long N; int S, rays_per_cta, nst_plan, D; uint32_t rec_act; long long n_tiles;
-  float* rgb_w; float* rgb_b;
-};
-
-__global__ void __launch_bounds__(256, 4) head_grads_kernel(const HeadGradParams p) {
-  __shared__ float s_acc[8][12 * 32 + 3];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = lane * 4;
-  float a[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) a[i] = 0.f;
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-  for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-    const int cta = (int)(t / (2 * p.nst_plan)), st = (int)((t >> 1) % p.nst_plan), X = (int)(t & 1);
-    const int nrows = plan_cta_rows(p.N, p.S, p.rays_per_cta, cta);
-    const int lr0 = st * 256 + X * 128;
-    if (lr0 >= nrows) continue;
-    const long long row_begin = (long long)cta * p.rays_per_cta * p.S;
-    const int nv = (nrows - lr0 < 128) ? nrows - lr0 : 128;
-    const uint8_t* hv = p.act + (size_t)t * p.rec_act + rec_act_hv(p.D);
-#pragma unroll 8
-    for (int r = warp; r < nv; r += 8) {                  // 8 independent 256-byte row loads in flight per warp (the kernel is load-latency bound)
-      const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + r];
-      const uint2 w = *reinterpret_cast<const uint2*>(hv + img_off(r, c));
-      const __half2 h01 = *reinterpret_cast<const __half2*>(&w.x), h23 = *reinterpret_cast<const __half2*>(&w.y);
-      const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = fmaf(d.x, h[i], a[i]); a[4 + i] = fmaf(d.y, h[i], a[4 + i]); a[8 + i] = fmaf(d.z, h[i], a[8 + i]); }
-      b0 += d.x; b1 += d.y; b2 += d.z;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 12; ++i) s_acc[warp][i * 32 + lane] = a[i];
-  if (lane == 0) { s_acc[warp][384] = b0; s_acc[warp][385] = b1; s_acc[warp][386] = b2; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 387; i += 256) {
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) v += s_acc[w][i];
-    if (i < 384) {                                      // i = (j * 4 + k) * 32 + lane  ->  weight[j][lane * 4 + k]
-      const int j = i / 128, k = (i / 32) & 3, ln = i & 31;
-      atomicAdd(p.rgb_w + j * 128 + ln * 4 + k, v);
-    } else atomicAdd(p.rgb_b + (i - 384), v);
-  }
-}
-
 // views_linears[0].weight[c][W + e] += sum_rays dsum[ray][c] * gamma(viewdir_ray)[e]      (run_nerf_helpers.py:108-110);
 // block e == ICV: dbv[c] += sum_rays dsum[ray][c]  (this pass's bias gradient of views_linears[0], for the kernel below)
 __global__ void __launch_bounds__(128) views_enc_wgrad_kernel(const float* __restrict__ dsum, const float* __restrict__ encv, long long N, int ICV,

@@ -850,11 +850,12 @@ struct BwdTcPass {
     NB_LAUNCH_OK("absmax_kernel");
     NB_TRY(nerf_b200_raw2outputs_bwd(raw, z, rays + 3, cfg->ray_stride, noise, N, S, cfg->white_bkgd, g_rgb, d_raw, (void*)st));
     SeedParams sp;
-    sp.d_raw = d_raw; sp.mask = mask; sp.grad = grec; sp.rgb_w = net->rgb_w; sp.amax = amax;
+    sp.d_raw = d_raw; sp.mask = mask; sp.act = act; sp.grad = grec; sp.rgb_w = net->rgb_w; sp.amax = amax;
     sp.N = N; sp.S = S; sp.rays_per_cta = plan.rays_per_cta; sp.nst_plan = plan.nst; sp.D = D;
-    sp.rec_mask = rec_mask_bytes(D); sp.rec_grad = rec_grad_bytes(D); sp.n_tiles = plan.n_tiles;
-    dhv_seed_kernel<<<(int)(plan.n_tiles < 8 * sms ? plan.n_tiles : 8 * sms), 256, 0, st>>>(sp);
-    NB_LAUNCH_OK("dhv_seed_kernel");
+    sp.rec_mask = rec_mask_bytes(D); sp.rec_act = rec_act_bytes(D); sp.rec_grad = rec_grad_bytes(D); sp.n_tiles = plan.n_tiles;
+    sp.g_rgb_w = grads->rgb_w; sp.g_rgb_b = grads->rgb_b;
+    dhv_seed_heads_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(sp);
+    NB_LAUNCH_OK("dhv_seed_heads_kernel");
     return 0;
   }
 
@@ -883,9 +884,25 @@ struct BwdTcPass {
       tl->kind = 1;
       cudaEventRecord(tl->a, st);
     }
+    static const char* prof_path = getenv("NERF_B200_DBG_DGRAD_PROF");     // experiments: where the epilogue warps wait
+    static unsigned long long* prof_dev = nullptr;
+    dp.prof = nullptr;
+    if (prof_path) { if (!prof_dev) NB_CUDA(cudaMalloc(&prof_dev, 512 * 16 * 3 * 8)); dp.prof = prof_dev; }
     dgrad_tc2_kernel<<<grid, TC_THREADS, SM_ALLOC, st>>>(dp, wmap, gmap);
     if (tl) cudaEventRecord(tl->b, st);
     NB_LAUNCH_OK("dgrad_tc2_kernel");
+    if (prof_path) {
+      static unsigned long long h[512 * 16 * 3];
+      NB_CUDA(cudaStreamSynchronize(st));
+      NB_CUDA(cudaMemcpy(h, prof_dev, (size_t)grid * 16 * 3 * 8, cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(prof_path, "a")) {
+        double tot = 0, df = 0, gt = 0;
+        for (int i = 0; i < grid * 16; ++i) { tot += (double)h[3 * i]; df += (double)h[3 * i + 1]; gt += (double)h[3 * i + 2]; }
+        fprintf(f, "dgrad S=%d grid=%d: epilogue warps, mean cycles: total %.0f, waiting for d_full %.0f (%.1f %%), at the copy gates %.0f (%.1f %%)\n", S, grid,
+                tot / (grid * 16), df / (grid * 16), 100.0 * df / tot, gt / (grid * 16), 100.0 * gt / tot);
+        fclose(f);
+      }
+    }
     return 0;
   }
 
@@ -949,18 +966,11 @@ struct BwdTcPass {
     return 0;
   }
 
-  // 5. the small heads: rgb_linear, the view columns of views_linears[0] (after ALL of the pass's weight-gradient launches)
+  // 5. the view columns of views_linears[0] (after ALL of the pass's weight-gradient launches)
   int heads(cudaStream_t st) {
     const int sms = ds->sms, D = net->D, ICV = net->input_ch_views;
     encv_kernel<<<cdiv(N * ICV, 256), 256, 0, st>>>(rays + 8, cfg->ray_stride, N, ICV, encv);
     NB_LAUNCH_OK("encv_kernel");
-    HeadGradParams hp;
-    hp.act = act; hp.d_raw = d_raw;
-    hp.N = N; hp.S = S; hp.rays_per_cta = plan.rays_per_cta; hp.nst_plan = plan.nst; hp.D = D;
-    hp.rec_act = rec_act_bytes(D); hp.n_tiles = plan.n_tiles;
-    hp.rgb_w = grads->rgb_w; hp.rgb_b = grads->rgb_b;
-    head_grads_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(hp);
-    NB_LAUNCH_OK("head_grads_kernel");
     dim3 vg(ICV + 1, cdiv(N, 64));
     views_enc_wgrad_kernel<<<vg, 128, 0, st>>>(dsum, encv, N, ICV, grads->views_w, net->W + ICV, net->W, dbv);
     NB_LAUNCH_OK("views_enc_wgrad_kernel");
