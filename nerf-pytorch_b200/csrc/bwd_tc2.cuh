@@ -338,18 +338,18 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     const uint32_t slice = (uint32_t)q * 4096u;
     const uint64_t l2_first = ptx::l2_policy_evict_first();
     long long pf_gate = 0, pf_dfull = 0;
-    const long long pf_t0 = p.prof ? clock64() : 0;
+    const long long pf_t0 = (kExp && p.prof) ? clock64() : 0;
     auto emit_gate = [&]() {
-      const long long c0 = p.prof ? clock64() : 0;
+      const long long c0 = (kExp && p.prof) ? clock64() : 0;
       if (lane == 0) ptx::bulk_wait_read1();
       __syncwarp();
-      if (p.prof) pf_gate += clock64() - c0;
+      if (kExp && p.prof) pf_gate += clock64() - c0;
     };
     auto emit_slice = [&](uint8_t* dst_kblock, uint32_t src_kblock) {
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (!(p.dbg & 1)) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
+        if (!(kExp && (p.dbg & 1))) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
         ptx::bulk_commit();
       }
     };
@@ -368,9 +368,9 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
         // ReLU mask of this step's output (the pre-activation of pts layer D - j), fetched before the wait
         uint4 mk = make_uint4(0u, 0u, 0u, 0u);
         if (j >= 1) mk = *reinterpret_cast<const uint4*>(mrec + (uint32_t)(D - j) * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u);
-        { const long long c0 = p.prof ? clock64() : 0;
+        { const long long c0 = (kExp && p.prof) ? clock64() : 0;
           ptx::mbar_wait(bar_dfull + 8 * X, dph);
-          if (p.prof) pf_dfull += clock64() - c0; }
+          if (kExp && p.prof) pf_dfull += clock64() - c0; }
         dph ^= 1;
         ptx::tc_fence_after();
         const int colw = ch * 128;
@@ -415,7 +415,7 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     }
     }
     if (lane == 0) ptx::bulk_wait_all();
-    if (p.prof && lane == 0) {
+    if (kExp && p.prof && lane == 0) {
       unsigned long long* o = p.prof + ((size_t)blockIdx.x * 16 + (warp - 4)) * 3;
       o[0] = (unsigned long long)(clock64() - pf_t0); o[1] = (unsigned long long)pf_dfull; o[2] = (unsigned long long)pf_gate;
     }
@@ -470,7 +470,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1) wgra
   if ((sb & 1023u) != 0) __trap();
   int ji = -1;
   for (int i = 0; i < p.njobs; ++i) if ((int)blockIdx.x >= p.jobs[i].cta0 && (int)blockIdx.x < p.jobs[i].cta0 + p.jobs[i].ncta) ji = i;
-  if (p.prof && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[2 * blockIdx.x] = t_; }
+  if (kExp && p.prof && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[2 * blockIdx.x] = t_; }
   if (ji < 0) return;                                   // (uniform per CTA, before any barrier / allocation)
   const WgradJob job = p.jobs[ji];
   const int g = (int)blockIdx.x - job.cta0, G = job.ncta;
@@ -504,7 +504,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1) wgra
           ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(xkb + ykb) * 8192u);
           const uint8_t* xs = p.grad + (size_t)t * p.rec_grad + job.a_off + h * 8192;
           const uint8_t* ys = p.act + (size_t)t * p.rec_act + job.b_off + h * 8192;
-          if (p.dbg & 2) {
+          if (kExp && (p.dbg & 2)) {
             const uint64_t pol = ptx::l2_policy_evict_first();
             for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s_hint(sb + s * stride + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s, pol);
             for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s_hint(sb + s * stride + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s, pol);
@@ -524,7 +524,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1) wgra
     for (long long i = 0; i < my_halves; ++i) {
       ptx::mbar_wait(bar_full + 8 * s, ph);
       ptx::tc_fence_after();
-      if (p.dbg & 1) {
+      if (kExp && (p.dbg & 1)) {
         if (ptx::elect_one()) { ptx::mbar_arrive(bar_empty + 8 * s); if (i == my_halves - 1) ptx::mbar_arrive(bar_done); }
       } else if (ptx::elect_one()) {
         const uint32_t xb = sb + s * stride, yb = xb + ybase;
@@ -699,7 +699,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1) wgra
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
-  if (p.prof && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[2 * blockIdx.x + 1] = t_; }
+  if (kExp && p.prof && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[2 * blockIdx.x + 1] = t_; }
 }
 
 // dst[o][i] += inv_scale * sum_g partial[g][o][i]   (i < n_valid; dst row stride ldw)

@@ -55,7 +55,8 @@ static int smem_optin(const void* fn, size_t bytes) {
 
 // per-device facts (SM count; which kernels already have their > 48 KB shared-memory opt-in): the library may be used
 // on several devices of one process, and cudaFuncSetAttribute is per device
-static int dbg_emit() { static int v = -1; if (v < 0) { const char* e = getenv("NERF_B200_DBG_EMIT"); v = e ? atoi(e) : 0; } return v; }
+static const char* exp_env(const char* name) { return kExp ? getenv(name) : nullptr; }      // experiment switches: product build ignores them
+static int dbg_emit() { static int v = -1; if (v < 0) { const char* e = exp_env("NERF_B200_DBG_EMIT"); v = e ? atoi(e) : 0; } return v; }
 struct DeviceState { int sms; bool optin_fwd, optin_bwd; cudaStream_t side; cudaEvent_t ev[10]; };
 static DeviceState* device_state() {
   static DeviceState st[64];
@@ -802,8 +803,6 @@ int nerf_b200_march_bwd_tc_layout(int64_t N, int S, const NerfNetParams* net, in
 }
 
 namespace {
-constexpr int BWD_OVERLAP_SMS = 0, BWD_OVERLAP_CHUNKS = 1;     // defaults of NERF_B200_BWD_OVERLAP: off -- measured slower than one pass after the other
-                                                               // in every split (profiles/r02_bwd_overlap_sweep.jsonl)
 // One pass of the tensor-core backward, split into its phases so that the two passes of render_rays can interleave: the data-
 // gradient chain is bound by HBM WRITES (3.9 TB/s ceiling), the weight gradient by HBM READS; side by side on disjoint SMs they
 // share a bus that carries 6.6 TB/s of mixed traffic (profiles/r02_hbm_probe.json).
@@ -884,7 +883,7 @@ struct BwdTcPass {
       tl->kind = 1;
       cudaEventRecord(tl->a, st);
     }
-    static const char* prof_path = getenv("NERF_B200_DBG_DGRAD_PROF");     // experiments: where the epilogue warps wait
+    static const char* prof_path = exp_env("NERF_B200_DBG_DGRAD_PROF");     // experiments: where the epilogue warps wait
     static unsigned long long* prof_dev = nullptr;
     dp.prof = nullptr;
     if (prof_path) { if (!prof_dev) NB_CUDA(cudaMalloc(&prof_dev, 512 * 16 * 3 * 8)); dp.prof = prof_dev; }
@@ -913,7 +912,7 @@ struct BwdTcPass {
     BwdTcJobs J = make_bwd_jobs(*net, grads, ctas & ~1);           // whole CTA pairs: the kernel launches as 2-CTA clusters
     J.w[0].aux = 1; J.w[0].aux_dst = dsum;            // views job: per-ray row sums of d_hv
     J.w[1].aux = 2; J.w[1].aux_dst = grads->alpha_w; J.w[1].aux_b = grads->alpha_b;   // feature job: alpha_linear gradients
-    { static int noaux = -1; if (noaux < 0) { const char* e = getenv("NERF_B200_DBG_NOAUX"); noaux = e ? atoi(e) : 0; }
+    { static int noaux = -1; if (noaux < 0) { const char* e = exp_env("NERF_B200_DBG_NOAUX"); noaux = e ? atoi(e) : 0; }
       if (noaux & 1) J.w[0].aux = 0;
       if (noaux & 2) J.w[1].aux = 0;
       if (noaux & 4) for (int i = 0; i < J.n; ++i) J.w[i].db = nullptr; }
@@ -923,7 +922,7 @@ struct BwdTcPass {
     wp.N = N; wp.S = S; wp.rays_per_cta = plan.rays_per_cta; wp.nst_plan = plan.nst; wp.n_tiles = plan.n_tiles;
     wp.t0 = (long long)vc0 * plan.nst * 2; wp.t1 = (long long)vc1 * plan.nst * 2;
     wp.amax = amax; wp.partial = partial; wp.d_raw = d_raw; wp.njobs = J.n;
-    { static int wd = -1; if (wd < 0) { const char* e = getenv("NERF_B200_DBG_WGRAD"); wd = e ? atoi(e) : 0; } wp.dbg = wd; }
+    { static int wd = -1; if (wd < 0) { const char* e = exp_env("NERF_B200_DBG_WGRAD"); wd = e ? atoi(e) : 0; } wp.dbg = wd; }
     for (int i = 0; i < J.n; ++i) wp.jobs[i] = J.w[i];
     TimedLaunch* tl = nullptr;
     if (g_timing && g_ntimed < 4096) {
@@ -933,7 +932,7 @@ struct BwdTcPass {
       tl->kind = 2;
       cudaEventRecord(tl->a, st);
     }
-    static const char* prof_path = getenv("NERF_B200_DBG_WGRAD_PROF");     // experiments: per-CTA start / end times appended to a file
+    static const char* prof_path = exp_env("NERF_B200_DBG_WGRAD_PROF");     // experiments: per-CTA start / end times appended to a file
     static unsigned long long* prof_dev = nullptr;
     if (prof_path) { if (!prof_dev) NB_CUDA(cudaMalloc(&prof_dev, 1024 * 16)); wp.prof = prof_dev; }
     wgrad_tc_kernel<<<J.total_ctas, WG2_THREADS, WG2_TOTAL, st>>>(wp);
@@ -1025,11 +1024,13 @@ size_t nerf_b200_render_rays_bwd_tc_workspace_bytes(int64_t N, int S_coarse, con
 }
 
 // Backward of both passes of render_rays (run_nerf.py:765-772: loss = img2mse(rgb) + img2mse(rgb0); z_samples is detached, :394,
-// so the passes are independent).  Schedule on two streams (graph-capturable: the side stream forks from and joins `stream`):
-//   main: prologue(c) prologue(f) dgrad(c) | dgrad(f, chunk 1) | dgrad(f, chunk 2) ... |         wgrad(f, last chunk) heads(f)
-//   side:                                  | wgrad(c) heads(c) | wgrad(f, chunk 1)     ... | join
-// between the bars the chain (HBM writes) runs on `sms - w` SMs next to a weight gradient (HBM reads) on `w` SMs.
-// NERF_B200_BWD_OVERLAP = "w[,chunks]" overrides the split (0 = one pass after the other on one stream).
+// so the passes are independent).  Two streams (graph-capturable: the side stream forks from and joins `stream`).  Default schedule:
+//   main: prologue(c) dgrad(c) | wgrad(c)      | dgrad(f) | wgrad(f) heads(f) |
+//   side:                      | prologue(f)   |          | heads(c)          | join
+// the small memory-bound kernels of one pass (compositing adjoint, seed tiles + rgb_linear, view-column gradients) run on the SM
+// resources the weight-gradient kernel leaves free (it holds one 192-thread CTA per SM) instead of between the big kernels.
+// NERF_B200_BWD_OVERLAP = "0": one stream, one pass after the other;  "w[,chunks]" (w >= 16): split the SMs -- the fine pass's chain
+// on sms - w of them next to a weight gradient on w (measured slower in every split: profiles/r02_bwd_overlap_sweep.jsonl).
 int nerf_b200_render_rays_bwd_tc(const float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfBwdPass* coarse, const NerfBwdPass* fine,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_bwd_pass(rays, coarse, cfg)) return rc;
@@ -1042,11 +1043,11 @@ int nerf_b200_render_rays_bwd_tc(const float* rays, int64_t N, const NerfRenderC
   NB_TRY(c.init(workspace, cb));
   DeviceState* ds = c.ds;
   const int sms = ds->sms;
-  static int env_w = -2, env_chunks = 0;
+  static int env_w = -2, env_chunks = 1;                // -1: default schedule
   if (env_w == -2) {
     const char* e = getenv("NERF_B200_BWD_OVERLAP");
     env_w = -1;
-    if (e) { int a = -1, k = 0; const int n = sscanf(e, "%d,%d", &a, &k); if (n >= 1) env_w = a; if (n >= 2) env_chunks = k; }
+    if (e) { int a = -1, k = 1; const int n = sscanf(e, "%d,%d", &a, &k); if (n >= 1) env_w = a; if (n >= 2 && k > 0) env_chunks = k; }
   }
   if (!fine) {
     NB_TRY(c.prologue(st)); NB_TRY(c.dgrad(st, c.plan.grid, 0, c.plan.grid)); NB_TRY(c.wgrad(st, sms, 0, c.plan.grid)); NB_TRY(c.heads(st));
@@ -1054,14 +1055,13 @@ int nerf_b200_render_rays_bwd_tc(const float* rays, int64_t N, const NerfRenderC
   }
   BwdTcPass f = bind_pass(rays, N, cfg, fine);
   NB_TRY(f.init(static_cast<uint8_t*>(workspace) + cb, workspace_bytes - cb));
-  int w = (env_w >= 0) ? env_w : BWD_OVERLAP_SMS;
-  int chunks = (env_chunks > 0) ? env_chunks : BWD_OVERLAP_CHUNKS;
   const bool shared_grads = (coarse->grads->pts_w[0] == fine->grads->pts_w[0]);       // one network serving both passes: += races
+  int w = env_w;
   if (w > sms - 16) w = sms - 16;
-  w &= ~1;
-  if (w < 16 || shared_grads || f.plan.grid < 4) {
+  if (w > 0) w &= ~1;
+  if (w == 0 || (w > 0 && w < 16) || shared_grads || f.plan.grid < 4) {
     static int dc = -1, wc = -1;                       // NERF_B200_DBG_BWD_CTAS="d,w": CTA caps of the two kernels (scaling experiments)
-    if (dc < 0) { dc = 1 << 20; wc = sms; const char* e = getenv("NERF_B200_DBG_BWD_CTAS"); if (e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 2 && b >= 16 && b <= sms) { dc = a; wc = b; } } }
+    if (dc < 0) { dc = 1 << 20; wc = sms; const char* e = exp_env("NERF_B200_DBG_BWD_CTAS"); if (e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 2 && b >= 16 && b <= sms) { dc = a; wc = b; } } }
     NB_TRY(c.prologue(st)); NB_TRY(c.dgrad(st, dc, 0, c.plan.grid)); NB_TRY(c.wgrad(st, wc, 0, c.plan.grid)); NB_TRY(c.heads(st));
     NB_TRY(f.prologue(st)); NB_TRY(f.dgrad(st, dc, 0, f.plan.grid)); NB_TRY(f.wgrad(st, wc, 0, f.plan.grid)); NB_TRY(f.heads(st));
     return 0;
@@ -1071,6 +1071,28 @@ int nerf_b200_render_rays_bwd_tc(const float* rays, int64_t N, const NerfRenderC
     for (int i = 0; i < 10; ++i) NB_CUDA(cudaEventCreateWithFlags(&ds->ev[i], cudaEventDisableTiming));
   }
   cudaStream_t sd = ds->side;
+  if (w < 0) {
+    // ---- default: the small kernels ride next to the weight-gradient kernels ----
+    NB_TRY(c.prologue(st));
+    NB_TRY(c.dgrad(st, c.plan.grid, 0, c.plan.grid));
+    NB_CUDA(cudaEventRecord(ds->ev[0], st));
+    NB_CUDA(cudaStreamWaitEvent(sd, ds->ev[0], 0));
+    NB_TRY(f.prologue(sd));
+    NB_CUDA(cudaEventRecord(ds->ev[1], sd));
+    NB_TRY(c.wgrad(st, sms, 0, c.plan.grid));
+    NB_CUDA(cudaStreamWaitEvent(st, ds->ev[1], 0));
+    NB_TRY(f.dgrad(st, f.plan.grid, 0, f.plan.grid));
+    NB_CUDA(cudaEventRecord(ds->ev[2], st));
+    NB_CUDA(cudaStreamWaitEvent(sd, ds->ev[2], 0));
+    NB_TRY(c.heads(sd));
+    NB_CUDA(cudaEventRecord(ds->ev[3], sd));
+    NB_TRY(f.wgrad(st, sms, 0, f.plan.grid));
+    NB_TRY(f.heads(st));
+    NB_CUDA(cudaStreamWaitEvent(st, ds->ev[3], 0));
+    return 0;
+  }
+  // ---- SM split (experiment) ----
+  int chunks = env_chunks;
   if (chunks > 8) chunks = 8;
   if (chunks > f.plan.grid / 2) chunks = f.plan.grid / 2;
   if (chunks < 1) chunks = 1;

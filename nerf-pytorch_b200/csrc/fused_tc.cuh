@@ -366,40 +366,6 @@ __device__ __forceinline__ void store_act32_pre(const float (&x)[32], const uint
   }
 }
 
-// Training mode: the same 32 columns also go straight from registers to the tile image in global memory (the record the
-// backward reads).  A row's eight 16-byte chunks sit at chunk positions c ^ (r & 7): chunks 2p and 2p + 1 share one aligned
-// 32-byte sector, in swapped order when r is odd, so a thread writes its 32 columns as two full-sector 32-byte stores.
-// gsec[p] = byte offset of the sector holding chunks 2p, 2p + 1 of this thread's row inside a K-block (see img_sector_offsets);
-// `field` = address of the K-block pair of this warp's column half in the record.
-__device__ __forceinline__ void img_sector_offsets(int r, uint32_t (&gsec)[4]) {
-#pragma unroll
-  for (int p = 0; p < 4; ++p) gsec[p] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + (uint32_t)(((2 * p) ^ (r & 6)) << 4);
-}
-template <int COL0>
-__device__ __forceinline__ void store_img32_global(const uint32_t (&h)[16], uint8_t* field, const uint32_t (&gsec)[4], bool odd) {
-  constexpr uint32_t kb = (uint32_t)(COL0 >> 6) * 16384u;
-  constexpr int p0 = ((COL0 & 63) >> 3) >> 1;
-#pragma unroll
-  for (int g2 = 0; g2 < 2; ++g2) {
-    const uint32_t* lo = &h[8 * g2];
-    const uint32_t* hi = &h[8 * g2 + 4];
-    ptx::st_global_v8(field + kb + gsec[p0 + g2], odd ? hi[0] : lo[0], odd ? hi[1] : lo[1], odd ? hi[2] : lo[2], odd ? hi[3] : lo[3],
-                      odd ? lo[0] : hi[0], odd ? lo[1] : hi[1], odd ? lo[2] : hi[2], odd ? lo[3] : hi[3]);
-  }
-}
-// store_act32_pre + the global copy
-template <bool RELU, int COL0>
-__device__ __forceinline__ void store_act32_emit(const float (&x)[32], const uint32_t (&sw)[8], uint8_t* field, const uint32_t (&gsec)[4], bool odd) {
-  constexpr uint32_t kb = (uint32_t)(COL0 >> 6) * 16384u;
-  constexpr int c16_0 = (COL0 & 63) >> 3;
-  uint32_t h[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) h[i] = RELU ? ptx::cvt_relu_f16x2(x[2 * i], x[2 * i + 1]) : ptx::cvt_f16x2(x[2 * i], x[2 * i + 1]);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) ptx::st_shared_v4(sw[c16_0 + g] + kb, h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
-  store_img32_global<COL0>(h, field, gsec, odd);
-}
-
 // segmented (per-ray) inclusive scans over one warp; `s` = lane of the segment start at or before
 // this lane inside the warp, or -1 when the segment began in an earlier warp.
 __device__ __forceinline__ float seg_scan_mul(float v, int lane, int s) {

@@ -297,16 +297,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
     const uint32_t slice = (uint32_t)q * 4096u;
     const uint64_t l2_first = EMIT ? ptx::l2_policy_evict_first() : 0ull;      // records are written once, read once by the backward
     auto emit_gate = [&](bool all) {
-      if (sv.dbg & 8) return;
+      if (kExp && (sv.dbg & 8)) return;
       if (lane == 0) { if (all) ptx::bulk_wait_read0(); else ptx::bulk_wait_read1(); }
       __syncwarp();
     };
     auto emit_slice = [&](uint8_t* dst_kblock, uint32_t src_kblock) {
-      if (sv.dbg & 8) return;
+      if (kExp && (sv.dbg & 8)) return;
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (!(sv.dbg & 1)) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
+        if (!(kExp && (sv.dbg & 1))) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
         ptx::bulk_commit();
       }
     };
@@ -346,7 +346,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
             if (b < 3) ptx::tmem_ld_x32(t_lane + col0 + 32, vn);
             float x[32];
             as_float32(v, x);
-            if (EMIT && l < D && !(sv.dbg & 4)) {
+            if (EMIT && l < D && !(kExp && (sv.dbg & 4))) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) mk[b] = mask_push(mk[b], x[j]);
             }
@@ -401,7 +401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           const long long t_f = (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) ? clock64() : 0;
           arrive_leader(bar_act + 8 * X);
           if (EMIT) {
-            if (l < D && !(sv.dbg & 4)) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+            if (l < D && !(kExp && (sv.dbg & 4))) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
             // second K-block of h_l (feature_linear's output, l == D, is not recorded)
             if (l < D && write_act) emit_slice(arec + rec_act_h(l) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
           }
