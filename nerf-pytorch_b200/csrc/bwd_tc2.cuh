@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256, 4) dhv_seed_heads_kernel(const SeedParams
       uint2 out = make_uint2(0u, 0u);
       if (r < nv) {
         const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + r];
-        const uint2 w = *reinterpret_cast<const uint2*>(hv + img_off(r, c));
+        const uint2 w = *reinterpret_cast<const uint2*>(hv + img_off(r, c, 128));
         const uint32_t m = *reinterpret_cast<const uint32_t*>(mrec + (uint32_t)r * 8u);
         const __half2 h01 = *reinterpret_cast<const __half2*>(&w.x), h23 = *reinterpret_cast<const __half2*>(&w.y);
         const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256, 4) dhv_seed_heads_kernel(const SeedParams
         b0 += d.x; b1 += d.y; b2 += d.z;
         out = make_uint2(ptx::cvt_sat_f16x2(x[0], x[1]), ptx::cvt_sat_f16x2(x[2], x[3]));
       }
-      *reinterpret_cast<uint2*>(g + img_off(r, c)) = out;
+      *reinterpret_cast<uint2*>(g + img_off(r, c, 128)) = out;
     }
   }
 #pragma unroll
@@ -306,7 +306,8 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
     }
   } else if (warp == 3) {
     // =========================== seed loader (both CTAs): d_hv tile of (super-tile, slot) -> SEED ===========
-    // one 32 KB box of the gradient-record tensor map per (st, X); bytes of both CTAs are counted on the leader's barrier
+    // the d_hv image (128 columns: in the record [half][K-block] pieces of 8 KB, in shared memory [K-block][half]) = four
+    // 8 KB boxes of the gradient-record tensor map per (st, X); bytes of both CTAs are counted on the leader's barrier
     const int rec_rows = (int)(p.rec_grad >> 9);
     for (int vc = p.vc0 + (int)blockIdx.x; vc < p.vc1; vc += (int)gridDim.x)
     for (int st = 0, nst = plan_cta_nst(p.N, p.S, p.rays_per_cta, vc); st < nst; ++st) {
@@ -315,7 +316,9 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_arrive_expect_tx(bar_seedfull, 2u * 32768u);
           const long long t = ((long long)vc * p.nst_plan + st) * 2 + X;
-          ptx::tma2_load_2d(sb + DG2_SEED, (const void*)&gmap, 0, (int)(t * rec_rows), bar_seedfull);
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc)                              // pc = half * 2 + kb  (record order)
+            ptx::tma2_load_2d(sb + DG2_SEED + (uint32_t)(pc & 1) * 16384u + (uint32_t)(pc >> 1) * 8192u, (const void*)&gmap, 0, (int)(t * rec_rows) + pc * 16, bar_seedfull);
         }
         __syncwarp();
       }
@@ -345,11 +348,11 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
       __syncwarp();
       if (kExp && p.prof) pf_gate += clock64() - c0;
     };
-    auto emit_slice = [&](uint8_t* dst_kblock, uint32_t src_kblock) {
+    auto emit_slice = [&](uint8_t* dst_img, int kb, uint32_t src_kblock) {
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (!(kExp && (p.dbg & 1))) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
+        if (!(kExp && (p.dbg & 1))) ptx::bulk_s2g_hint(dst_img + img_slice_off(q, kb, 256), src_kblock + slice, 4096u, l2_first);
         ptx::bulk_commit();
       }
     };
@@ -401,7 +404,7 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
           // next step's A operand, in place; batches 0, 1 fill K-block 2 ch, batches 2, 3 K-block 2 ch + 1
           if (b == 0) emit_gate();
           if (b == 2) {
-            emit_slice(grec + rec_grad_step(j) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
+            emit_slice(grec + rec_grad_step(j), 2 * ch, act_base + (uint32_t)(2 * ch) * 16384u);
             emit_gate();
           }
           if (b == 0) store_grad32_pre<0>(x, swk); else if (b == 1) store_grad32_pre<32>(x, swk);
@@ -410,7 +413,7 @@ dgrad_tc2_kernel(const DgradParams p, const __grid_constant__ CUtensorMap wmap, 
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         arrive_leader(bar_act + 8 * X);
-        emit_slice(grec + rec_grad_step(j) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
+        emit_slice(grec + rec_grad_step(j), 2 * ch + 1, act_base + (uint32_t)(2 * ch + 1) * 16384u);
       }
     }
     }
@@ -502,15 +505,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1) wgra
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(xkb + ykb) * 8192u);
-          const uint8_t* xs = p.grad + (size_t)t * p.rec_grad + job.a_off + h * 8192;
-          const uint8_t* ys = p.act + (size_t)t * p.rec_act + job.b_off + h * 8192;
+          // 64-row half tile h of each operand: its K-blocks are adjacent in the record -> one contiguous piece per operand
+          const uint8_t* xs = p.grad + (size_t)t * p.rec_grad + job.a_off + (size_t)h * xkb * 8192;
+          const uint8_t* ys = p.act + (size_t)t * p.rec_act + job.b_off + (size_t)h * ykb * 8192;
           if (kExp && (p.dbg & 2)) {
             const uint64_t pol = ptx::l2_policy_evict_first();
-            for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s_hint(sb + s * stride + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s, pol);
-            for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s_hint(sb + s * stride + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s, pol);
+            ptx::bulk_g2s_hint(sb + s * stride, xs, (uint32_t)xkb * 8192u, bar_full + 8 * s, pol);
+            ptx::bulk_g2s_hint(sb + s * stride + ybase, ys, (uint32_t)ykb * 8192u, bar_full + 8 * s, pol);
           } else {
-          for (int kb = 0; kb < xkb; ++kb) ptx::bulk_g2s(sb + s * stride + kb * 8192, xs + (size_t)kb * 16384, 8192, bar_full + 8 * s);
-          for (int kb = 0; kb < ykb; ++kb) ptx::bulk_g2s(sb + s * stride + ybase + kb * 8192, ys + (size_t)kb * 16384, 8192, bar_full + 8 * s);
+          ptx::bulk_g2s(sb + s * stride, xs, (uint32_t)xkb * 8192u, bar_full + 8 * s);
+          ptx::bulk_g2s(sb + s * stride + ybase, ys, (uint32_t)ykb * 8192u, bar_full + 8 * s);
           }
         }
         __syncwarp();

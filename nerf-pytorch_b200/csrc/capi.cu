@@ -874,7 +874,7 @@ struct BwdTcPass {
     if (grid < 2) grid = 2;
     CUtensorMap wmap, gmap;
     NB_TRY(make_row_map(&wmap, pk + PL.off_bwd_pair, PL.bwd_bytes, 16));
-    NB_TRY(make_row_map(&gmap, grec, (size_t)plan.n_tiles * rec_grad_bytes(D), 64));
+    NB_TRY(make_row_map(&gmap, grec, (size_t)plan.n_tiles * rec_grad_bytes(D), 16));      // 8 KB boxes: the pieces of the d_hv image
     TimedLaunch* tl = nullptr;
     if (g_timing && g_ntimed < 4096) {
       tl = &g_timed[g_ntimed++];

@@ -301,12 +301,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
       if (lane == 0) { if (all) ptx::bulk_wait_read0(); else ptx::bulk_wait_read1(); }
       __syncwarp();
     };
-    auto emit_slice = [&](uint8_t* dst_kblock, uint32_t src_kblock) {
+    // dst_img: the image in the record, kb: its K-block, C: its columns; src_kblock: the K-block in shared memory
+    auto emit_slice = [&](uint8_t* dst_img, int kb, int C, uint32_t src_kblock) {
       if (kExp && (sv.dbg & 8)) return;
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (!(kExp && (sv.dbg & 1))) ptx::bulk_s2g_hint(dst_kblock + slice, src_kblock + slice, 4096u, l2_first);
+        if (!(kExp && (sv.dbg & 1))) ptx::bulk_s2g_hint(dst_img + img_slice_off(q, kb, C), src_kblock + slice, 4096u, l2_first);
         ptx::bulk_commit();
       }
     };
@@ -376,7 +377,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
                 // batches 0, 1 fill K-block 2 ch, batches 2, 3 K-block 2 ch + 1 (the previous layer's copies: one group each, in this order)
                 if (b == 0) emit_gate(false);
                 if (b == 2) {
-                  if (l < D) emit_slice(arec + rec_act_h(l) + (uint32_t)(2 * ch) * 16384u, act_base + (uint32_t)(2 * ch) * 16384u);
+                  if (l < D) emit_slice(arec + rec_act_h(l), 2 * ch, 256, act_base + (uint32_t)(2 * ch) * 16384u);
                   emit_gate(l == D);                            // (l == D: nothing was committed in between -> drain everything)
                 }
               }
@@ -403,7 +404,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           if (EMIT) {
             if (l < D && !(kExp && (sv.dbg & 4))) *reinterpret_cast<uint4*>(mrec + (uint32_t)l * 4096u + (uint32_t)ch * 2048u + (uint32_t)r * 16u) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
             // second K-block of h_l (feature_linear's output, l == D, is not recorded)
-            if (l < D && write_act) emit_slice(arec + rec_act_h(l) + (uint32_t)(2 * ch + 1) * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
+            if (l < D && write_act) emit_slice(arec + rec_act_h(l), 2 * ch + 1, 256, act_base + (uint32_t)(2 * ch + 1) * 16384u);
           }
           if (tr) trp[2] = clock64();
           if (kTrace2 && p.trace && blockIdx.x < 2 && st == 1 && l == 3 && lane == 0) { p.trace[2500 + blockIdx.x * 32 + (warp - 4) * 2] = t_f; p.trace[2501 + blockIdx.x * 32 + (warp - 4) * 2] = clock64(); }
@@ -447,7 +448,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) march
           }
           if (EMIT) {
             *reinterpret_cast<uint2*>(mrec + (uint32_t)D * 4096u + (uint32_t)ch * 1024u + (uint32_t)r * 8u) = make_uint2(mkv[0], mkv[1]);
-            emit_slice(arec + rec_act_hv(D) + (uint32_t)ch * 16384u, act_base + (uint32_t)(2 * ch + 1) * 16384u);
+            emit_slice(arec + rec_act_hv(D), ch, 128, act_base + (uint32_t)(2 * ch + 1) * 16384u);
           }
         }
         if (l == defer_l && st > 0 && ch == 0) composite_st(st - 1);

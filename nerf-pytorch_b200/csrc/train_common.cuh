@@ -2,10 +2,15 @@
 // backward (bwd_tc2.cuh): the tile plan, the per-tile activation / mask / gradient records and the mask bit order.
 //
 // The forward walks each CTA's rows in 128-row tiles (two per 256-row super-tile).  In training mode it leaves, per
-// tile, a record of fp16 "tile images" -- [128 rows x C columns] stored byte-for-byte in the shared-memory operand
-// layout (C/64 K-blocks of 16 KB, SWIZZLE_128B: row r of a K-block at (r>>3)*1024 + (r&7)*128, its 16-byte chunk c
-// at ((c ^ (r&7)) << 4)) -- so that ONE bulk copy makes a tile MMA-ready again, as a K-major A operand (dgrad) or as
-// an MN-major operand (wgrad: dW = dA^T H reduces over the sample rows).
+// tile, a record of fp16 "tile images" -- [128 rows x C columns] in the shared-memory operand layout (K-blocks of 64
+// columns, SWIZZLE_128B: row r of a K-block at (r>>3)*1024 + (r&7)*128, its 16-byte chunk c at ((c ^ (r&7)) << 4)), so
+// that bulk copies make a tile MMA-ready again, as a K-major A operand (dgrad) or as an MN-major operand (wgrad:
+// dW = dA^T H reduces over the sample rows).  In global memory an image is stored as TWO HALF IMAGES of 64 rows:
+//   [half h = r >> 6][K-block kb = col >> 6][64 rows x 128 B = 8 KB]
+// i.e. the 8 KB pieces of a K-block's upper and lower 64 rows are not adjacent (as they are in shared memory), the K-blocks of
+// one 64-row half are: the weight gradient streams 64-row half tiles, and reads each operand as ONE contiguous C/64 x 8 KB
+// piece instead of C/64 pieces 16 KB apart (HBM reads of scattered 8 KB pieces reach 4.1 TB/s, of 32 KB pieces 6.5: measured,
+// profiles/r02_dram_stream_probe.jsonl).  A warp of the forward / dgrad epilogue owns 32 rows = a 4 KB slice of either layout.
 //
 //   activation record (forward -> backward), rec_act_bytes(D):
 //     [0, 16 KB)                       enc    : gamma(p), 64 columns (63 + zero pad)
@@ -68,9 +73,13 @@ __host__ __device__ __forceinline__ uint32_t rec_grad_bytes(int D) { return 3276
 __host__ __device__ __forceinline__ uint32_t rec_grad_step(int j) { return 32768u + (uint32_t)j * 65536u; }         // output of dgrad step j
 __host__ __device__ __forceinline__ uint32_t rec_grad_dA(int l, int D) { return rec_grad_step(D - l); }              // pts layer l
 
-// byte offset of element (row r, column col) inside a tile image
-__host__ __device__ __forceinline__ uint32_t img_off(int r, int col) {
-  return (uint32_t)((col >> 6) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2);
+// byte offset of element (row r, column col) inside a [128 x C] tile image in global memory
+__host__ __device__ __forceinline__ uint32_t img_off(int r, int col, int C) {
+  return (uint32_t)((r >> 6) * (C >> 6) * 8192 + (col >> 6) * 8192 + ((r & 63) >> 3) * 1024 + (r & 7) * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2);
+}
+// byte offset of the 4 KB slice (rows 32 q .. 32 q + 31) of K-block kb inside a [128 x C] tile image in global memory
+__host__ __device__ __forceinline__ uint32_t img_slice_off(int q, int kb, int C) {
+  return (uint32_t)((q >> 1) * (C >> 6) * 8192 + kb * 8192 + (q & 1) * 4096);
 }
 
 // rows of CTA `cta` and the super-tiles its PAIR runs (both CTAs of a pair run the same number)

@@ -9,7 +9,8 @@ def img_index(Ccols):
     """element (fp16) index of (row r, column col) inside a [128 x Ccols] tile image"""
     r = np.arange(128)[:, None]
     col = np.arange(Ccols)[None, :]
-    off = (col >> 6) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2
+    off = ((r >> 6) * (Ccols >> 6) * 8192 + (col >> 6) * 8192 + ((r & 63) >> 3) * 1024 + (r & 7) * 128
+           + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2)                  # csrc/train_common.cuh: img_off
     return off // 2
 
 
