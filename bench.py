@@ -36,6 +36,7 @@ REF = os.path.join(ROOT, "baseline", "_ref")
 
 N_RAYS, N_SAMPLES, N_IMPORTANCE = 4096, 64, 128
 FLOP_PER_RAY_FWD = 303_824_896          # 593 408 MAC x 2 x 256 evaluations
+TRAIN_BYTES_PER_TILE = 1230848 + 1411072          # record bytes written + read per 128-row tile of a train step
 FLOP_PER_RAY_TRAIN = 893_190_144        # forward + wgrad + dgrad (no recompute counted)
 WORKLOAD = "lego 400x400 synthetic rays, N_rand=4096, N_samples=64 + N_importance=128, D=8 W=256 use_viewdirs, forward render_rays"
 WORKLOAD_TRAIN = "lego 400x400 synthetic rays, N_rand=4096, 64+128 samples, D=8 W=256 use_viewdirs: render(retraw) + 2 x img2mse + backward + Adam + lr decay (run_nerf.py:760-784), perturb=1"
@@ -478,7 +479,13 @@ def main():
                  "roofline": {"bound": "tensor", "what": "whole train step: algorithmic 893 190 144 FLOP/ray (fwd + dgrad + wgrad, SURVEY 8d) over the step's device time",
                               "achieved": ach_t, "peak": peak, "unit": "TFLOP/s", "frac": ach_t / peak if peak else None, "peak_source": peak_src,
                               "kernel_ms_per_step": {"forward_passes_training_mode": kinds[0], "dgrad_chains": kinds[1], "wgrad": kinds[2]},
-                              "note": "wgrad streams 2 x 64 KB of fp16 tile images per tile-layer at 64 MAC/B: HBM-bound by design (DESIGN.md 9)"}}
+                              "hbm": {"what": "bytes the step's design moves through HBM (DESIGN.md 9): per 128-row tile 1 230 848 B of records written (activations, "
+                                              "masks, gradients) and 1 411 072 B read back (wgrad 1 310 720, dgrad 65 536, rgb head 34 816)",
+                                      "bytes_per_step": TRAIN_BYTES_PER_TILE * N_RAYS * 256 // 128,
+                                      "achieved_gbs": TRAIN_BYTES_PER_TILE * N_RAYS * 256 // 128 / (ms_t * 1e-3) / 1e9, "peak_gbs": hbm_gbs,
+                                      "frac": (TRAIN_BYTES_PER_TILE * N_RAYS * 256 // 128 / (ms_t * 1e-3) / 1e9 / hbm_gbs) if hbm_gbs else None},
+                              "note": "the step is bound by HBM (record traffic) and shared-memory bandwidth, not by the tensor pipe: wgrad streams 2 x 64 KB of "
+                                      "fp16 tile images per tile-layer at 64 MAC/B (DESIGN.md 9)"}}
         if world > 1:
             # strong scaling: the SAME global 4096-ray batch split over the ranks, one flat all-reduce per step
             n_local = N_RAYS // world
