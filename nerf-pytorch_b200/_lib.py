@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerf_b200.so")
+# NERF_B200_EXPERIMENTS=1 selects the build with the NERF_B200_DBG_* switches compiled in (libnerf_b200_exp.so: same sources,
+# -DNERF_B200_EXPERIMENTS; tools only)
+LIB_PATH = os.path.join(_HERE, "libnerf_b200_exp.so" if os.environ.get("NERF_B200_EXPERIMENTS") == "1" else "libnerf_b200.so")
 MAX_D = 16
 PREC_TC_FP16, PREC_FP32 = 0, 1
 

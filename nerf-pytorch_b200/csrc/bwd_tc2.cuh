@@ -83,7 +83,7 @@ struct SeedParams {
   float* g_rgb_w; float* g_rgb_b;
 };
 
-__global__ void __launch_bounds__(256, 4) dhv_seed_heads_kernel(const SeedParams p) {
+__global__ void __launch_bounds__(256, 3) dhv_seed_heads_kernel(const SeedParams p) {
   __shared__ float s_acc[8][12 * 32 + 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane * 4, ch = lane >> 4, wsel = (lane >> 3) & 1, bit0 = c & 31;
@@ -105,22 +105,37 @@ __global__ void __launch_bounds__(256, 4) dhv_seed_heads_kernel(const SeedParams
     const uint8_t* hv = p.act + (size_t)t * p.rec_act + rec_act_hv(p.D);
     const uint8_t* mrec = p.mask + (size_t)t * p.rec_mask + (uint32_t)p.D * 4096u + (uint32_t)ch * 1024u + (uint32_t)wsel * 4u;
     uint8_t* const g = p.grad + (size_t)t * p.rec_grad;
-#pragma unroll 8
-    for (int r = warp; r < 128; r += 8) {                 // 8 independent row loads in flight per warp (load-latency bound)
+    // warp w takes rows 16 w .. 16 w + 15: their dL/draw rows come in as ONE coalesced load (lane i < 16 holds row i's float4 and
+    // hands it out by shuffle), which leaves the registers for all 16 hv / mask loads to be in flight at once (load-latency bound)
+    const int rbase = warp * 16;
+    float4 dmine = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < 16 && rbase + lane < nv) dmine = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + rbase + lane];
+    uint2 hw[16];
+    uint32_t mw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int r = rbase + k;
+      hw[k] = make_uint2(0u, 0u); mw[k] = 0u;
+      if (r < nv) {
+        hw[k] = *reinterpret_cast<const uint2*>(hv + img_off(r, c, 128));
+        mw[k] = *reinterpret_cast<const uint32_t*>(mrec + (uint32_t)r * 8u);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int r = rbase + k;
+      const float dx = __shfl_sync(0xffffffffu, dmine.x, k), dy = __shfl_sync(0xffffffffu, dmine.y, k), dz = __shfl_sync(0xffffffffu, dmine.z, k);
       uint2 out = make_uint2(0u, 0u);
       if (r < nv) {
-        const float4 d = reinterpret_cast<const float4*>(p.d_raw)[row_begin + lr0 + r];
-        const uint2 w = *reinterpret_cast<const uint2*>(hv + img_off(r, c, 128));
-        const uint32_t m = *reinterpret_cast<const uint32_t*>(mrec + (uint32_t)r * 8u);
-        const __half2 h01 = *reinterpret_cast<const __half2*>(&w.x), h23 = *reinterpret_cast<const __half2*>(&w.y);
+        const __half2 h01 = *reinterpret_cast<const __half2*>(&hw[k].x), h23 = *reinterpret_cast<const __half2*>(&hw[k].y);
         const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
         float x[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          a[i] = fmaf(d.x, h[i], a[i]); a[4 + i] = fmaf(d.y, h[i], a[4 + i]); a[8 + i] = fmaf(d.z, h[i], a[8 + i]);
-          x[i] = mask_apply(m, bit0 + i, fmaf(d.x, wr[i], fmaf(d.y, wg[i], d.z * wb[i])));
+          a[i] = fmaf(dx, h[i], a[i]); a[4 + i] = fmaf(dy, h[i], a[4 + i]); a[8 + i] = fmaf(dz, h[i], a[8 + i]);
+          x[i] = mask_apply(mw[k], bit0 + i, fmaf(dx, wr[i], fmaf(dy, wg[i], dz * wb[i])));
         }
-        b0 += d.x; b1 += d.y; b2 += d.z;
+        b0 += dx; b1 += dy; b2 += dz;
         out = make_uint2(ptx::cvt_sat_f16x2(x[0], x[1]), ptx::cvt_sat_f16x2(x[2], x[3]));
       }
       *reinterpret_cast<uint2*>(g + img_off(r, c, 128)) = out;

@@ -717,7 +717,7 @@ BwdTcJobs make_bwd_jobs(const NerfNetParams& n, const NerfNetGrads* g, int sms) 
     if (sk) add(rec_grad_dA(l, D), 256, 0, 64, g ? g->pts_w[l] : nullptr, W + IC, IC, nullptr);        // the [input_pts] columns
   }
   add(rec_grad_dA(0, D), 256, 0, 64, g ? g->pts_w[0] : nullptr, IC, IC, g ? g->pts_b[0] : nullptr);
-  // CTAs per job ~ its measured cost (profiles/r02_wgrad_job_balance.txt: per-job finish times of a byte-proportional split):
+  // CTAs per job ~ its measured cost (profiles/r02_backward_experiments.txt: per-job finish times of a byte-proportional split):
   // bytes streamed per tile (Mc + Nc columns), x 1.27 for the feature job (its spare warps also sweep B for alpha_linear),
   // x 1.06 for the views job (per-ray atomics), x 1.16 for a 64-wide B with a bias gradient (short stages, same column sums)
   auto cost = [&](int i) {
@@ -853,7 +853,7 @@ struct BwdTcPass {
     sp.N = N; sp.S = S; sp.rays_per_cta = plan.rays_per_cta; sp.nst_plan = plan.nst; sp.D = D;
     sp.rec_mask = rec_mask_bytes(D); sp.rec_act = rec_act_bytes(D); sp.rec_grad = rec_grad_bytes(D); sp.n_tiles = plan.n_tiles;
     sp.g_rgb_w = grads->rgb_w; sp.g_rgb_b = grads->rgb_b;
-    dhv_seed_heads_kernel<<<(int)(plan.n_tiles < 4 * sms ? plan.n_tiles : 4 * sms), 256, 0, st>>>(sp);
+    dhv_seed_heads_kernel<<<(int)(plan.n_tiles < 3 * sms ? plan.n_tiles : 3 * sms), 256, 0, st>>>(sp);
     NB_LAUNCH_OK("dhv_seed_heads_kernel");
     return 0;
   }
