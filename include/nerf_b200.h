@@ -126,6 +126,15 @@ typedef struct NerfCamera {
 int nerf_b200_pack_rays(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam,
                         int64_t N, int64_t pixel0, int ndc, float near, float far, int use_viewdirs,
                         float* out, void* stream);
+/* the arguments of nerf_b200_pack_rays as a struct: nerf_b200_render_fwd builds the batch inside its per-ray prologue launch */
+typedef struct NerfRayGen {
+  const float* rays_o; const float* rays_d;   /* [N,3] each, or both NULL: generate from `cam` for pixels [pixel0, pixel0 + N) */
+  const float* view_src;                      /* [N,3] or NULL */
+  const NerfCamera* cam;                      /* needed to generate rays and for ndc */
+  int64_t pixel0;
+  int32_t ndc, use_viewdirs;
+  float near, far;
+} NerfRayGen;
 /* same, for an arbitrary device list of pixel ids (row-major j * W + i) of the camera's image: the per-image random
  * pixel choice of train() (run_nerf.py:728-757: get_rays for the whole image, meshgrid, np.random.choice, gather)
  * without the [H,W,3] ray tensors */
@@ -164,6 +173,14 @@ int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg*
                               float* z_coarse /*[N,S_c]*/, const NerfPassOut* coarse,
                               float* z_fine, float* z_std, const NerfPassOut* fine,
                               void* workspace, size_t workspace_bytes, void* stream);
+/* render() for one chunk (run_nerf.py:69-134 with N <= chunk): nerf_b200_render_rays_fwd whose prologue launch also BUILDS the ray
+ * batch `rays` [N, 8 | 11] from `gen` (one launch less than pack_rays + render_rays_fwd; the exact path launches pack_rays itself) */
+int nerf_b200_render_fwd(const NerfRayGen* gen, float* rays, int64_t N, const NerfRenderCfg* cfg,
+                         const NerfNetParams* net_coarse, const void* packed_coarse, const NerfNetParams* net_fine,
+                         const void* packed_fine, const float* t_vals, const float* u_det, const float* t_rand,
+                         const float* u_rand, const float* noise0, const float* noise1, float* z_coarse,
+                         const NerfPassOut* coarse, float* z_fine, float* z_std, const NerfPassOut* fine,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- training mode of the fused pass: besides its outputs (out->raw is required) the pass leaves, per 128-row
  *      tile, a record of fp16 activation images (encodings, post-ReLU h_l, feature, view layer) and the sign

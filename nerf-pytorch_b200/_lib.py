@@ -54,6 +54,11 @@ class NerfTrainSave(C.Structure):
     _fields_ = [("act", c_fp), ("act_bytes", C.c_size_t), ("mask", c_fp), ("mask_bytes", C.c_size_t)]
 
 
+class NerfRayGen(C.Structure):
+    _fields_ = [("rays_o", c_fp), ("rays_d", c_fp), ("view_src", c_fp), ("cam", C.POINTER(NerfCamera)), ("pixel0", C.c_int64),
+                ("ndc", C.c_int32), ("use_viewdirs", C.c_int32), ("near", C.c_float), ("far", C.c_float)]
+
+
 class NerfBwdPass(C.Structure):
     _fields_ = [("z_vals", c_fp), ("noise", c_fp), ("S", C.c_int), ("net", C.POINTER(NerfNetParams)), ("packed", c_fp), ("raw", c_fp),
                 ("save", C.POINTER(NerfTrainSave)), ("g_rgb", c_fp), ("grads", C.POINTER(NerfNetGrads))]
@@ -87,6 +92,11 @@ SIGNATURES = {
                                             c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                             c_fp, C.POINTER(NerfPassOut), c_fp, c_fp, C.POINTER(NerfPassOut),
                                             c_fp, C.c_size_t, c_fp]),
+    "nerf_b200_render_fwd": (C.c_int, [C.POINTER(NerfRayGen), c_fp, C.c_int64, C.POINTER(NerfRenderCfg),
+                                       C.POINTER(NerfNetParams), c_fp, C.POINTER(NerfNetParams), c_fp,
+                                       c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                       c_fp, C.POINTER(NerfPassOut), c_fp, c_fp, C.POINTER(NerfPassOut),
+                                       c_fp, C.c_size_t, c_fp]),
     "nerf_b200_march_train": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_int, C.POINTER(NerfNetParams), c_fp,
                                         C.POINTER(NerfRenderCfg), C.POINTER(NerfPassOut), c_fp, C.c_size_t,
                                         C.POINTER(NerfTrainSave), c_fp]),

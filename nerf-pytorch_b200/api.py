@@ -444,6 +444,41 @@ def _train_save(lib, N, S, net_params, dev):
     return sv, act, mask
 
 
+# render() -> batchify_rays -> render_rays -> _RenderRays.forward: when the whole image is ONE chunk, render() does not launch
+# nerf_b200_pack_rays itself but leaves (batch tensor, NerfRayGen + the objects it points to) here; the forward of that very
+# tensor hands the generator to nerf_b200_render_fwd, whose per-ray prologue launch builds the batch (4 launches per step
+# instead of 5).  Anything else that touches the batch first must call _flush_deferred_pack().
+_DEFERRED_PACK = None
+
+
+def _launch_pack(lib, gen, out):
+    g = gen[0]
+    check(lib.nerf_b200_pack_rays(g.rays_o, g.rays_d, g.view_src, g.cam, out.shape[0], g.pixel0, g.ndc, g.near, g.far, g.use_viewdirs,
+                                  _ptr(out), _stream(out)), "pack_rays")
+
+
+def _take_deferred_pack(ray_batch):
+    global _DEFERRED_PACK
+    d = _DEFERRED_PACK
+    if d is None:
+        return None
+    _DEFERRED_PACK = None
+    if d[0].data_ptr() == ray_batch.data_ptr() and d[0].shape == ray_batch.shape:
+        return d[1]
+    with _on(d[0]):                                          # a different tensor reached the forward: build the batch the plain way
+        _launch_pack(_lib.load(), d[1], d[0])
+    return None
+
+
+def _flush_deferred_pack():
+    global _DEFERRED_PACK
+    d = _DEFERRED_PACK
+    if d is not None:
+        _DEFERRED_PACK = None
+        with _on(d[0]):
+            _launch_pack(_lib.load(), d[1], d[0])
+
+
 class _RenderRays(torch.autograd.Function):
     """Forward: nerf_b200_render_rays_fwd (coarse z -> fused pass -> resample -> fused pass); when a parameter needs a
     gradient and the tensor-core backward is selected, the training-mode variant that also leaves the per-tile
@@ -490,7 +525,12 @@ class _RenderRays(torch.autograd.Function):
                   _ptr(z_c), C.byref(out_c), _ptr(z_f), _ptr(z_std), C.byref(out_f) if out_f is not None else None,
                   _ptr(ws), ws_bytes)
         saved_rec = ()
+        # render() may have left the construction of this very batch to the prologue launch (_DEFERRED_PACK): take it over here
+        gen = _take_deferred_pack(ray_batch)
         with _on(ray_batch):
+            if gen is not None and train_tc:                 # the training-mode entry builds nothing: one extra launch now
+                _launch_pack(lib, gen, ray_batch)
+                gen = None
             if train_tc:
                 sv_c, act_c, mask_c = _train_save(lib, N, Sc, pc, dev)
                 saved_rec = (raw_c, act_c, mask_c)
@@ -500,6 +540,8 @@ class _RenderRays(torch.autograd.Function):
                     saved_rec += (raw_f, act_f, mask_f)
                 check(lib.nerf_b200_render_rays_fwd_train(*common, C.byref(sv_c), C.byref(sv_f) if sv_f is not None else None,
                                                           _stream(ray_batch)), "render_rays_fwd_train")
+            elif gen is not None:
+                check(lib.nerf_b200_render_fwd(C.byref(gen[0]), *common, _stream(ray_batch)), "render_fwd")
             else:
                 check(lib.nerf_b200_render_rays_fwd(*common, _stream(ray_batch)), "render_rays_fwd")
         ctx.cfgd, ctx.nets, ctx.train_tc = cfgd, (net_c, net_f), train_tc
@@ -693,7 +735,16 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     nf = (float(near), float(far)) if scalar_bounds else (0., 1.)
     packed = torch.empty((N, 11 if use_viewdirs else 8), device=dev, dtype=torch.float32)
 
+    # one chunk, scalar bounds, one camera: the batch is built by render_rays' own prologue launch (see _DEFERRED_PACK)
+    defer = scalar_bounds and c2w_staticcam is None and N <= chunk and get_precision() == "tc_fp16"
+
     def pack(o, d, view_src, cam, out, ndc_, viewdirs_):
+        global _DEFERRED_PACK
+        if defer and out is packed:
+            _flush_deferred_pack()
+            gen = _lib.NerfRayGen(_ptr(o), _ptr(d), _ptr(view_src), C.pointer(cam), 0, ndc_, int(bool(viewdirs_)), nf[0], nf[1])
+            _DEFERRED_PACK = (packed, (gen, cam, o, d, view_src))
+            return
         check(lib.nerf_b200_pack_rays(_ptr(o), _ptr(d), _ptr(view_src), C.byref(cam), N, 0, ndc_, nf[0], nf[1], int(bool(viewdirs_)),
                                       _ptr(out), _stream(out)), "pack_rays")
 
@@ -718,7 +769,10 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
             else torch.as_tensor(x, dtype=torch.float32, device=dev).reshape(N)
         packed[:, 6] = shape_col(near)
         packed[:, 7] = shape_col(far)
-    all_ret = batchify_rays(packed, chunk, **kwargs)
+    try:
+        all_ret = batchify_rays(packed, chunk, **kwargs)
+    finally:
+        _flush_deferred_pack()                                # (only if the forward never saw the batch: an exception on the way)
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
     k_extract = ["rgb_map", "disp_map", "acc_map"]

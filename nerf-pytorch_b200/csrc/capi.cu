@@ -355,13 +355,10 @@ int nerf_b200_raw2outputs_bwd(const float* raw, const float* z_vals, const float
   return 0;
 }
 
-static int pack_rays_impl(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam, int64_t N,
-                          int64_t pixel0, const int64_t* pixel_index, int ndc, float near, float far, int use_viewdirs, float* out, void* stream) {
-  NB_CHECK_ARG(out != nullptr, "NULL output");
+static int fill_pack_args(PackRaysArgs& a, const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam, int64_t N,
+                          int64_t pixel0, const int64_t* pixel_index, int ndc, float near, float far, int use_viewdirs) {
   NB_CHECK_ARG((rays_o && rays_d) || (cam && !rays_o && !rays_d), "give rays_o and rays_d, or a camera to generate them");
   NB_CHECK_ARG(!ndc || cam, "ndc needs the camera (H, W, focal)");
-  if (N == 0) return 0;
-  PackRaysArgs a;
   memset(&a, 0, sizeof(a));
   a.rays_o = rays_o; a.rays_d = rays_d; a.view_src = view_src; a.N = N; a.pixel0 = pixel0;
   a.pixel_index = reinterpret_cast<const long long*>(pixel_index);
@@ -372,6 +369,15 @@ static int pack_rays_impl(const float* rays_o, const float* rays_d, const float*
     a.ndc_cw = (float)(-1.0 / ((double)cam->W / (2.0 * (double)cam->fx)));      // run_nerf_helpers.py:181 (focal = K[0][0])
     a.ndc_ch = (float)(-1.0 / ((double)cam->H / (2.0 * (double)cam->fx)));
   }
+  return 0;
+}
+
+static int pack_rays_impl(const float* rays_o, const float* rays_d, const float* view_src, const NerfCamera* cam, int64_t N,
+                          int64_t pixel0, const int64_t* pixel_index, int ndc, float near, float far, int use_viewdirs, float* out, void* stream) {
+  NB_CHECK_ARG(out != nullptr, "NULL output");
+  if (N == 0) return 0;
+  PackRaysArgs a;
+  if (int rc = fill_pack_args(a, rays_o, rays_d, view_src, cam, N, pixel0, pixel_index, ndc, near, far, use_viewdirs)) return rc;
   pack_rays_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(a, out);
   NB_LAUNCH_OK("pack_rays_kernel");
   return 0;
@@ -498,9 +504,19 @@ static int render_rays_fwd_impl(const float* rays, int64_t N, const NerfRenderCf
                                 const float* t_vals, const float* u_det, const float* t_rand, const float* u_rand,
                                 const float* noise0, const float* noise1, float* z_coarse, const NerfPassOut* coarse,
                                 float* z_fine, float* z_std, const NerfPassOut* fine, void* workspace,
-                                size_t workspace_bytes, const NerfTrainSave* save_coarse, const NerfTrainSave* save_fine, void* stream) {
+                                size_t workspace_bytes, const NerfTrainSave* save_coarse, const NerfTrainSave* save_fine, void* stream,
+                                const NerfRayGen* gen = nullptr) {
   NB_CHECK_ARG(rays && cfg && net_coarse && t_vals && z_coarse && coarse, "NULL pointer");
   if (N == 0) return 0;
+  // gen: `rays` is still to be built (render()'s batch construction, run_nerf.py:95-123) -- by the prologue kernel below on the
+  // tensor-core path, by pack_rays_kernel otherwise
+  PackRaysArgs pk;
+  bool pack_pending = false;
+  if (gen) {
+    NB_CHECK_ARG(cfg->ray_stride == (gen->use_viewdirs ? 11 : 8), "ray_stride does not match the batch to build");
+    if (int rc = fill_pack_args(pk, gen->rays_o, gen->rays_d, gen->view_src, gen->cam, N, gen->pixel0, nullptr, gen->ndc, gen->near, gen->far, gen->use_viewdirs)) return rc;
+    pack_pending = true;
+  }
   const int Sc = cfg->N_samples, Ni = cfg->N_importance;
   NB_CHECK_ARG(Sc >= 1 && Ni >= 0, "bad sample counts");
   NB_CHECK_ARG(!cfg->perturb || t_rand, "perturb > 0 needs t_rand");
@@ -532,9 +548,14 @@ static int render_rays_fwd_impl(const float* rays, int64_t N, const NerfRenderCf
       }
     }
     a.t_vals = t_vals; a.t_rand = cfg->perturb ? t_rand : nullptr; a.S = Sc; a.lindisp = cfg->lindisp; a.z_out = z_coarse;
+    if (pack_pending) { a.pack = pk; a.pack_out = const_cast<float*>(rays); pack_pending = false; }
     ray_setup_kernel<<<cdiv(N, VB_RAYS), 256, 0, (cudaStream_t)stream>>>(a);
     NB_LAUNCH_OK("ray_setup_kernel");
   } else {
+    if (pack_pending) {
+      pack_rays_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(pk, const_cast<float*>(rays));
+      NB_LAUNCH_OK("pack_rays_kernel");
+    }
     if (int rc = nerf_b200_coarse_z(rays, cfg->ray_stride, t_vals, cfg->perturb ? t_rand : nullptr, N, Sc, cfg->lindisp, z_coarse, stream)) return rc;
   }
   // coarse pass (:381-386)
@@ -557,6 +578,19 @@ int nerf_b200_render_rays_fwd(const float* rays, int64_t N, const NerfRenderCfg*
                               size_t workspace_bytes, void* stream) {
   return render_rays_fwd_impl(rays, N, cfg, net_coarse, packed_coarse, net_fine, packed_fine, t_vals, u_det, t_rand, u_rand, noise0, noise1,
                               z_coarse, coarse, z_fine, z_std, fine, workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+// render() for one chunk: the ray batch is BUILT (get_rays / viewdirs / NDC / near-far / packing, run_nerf.py:95-123) by the same
+// prologue launch that samples z and fills the view-bias tables, into `rays` [N, 8 | 11], then rendered as above
+int nerf_b200_render_fwd(const NerfRayGen* gen, float* rays, int64_t N, const NerfRenderCfg* cfg, const NerfNetParams* net_coarse,
+                         const void* packed_coarse, const NerfNetParams* net_fine, const void* packed_fine,
+                         const float* t_vals, const float* u_det, const float* t_rand, const float* u_rand,
+                         const float* noise0, const float* noise1, float* z_coarse, const NerfPassOut* coarse,
+                         float* z_fine, float* z_std, const NerfPassOut* fine, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  NB_CHECK_ARG(gen != nullptr, "NULL ray generator");
+  return render_rays_fwd_impl(rays, N, cfg, net_coarse, packed_coarse, net_fine, packed_fine, t_vals, u_det, t_rand, u_rand, noise0, noise1,
+                              z_coarse, coarse, z_fine, z_std, fine, workspace, workspace_bytes, nullptr, nullptr, stream, gen);
 }
 
 // the same call in training mode: both passes also leave their per-tile records (activation images + ReLU masks) for

@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "small_kernels.cuh"
 
 namespace nb {
 
@@ -218,6 +219,8 @@ struct RaySetupArgs {
   const float* vdir_a; float* vb_a;               // net A side table (128 x ICV weights + 128 biases) -> vb_a [N,128]
   const float* vdir_b; float* vb_b;               // net B or NULL
   const float* t_vals; const float* t_rand; int S, lindisp; float* z_out;   // z_out NULL: no z sampling
+  float* pack_out;                                // not NULL: the block first BUILDS its rows of `rays` (render()'s ray batch
+  PackRaysArgs pack;                              //           construction, pack_ray_row) -- same buffer as `rays`
 };
 __device__ __forceinline__ float setup_z_at(float near, float far, float t, int lindisp) {
   const float omt = __fsub_rn(1.0f, t);
@@ -230,6 +233,10 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const RaySetupArgs a) {
   const long long n0 = (long long)blockIdx.x * VB_RAYS;
   const int j = threadIdx.x & 127, net = threadIdx.x >> 7;
   const int ICV = a.ICV;
+  if (a.pack_out != nullptr) {                      // run_nerf.py:95-123 for this block's rays, then everyone reads them back
+    if (threadIdx.x < VB_RAYS && n0 + threadIdx.x < a.N) pack_ray_row(a.pack, n0 + threadIdx.x, a.pack_out);
+    __syncthreads();
+  }
   if (a.vb_a != nullptr) {
     for (int i = threadIdx.x; i < VB_RAYS * ICV; i += 256) {
       const int r = i / ICV, c = i - r * ICV;

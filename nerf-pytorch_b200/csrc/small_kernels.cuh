@@ -73,9 +73,8 @@ struct PackRaysArgs {
   float near, far, ndc_cw, ndc_ch;              // ndc_cw = -1/(W/(2 focal)), ndc_ch = -1/(H/(2 focal)) (host double -> float)
 };
 
-__global__ void pack_rays_kernel(PackRaysArgs a, float* __restrict__ out) {
-  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= a.N) return;
+// row n of the batch -> out + n * stride
+__device__ __forceinline__ void pack_ray_row(const PackRaysArgs& a, long long n, float* __restrict__ out) {
   float o[3], d[3];
   if (a.rays_d != nullptr) {
 #pragma unroll
@@ -110,6 +109,10 @@ __global__ void pack_rays_kernel(PackRaysArgs a, float* __restrict__ out) {
     o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
   }
   r[0] = o[0]; r[1] = o[1]; r[2] = o[2]; r[3] = d[0]; r[4] = d[1]; r[5] = d[2]; r[6] = a.near; r[7] = a.far;
+}
+__global__ void pack_rays_kernel(PackRaysArgs a, float* __restrict__ out) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < a.N) pack_ray_row(a, n, out);
 }
 
 // to8b (run_nerf_helpers.py:11: (255 * clip(x, 0, 1)).astype(uint8)) on the device, for render_path-style image output

@@ -154,3 +154,32 @@ def test_graphed_render_matches_render(G):
         g.refresh()
     with pytest.raises(ValueError):
         G.nb.GraphedRender(400, 400, sb["K"], 16, **dict(kw, perturb=1.))
+
+
+@pytest.mark.parametrize("mode", ["rays", "c2w", "c2w_ndc"])
+def test_render_builds_the_batch_in_the_prologue_launch(G, mode):
+    """render() of a single chunk leaves the ray-batch construction (run_nerf.py:95-123) to render_rays' per-ray prologue launch
+    (nerf_b200_render_fwd): 4 library launches per call, and bit-identical maps to the two-chunk call of the same image, which
+    builds the batch with nerf_b200_pack_rays first."""
+    nets = [G.make_net(G.synth.nerf_state(0)), G.make_net(G.synth.nerf_state(1))]
+    kw = dict(use_viewdirs=True, network_fn=nets[0], network_fine=nets[1], network_query_fn=G.query_fn(), N_samples=64, N_importance=128,
+              perturb=0., white_bkgd=True, raw_noise_std=0.)
+    if mode == "rays":
+        sb = G.synth.ray_batch("lego", 600, seed=11)
+        args, kw2, K = (400, 400), dict(rays=G.dev(sb["rays"]), ndc=False, near=2., far=6.), sb["K"]
+    else:
+        H, W, f = 20, 30, 25.0
+        K = np.array([[f, 0, 0.5 * W], [0, f, 0.5 * H], [0, 0, 1]], np.float32)
+        c2w = torch.tensor([[1., 0., 0., 0.1], [0., 0.96, -0.28, 0.2], [0., 0.28, 0.96, 3.5 if mode == "c2w" else 0.4]], device="cuda")
+        args = (H, W)
+        kw2 = dict(c2w=c2w, ndc=(mode == "c2w_ndc"), near=(0. if mode == "c2w_ndc" else 2.), far=(1. if mode == "c2w_ndc" else 6.))
+    with torch.no_grad():
+        G.nb.render(*args, K, chunk=32768, **kw2, **kw)                       # (packs the weights once)
+        l0 = G.nb.launch_count()
+        one = G.nb.render(*args, K, chunk=32768, **kw2, **kw)
+        n_one = G.nb.launch_count() - l0
+        two = G.nb.render(*args, K, chunk=304, **kw2, **kw)
+    assert n_one == 4, n_one
+    for a, b in zip(one[:3], two[:3]):
+        assert torch.equal(a, b)
+    assert torch.equal(one[3]["rgb0"], two[3]["rgb0"]) and torch.equal(one[3]["z_std"], two[3]["z_std"])
