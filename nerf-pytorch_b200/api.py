@@ -653,9 +653,10 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             t_rand = torch.tensor(np.random.rand(N, N_samples), dtype=torch.float32, device=dev)
         else:
             t_rand = torch.rand(N, N_samples, device=dev)
-        if N_importance > 0:
-            u_rand, _ = _draw_u((N, N_importance), False, pytest, dev)           # det = (perturb == 0), :393
+    # draw order of the reference (a seeded run consumes the generator alike): t_rand :371, coarse noise :285, u :208, fine noise :285
     noise0 = _draw_noise((N, N_samples), float(raw_noise_std), pytest, dev)
+    if perturb > 0. and N_importance > 0:
+        u_rand, _ = _draw_u((N, N_importance), False, pytest, dev)               # det = (perturb == 0), :393
     noise1 = _draw_noise((N, N_samples + N_importance), float(raw_noise_std), pytest, dev) if N_importance > 0 else None
     cfgd = dict(N_samples=int(N_samples), N_importance=int(N_importance), multires=int(mr), multires_views=int(mrv),
                 lindisp=bool(lindisp), perturb=float(perturb), white_bkgd=bool(white_bkgd), retraw=bool(retraw))

@@ -159,12 +159,12 @@ class FusedTrainStep:
             check(lib.nerf_b200_pack_weights(C.byref(self._np_c), api._ptr(self._pk_c), self._pk_c.numel(), st), "pack_weights")
             if self._pk_f is not self._pk_c:
                 check(lib.nerf_b200_pack_weights(C.byref(self._np_f), api._ptr(self._pk_f), self._pk_f.numel(), st), "pack_weights")
-            if self.t_rand is not None:
+            if self.t_rand is not None:                                 # (the reference's draw order)
                 self.t_rand.uniform_()                                  # run_nerf.py:371
-            if self.u_rand is not None:
-                self.u_rand.uniform_()                                  # run_nerf_helpers.py:208
             if self.noise0 is not None:
                 self.noise0.normal_().mul_(self.noise_std)              # run_nerf.py:285
+            if self.u_rand is not None:
+                self.u_rand.uniform_()                                  # run_nerf_helpers.py:208
             if self.noise1 is not None:
                 self.noise1.normal_().mul_(self.noise_std)
             fine = self.Ni > 0
