@@ -171,6 +171,20 @@ class NeRF(nn.Module):
         return self.output_linear(h)
 
     # ---- C-ABI views of the live parameter storages ------------------------------------------
+    def _named_params(self):
+        """list(self.named_parameters()), cached: walking the module tree costs ~50 us per network and every render_rays call needs
+        the list several times.  The cache holds (owner module, attribute, name, parameter) and is valid as long as every owner
+        still holds that very Parameter object (assigning a new Parameter to a layer rebuilds it)."""
+        c = self.__dict__.get("_np_cache")
+        if c is not None and all(m._parameters.get(a) is q for m, a, _, q in c):
+            return c
+        c = []
+        for name, q in self.named_parameters():
+            prefix, _, attr = name.rpartition(".")
+            c.append((self.get_submodule(prefix) if prefix else self, attr, name, q))
+        self.__dict__["_np_cache"] = c
+        return c
+
     def _check_device(self):
         p = self.pts_linears[0].weight
         if not p.is_cuda:
@@ -238,7 +252,7 @@ class NeRF(nn.Module):
         whenever a parameter changed in place (optimizer.step bumps Parameter._version; load_state_dict / .to()
         change data_ptr) or invalidate_pack() was called."""
         dev = self._check_device()
-        key = (getattr(self, "_pack_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (getattr(self, "_pack_epoch", 0),) + tuple((q.data_ptr(), q._version) for _, _, _, q in self._named_params())
         if self._pack is not None and self._pack[0] == key:
             return self._pack[1]
         lib = _lib.load()
@@ -544,17 +558,20 @@ class _RenderRays(torch.autograd.Function):
                 check(lib.nerf_b200_render_fwd(C.byref(gen[0]), *common, _stream(ray_batch)), "render_fwd")
             else:
                 check(lib.nerf_b200_render_rays_fwd(*common, _stream(ray_batch)), "render_rays_fwd")
-        ctx.cfgd, ctx.nets, ctx.train_tc = cfgd, (net_c, net_f), train_tc
-        ctx.save_for_backward(ray_batch, z_c, z_f if fine else torch.empty(0, device=dev),
-                              noise0 if noise0 is not None else torch.empty(0, device=dev),
-                              noise1 if noise1 is not None else torch.empty(0, device=dev), *saved_rec)
+        if ctx is not None:
+            ctx.cfgd, ctx.nets, ctx.train_tc = cfgd, (net_c, net_f), train_tc
+            ctx.save_for_backward(ray_batch, z_c, z_f if fine else torch.empty(0, device=dev),
+                                  noise0 if noise0 is not None else torch.empty(0, device=dev),
+                                  noise1 if noise1 is not None else torch.empty(0, device=dev), *saved_rec)
         if fine:
             rets = (o["rgb"], o["disp"], o["acc"], o["rgb0"], o["disp0"], o["acc0"], z_std,
                     raw_f if retraw else torch.empty(0, device=dev))
-            ctx.mark_non_differentiable(o["disp"], o["acc"], o["disp0"], o["acc0"], z_std, rets[7])
+            if ctx is not None:
+                ctx.mark_non_differentiable(o["disp"], o["acc"], o["disp0"], o["acc0"], z_std, rets[7])
         else:
             rets = (o["rgb0"], o["disp0"], o["acc0"], raw_c if retraw else torch.empty(0, device=dev))
-            ctx.mark_non_differentiable(o["disp0"], o["acc0"], rets[3])
+            if ctx is not None:
+                ctx.mark_non_differentiable(o["disp0"], o["acc0"], rets[3])
         return rets
 
     @staticmethod
@@ -612,9 +629,9 @@ class _RenderRays(torch.autograd.Function):
                     check(lib.nerf_b200_march_bwd(_ptr(ray_batch), _ptr(z), nz, N, S, C.byref(n), _ptr(None), C.byref(cfg),
                                                   _ptr(g_rgb), C.byref(gs), _ptr(ws), ws_bytes, _stream(z)), "march_bwd")
         out = [None] * 8
-        out += [grads_c[k] for k, _ in net_c.named_parameters()]
+        out += [grads_c[k] for _, _, k, _ in net_c._named_params()]
         if net_f is not None:
-            out += [grads_f[k] for k, _ in net_f.named_parameters()]
+            out += [grads_f[k] for _, _, k, _ in net_f._named_params()]
         return tuple(out)
 
 
@@ -661,9 +678,13 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     cfgd = dict(N_samples=int(N_samples), N_importance=int(N_importance), multires=int(mr), multires_views=int(mrv),
                 lindisp=bool(lindisp), perturb=float(perturb), white_bkgd=bool(white_bkgd), retraw=bool(retraw))
     net_f = network_fine if N_importance > 0 else None          # the reference ignores network_fine without fine samples
-    params = list(network_fn.parameters()) + (list(net_f.parameters()) if net_f is not None else [])
+    params = [q for _, _, _, q in network_fn._named_params()] + ([q for _, _, _, q in net_f._named_params()] if net_f is not None else [])
     cfgd["want_grad"] = bool(torch.is_grad_enabled() and any(p.requires_grad for p in params))
-    outs = _RenderRays.apply(ray_batch, cfgd, network_fn, net_f, t_rand, u_rand, noise0, noise1, *params)
+    if cfgd["want_grad"]:
+        outs = _RenderRays.apply(ray_batch, cfgd, network_fn, net_f, t_rand, u_rand, noise0, noise1, *params)
+    else:                                                        # inference: no autograd node to build (saves ~50 us of host time per call)
+        with torch.no_grad():
+            outs = _RenderRays.forward(None, ray_batch, cfgd, network_fn, net_f, t_rand, u_rand, noise0, noise1)
     if N_importance > 0:
         rgb, disp, acc, rgb0, disp0, acc0, z_std, raw = outs
         ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}
