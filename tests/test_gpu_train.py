@@ -90,7 +90,7 @@ def _close_frac(a, b, rtol, atol):
     return float(np.mean(np.isclose(a, b, rtol=rtol, atol=atol)))
 
 
-@pytest.mark.parametrize("N,S", [(100, 64), (37, 192)])
+@pytest.mark.parametrize("N,S", [(100, 64), (37, 192), (50, 40)])
 def test_training_forward_records(G, N, S):
     """EMIT changes nothing in the pass's outputs and leaves records that decode to the fp16 activations / sign masks."""
     import tc_records as R
@@ -176,7 +176,7 @@ def _bwd_tc(G, net, rays11, zd, raw, act, mask, g_rgb):
     return {k: v.cpu().numpy() for k, v in grads.items()}, ws.cpu().numpy()[base:]
 
 
-@pytest.mark.parametrize("N,S,sharpen", [(100, 64, False), (37, 192, False), (64, 64, True)])
+@pytest.mark.parametrize("N,S,sharpen", [(100, 64, False), (37, 192, False), (64, 64, True), (50, 40, False)])
 def test_backward_stages_match_emulation(G, N, S, sharpen):
     """Every stage of the tensor-core backward, given the CUDA forward's own records: dL/draw, the d_hv seed, each dgrad
     step's fp16 tile image, and all 24 gradient tensors -- against the same arithmetic in torch (oracle/tc_emul.py)."""
