@@ -116,6 +116,27 @@ def test_create_nerf_structure(nb, tmp_path):
     assert "ndc" not in tr3 and "lindisp" not in tr3                                          # :250-253
 
 
+def test_cached_parameter_list_follows_the_module(nb):
+    """NeRF._named_params() (the cached list every render_rays call uses) equals named_parameters(), in its order, survives
+    load_state_dict / deepcopy, and is rebuilt when a layer gets a NEW Parameter object."""
+    import copy
+    net = nb.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    def names_ids(n):
+        return [(k, id(q)) for _, _, k, q in n._named_params()]
+    ref = [(k, id(q)) for k, q in net.named_parameters()]
+    assert names_ids(net) == ref and len(ref) == 24
+    assert net._named_params() is net._named_params()                                   # cached
+    net.load_state_dict(copy.deepcopy(net.state_dict()))
+    assert names_ids(net) == ref                                                        # same Parameter objects
+    twin = copy.deepcopy(net)
+    assert names_ids(twin) == [(k, id(q)) for k, q in twin.named_parameters()]
+    assert all(a[1] != b[1] for a, b in zip(names_ids(twin), ref))                      # the copy lists its own parameters
+    net.rgb_linear.bias = torch.nn.Parameter(torch.zeros(3))
+    assert names_ids(net) == [(k, id(q)) for k, q in net.named_parameters()] and names_ids(net) != ref
+    plain = nb.NeRF(D=4, W=64, input_ch=63, input_ch_views=27, output_ch=4, skips=[], use_viewdirs=False)
+    assert [k for _, _, k, _ in plain._named_params()] == [k for k, _ in plain.named_parameters()]
+
+
 def test_keras_weight_import_matches_the_reference(nb):
     """NeRF.load_weights_from_keras vs the reference's own (run_nerf_helpers.py:121-148) on a synthetic Keras-style weight list;
     needs /root/reference (build container), otherwise checks the documented layout only."""
