@@ -183,10 +183,11 @@ int nerf_b200_render_fwd(const NerfRayGen* gen, float* rays, int64_t N, const Ne
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- training mode of the fused pass: besides its outputs (out->raw is required) the pass leaves, per 128-row
- *      tile, a record of fp16 activation images (encodings, post-ReLU h_l, feature, view layer) and the sign
- *      bits of the pre-activations (csrc/train_common.cuh) -- what the reference's autograd saves
- *      (run_nerf_helpers.py:96-119), but written once, in the MMA operand layout, by cp.async.bulk from the
- *      shared-memory tiles the forward produces anyway.  use_viewdirs networks, tensor-core precision. ---- */
+ *      tile, a record of fp16 activation images (encodings, post-ReLU h_l, view layer; 560 KB for D = 8) and the
+ *      sign bits of the pre-activations (csrc/train_common.cuh) -- what the reference's autograd saves
+ *      (run_nerf_helpers.py:96-119), but written once, in the MMA operand layout (two 64-row half images per
+ *      tile image), by cp.async.bulk from the shared-memory tiles the forward produces anyway.
+ *      use_viewdirs networks, tensor-core precision. ---------------------------------------------------------- */
 typedef struct NerfTrainSave {
   void*  act;   size_t act_bytes;    /* activation records: nerf_b200_train_record_bytes(...)            */
   void*  mask;  size_t mask_bytes;   /* ReLU sign-bit records                                            */
