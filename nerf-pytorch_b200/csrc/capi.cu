@@ -733,7 +733,7 @@ struct BwdTcJobs { int n; WgradJob w[WG2_MAX_JOBS]; ReduceJob r[WG2_MAX_JOBS]; i
 BwdTcJobs make_bwd_jobs(const NerfNetParams& n, const NerfNetGrads* g, int sms) {
   BwdTcJobs J;
   memset(&J, 0, sizeof(J));
-  const int D = n.D, W = n.W, IC = n.input_ch, ICV = n.input_ch_views;
+  const int D = n.D, W = n.W, IC = n.input_ch;
   auto add = [&](uint32_t a_off, int Mc, uint32_t b_off, int Nc, float* dst, int ldw, int n_valid, float* db) {
     WgradJob& w = J.w[J.n];
     ReduceJob& r = J.r[J.n];
@@ -1001,7 +1001,7 @@ struct BwdTcPass {
 
   // 5. the view columns of views_linears[0] (after ALL of the pass's weight-gradient launches)
   int heads(cudaStream_t st) {
-    const int sms = ds->sms, D = net->D, ICV = net->input_ch_views;
+    const int ICV = net->input_ch_views;
     encv_kernel<<<cdiv(N * ICV, 256), 256, 0, st>>>(rays + 8, cfg->ray_stride, N, ICV, encv);
     NB_LAUNCH_OK("encv_kernel");
     dim3 vg(ICV + 1, cdiv(N, 64));
