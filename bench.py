@@ -101,7 +101,7 @@ def _cpu_limit():
     return n
 
 
-def cpu_rays_per_s(n_rays, reps, warmup, budget_s=45.0):
+def cpu_rays_per_s(n_rays, reps, warmup, budget_s=45.0, train_step=False):
     """The reference's forward render of `n_rays` rays on the host cores: the unmodified script when baseline/_ref exists
     (kind "reference"), else the restated op chain (kind "port").  The thread count is calibrated ON THE REAL SAMPLE SIZE
     (more threads than the container owns slows torch's CPU ops down badly); time-bounded; returns the MEDIAN."""
@@ -111,9 +111,20 @@ def cpu_rays_per_s(n_rays, reps, warmup, budget_s=45.0):
     sb = synth.ray_batch("lego", n_rays, seed=0)
     rays = torch.from_numpy(sb["rays"])
     mod = import_reference()
+    train_fn = None
     if mod is not None and not torch.cuda.is_available():
         kind = "reference"
-        tr, te, _, _ = reference_setup(mod, torch.device("cpu"), tempfile.mkdtemp())
+        tr, te, _, opt = reference_setup(mod, torch.device("cpu"), tempfile.mkdtemp())
+        target = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(1))
+
+        def train_fn():                                          # the body of train()'s step, run_nerf.py:760-776
+            t0 = time.perf_counter()
+            rgb, disp, acc, extras = mod.render(sb["H"], sb["W"], sb["K"], chunk=32768, rays=rays, verbose=False, retraw=True, **tr)
+            opt.zero_grad()
+            loss = mod.img2mse(rgb, target) + mod.img2mse(extras["rgb0"], target)
+            loss.backward()
+            opt.step()
+            return time.perf_counter() - t0
 
         def run():
             t0 = time.perf_counter()
@@ -149,7 +160,8 @@ def cpu_rays_per_s(n_rays, reps, warmup, budget_s=45.0):
         if ts and time.perf_counter() - t_start > budget_s:
             break
     sec = float(np.median(ts))
-    return n_rays / sec, sec, best_t, kind, len(ts)
+    train_sec = train_fn() if (train_step and train_fn is not None) else None      # ONE training step (forward and train)
+    return n_rays / sec, sec, best_t, kind, len(ts), train_sec
 
 
 def reference_arm(args, rank):
@@ -159,7 +171,7 @@ def reference_arm(args, rank):
         return
     os.environ["CUDA_VISIBLE_DEVICES"] = ""                      # the reference picks cuda when it sees one (run_nerf.py:21)
     steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    rps, sec, threads, kind, done = cpu_rays_per_s(N_RAYS, steps, warmup, budget_s=150.0)
+    rps, sec, threads, kind, done, train_sec = cpu_rays_per_s(N_RAYS, steps, warmup, budget_s=150.0, train_step=True)
     line = {"impl": "reference", "metric": "rays/sec", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": done, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -167,7 +179,9 @@ def reference_arm(args, rank):
             "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": kind,
                              "sample": f"{N_RAYS} rays x (64+128) samples per step (the full batch), median of {done} step(s), "
                                        f"{'the unmodified run_nerf.render from baseline/_ref' if kind == 'reference' else 'torch fp32 CPU ops, the op chain of the reference (oracle/torch_ref.py)'}, "
-                                       f"{threads} torch threads (calibrated on this batch; {os.cpu_count()} logical CPUs visible)"},
+                                       f"{threads} torch threads (calibrated on this batch; {os.cpu_count()} logical CPUs visible)",
+                             "train": None if train_sec is None else {"value": N_RAYS / train_sec, "unit": "rays/s", "ms_per_step": train_sec * 1e3, "steps": 1,
+                                                                       "what": "one step of the reference's loop body on the same threads: render(retraw=True), two img2mse, backward, Adam"}},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

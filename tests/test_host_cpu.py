@@ -172,6 +172,9 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
     assert line["steps"] >= 1 and abs(line["ms_per_step"] * 1e-3 * line["value"] - 4096) < 1.0     # measured, not extrapolated
+    tr = line["cpu_baseline"].get("train")
+    if line["cpu_baseline"]["kind"] == "reference":                                                 # forward AND train beside the GPU numbers
+        assert tr is not None and tr["value"] > 0 and abs(tr["ms_per_step"] * 1e-3 * tr["value"] - 4096) < 1.0
 
 
 def _cuobjdump(*args):
