@@ -171,7 +171,9 @@ def reference_arm(args, rank):
         return
     os.environ["CUDA_VISIBLE_DEVICES"] = ""                      # the reference picks cuda when it sees one (run_nerf.py:21)
     steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    rps, sec, threads, kind, done, train_sec = cpu_rays_per_s(N_RAYS, steps, warmup, budget_s=150.0, train_step=True)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):                # the reference prints ('Found ckpts', 'Not ndc!'): stdout carries ONE JSON line
+        rps, sec, threads, kind, done, train_sec = cpu_rays_per_s(N_RAYS, steps, warmup, budget_s=150.0, train_step=True)
     line = {"impl": "reference", "metric": "rays/sec", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": done, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
