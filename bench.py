@@ -495,6 +495,8 @@ def main():
                  "roofline": {"bound": "tensor", "what": "whole train step: algorithmic 893 190 144 FLOP/ray (fwd + dgrad + wgrad, SURVEY 8d) over the step's device time",
                               "achieved": ach_t, "peak": peak, "unit": "TFLOP/s", "frac": ach_t / peak if peak else None, "peak_source": peak_src,
                               "kernel_ms_per_step": {"forward_passes_training_mode": kinds[0], "dgrad_chains": kinds[1], "wgrad": kinds[2]},
+                              "kernel_ms_note": "split taken in a separate EAGER pass with CUDA events around each launch (3 steps, straight after the timed loops): "
+                                                "the kernels run a few % slower there than inside the graph replay that `ms_per_step` times; use it for the shares",
                               "hbm": {"what": "bytes the step's design moves through HBM (DESIGN.md 9): per 128-row tile 1 230 848 B of records written (activations, "
                                               "masks, gradients) and 1 411 072 B read back (wgrad 1 310 720, dgrad 65 536, rgb head 34 816)",
                                       "bytes_per_step": TRAIN_BYTES_PER_TILE * N_RAYS * 256 // 128,
