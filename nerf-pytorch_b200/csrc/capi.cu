@@ -69,7 +69,16 @@ static DeviceState* device_state() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     st[dev].sms = n > 0 ? n : 148;
     st[dev].optin_fwd = st[dev].optin_bwd = false;
+    // side stream + events of the two-pass backward: created with the device state (the first library call on a device), not
+    // lazily inside a call that may be running under stream capture
     st[dev].side = nullptr;
+    if (cudaStreamCreateWithFlags(&st[dev].side, cudaStreamNonBlocking) == cudaSuccess) {
+      for (int i = 0; i < 10; ++i)
+        if (cudaEventCreateWithFlags(&st[dev].ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(st[dev].side); st[dev].side = nullptr; break; }
+    } else {
+      st[dev].side = nullptr;
+    }
+    cudaGetLastError();
     init[dev] = true;
   }
   return &st[dev];
@@ -1100,9 +1109,10 @@ int nerf_b200_render_rays_bwd_tc(const float* rays, int64_t N, const NerfRenderC
     NB_TRY(f.prologue(st)); NB_TRY(f.dgrad(st, dc, 0, f.plan.grid)); NB_TRY(f.wgrad(st, wc, 0, f.plan.grid)); NB_TRY(f.heads(st));
     return 0;
   }
-  if (!ds->side) {
-    NB_CUDA(cudaStreamCreateWithFlags(&ds->side, cudaStreamNonBlocking));
-    for (int i = 0; i < 10; ++i) NB_CUDA(cudaEventCreateWithFlags(&ds->ev[i], cudaEventDisableTiming));
+  if (!ds->side) {                                   // (creation failed at start-up: one stream, one pass after the other)
+    NB_TRY(c.prologue(st)); NB_TRY(c.dgrad(st, c.plan.grid, 0, c.plan.grid)); NB_TRY(c.wgrad(st, sms, 0, c.plan.grid)); NB_TRY(c.heads(st));
+    NB_TRY(f.prologue(st)); NB_TRY(f.dgrad(st, f.plan.grid, 0, f.plan.grid)); NB_TRY(f.wgrad(st, sms, 0, f.plan.grid)); NB_TRY(f.heads(st));
+    return 0;
   }
   cudaStream_t sd = ds->side;
   if (w < 0) {
